@@ -1,0 +1,101 @@
+"""ctypes binding of libgmpnp.so (the C-ABI declared in include/gmpnp.h).
+
+There is no CPU fallback: if the CUDA library is missing the import of any solver
+raises, loudly.  Build it with ``python -c "import __graft_entry__ as g; g.build()"``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgmpnp.so")
+
+NPAR = 64
+
+
+class NewtonOpts(C.Structure):
+    """Mirror of ``gmpnp_newton_opts`` (dolfin NewtonSolver parameters, 1D:357-364, 3D:789-798)."""
+    _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("relax", C.c_double), ("xtol", C.c_double),
+                ("maxit", C.c_int), ("criterion", C.c_int), ("pivot", C.c_int), ("lin_maxit", C.c_int),
+                ("lin_restart", C.c_int), ("lin_rtol", C.c_double)]
+
+    @classmethod
+    def reference_1d(cls):
+        return cls(1e-4, 1e-4, 1.0, 1e-12, 50, 0, 1, 0, 0, 0.0)
+
+    @classmethod
+    def reference_3d(cls):
+        return cls(1e-4, 1e-4, 0.9, 1e-12, 50, 0, 1, 2000, 100, 1e-10)
+
+    @classmethod
+    def steady(cls, xtol=1e-12, maxit=50, relax=1.0):
+        return cls(1e-4, 1e-4, relax, xtol, maxit, 1, 1, 2000, 100, 1e-12)
+
+
+STATUS_NAMES = {0: "converged", 1: "maxit", 2: "not_finite", 3: "linear_failed"}
+
+_vp, _i, _d = C.c_void_p, C.c_int, C.c_double
+_pd, _pi = C.POINTER(C.c_double), C.POINTER(C.c_int)
+_po = C.POINTER(NewtonOpts)
+
+# name -> (restype, argtypes); every symbol include/gmpnp.h declares
+SIGNATURES = {
+    "gmpnp_strerror": (C.c_char_p, [_i]),
+    "gmpnp_last_cuda_error": (C.c_char_p, [_vp]),
+    "gmpnp_version": (_i, []),
+    "gmpnp_destroy": (None, [_vp]),
+    "gmpnp_launch_count": (C.c_longlong, [_vp]),
+    "gmpnp_create_1d": (_i, [C.POINTER(_vp), _i, _pd, _i, _i, _i]),
+    "gmpnp_set_params": (_i, [_vp, _pd, _i]),
+    "gmpnp_assemble_1d": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "gmpnp_newton_1d": (_i, [_vp, _vp, _vp, _po, _vp, _vp, _vp, _vp, _vp]),
+    "gmpnp_march_1d": (_i, [_vp, _vp, _vp, _i, _po, _vp, _vp, _vp, _vp, _vp]),
+    "gmpnp_steady_continuation_1d": (_i, [_vp, _vp, _vp, _i, _po, _vp, _vp, _vp, _vp]),
+    "gmpnp_field_1d": (_i, [_vp, _vp, _vp, _vp]),
+    "gmpnp_create_3d": (_i, [C.POINTER(_vp), _i, _pd, _i, _pi, _i, _pi, _i, _i, _i]),
+    "gmpnp_set_dirichlet_3d": (_i, [_vp, _pd, _i]),
+    "gmpnp_pattern_3d": (_i, [_vp, _pi, _pi, _pi]),
+    "gmpnp_assemble_3d": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "gmpnp_spmv_3d": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "gmpnp_newton_3d": (_i, [_vp, _vp, _vp, _po, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gmpnp_median_3d": (_i, [_vp, _vp, _i, _vp, _vp]),
+}
+
+_lib = None
+
+
+class GmpnpError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libgmpnp.so and declare the signatures.  Raises if the library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GmpnpError(
+            f"{LIB_PATH} not found: the CUDA library is not built (run __graft_entry__.build()). "
+            "There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, handle=None):
+    if rc != 0:
+        lib = load()
+        msg = lib.gmpnp_strerror(rc).decode()
+        if handle is not None and rc == -2:
+            msg += ": " + lib.gmpnp_last_cuda_error(handle).decode()
+        raise GmpnpError(f"libgmpnp error {rc}: {msg}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())

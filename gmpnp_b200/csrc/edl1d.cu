@@ -1,0 +1,751 @@
+// 1D planar EDL: fused P1 assembly + block-tridiagonal (7x7) Thomas elimination + Newton,
+// one 8-lane group per problem, whole Newton / time-march / continuation loop device-resident.
+//
+// Replaces the FEniCS work behind `solve(F + J_OH*v_OH*ds + J_H*v_H*ds == 0, u, bcs)`
+// (1D/MPNP_CO2ER_EDL.py:737-742): FFC element kernels for the forms 1D:381-595, dolfin's
+// SystemAssembler scatter, DirichletBC.apply (1D:350-355), the UMFPACK LU and dolfin's
+// NewtonSolver loop.
+//
+// Data layout (HBM):
+//   u, u_n          [problem][node][7]            node-major interleaved (56 B per node)
+//   workspace       [problem][node][7][8]         row j = (C'_k[j][0..6], d'_k[j]): the
+//                                                 eliminated super-diagonal block and rhs
+// Lane mapping inside a group: lane c<7 owns COLUMN c of every 7x7 block (trial component c),
+// lane 7 owns the right-hand side / residual.  The Jacobian never exists in HBM: row k is
+// assembled from cells k-1,k just in time, eliminated, and only (C'_k, d'_k) is stored.
+#include "common.cuh"
+
+namespace edl1d {
+
+constexpr int NS = 6;
+constexpr int NC = 7;
+constexpr int SM_P = 0;       // params            [64]
+constexpr int SM_U = 64;      // staged nodal vals [2][8]  (slot 7 holds the constant 1.0)
+constexpr int SM_A = 80;      // sub-diagonal block, column-major [7][8]
+constexpr int SM_M = 136;     // multipliers + pivot row [8]
+constexpr int SM_GROUP = 144; // doubles per group
+constexpr int GROUPS_PER_BLOCK = 16;
+constexpr int THREADS = GROUPS_PER_BLOCK * 8;
+
+// 3-point and 2-point Gauss-Legendre on [0,1] (FFC: degree 4 -> 3 points for J, degree 3 ->
+// 2 points for F)
+__device__ __constant__ double GX3[3] = {0.11270166537925831, 0.5, 0.88729833462074169};
+__device__ __constant__ double GW3[3] = {0.27777777777777779, 0.44444444444444442, 0.27777777777777779};
+__device__ __constant__ double GX2[2] = {0.21132486540518713, 0.78867513459481287};
+__device__ __constant__ double GW2[2] = {0.5, 0.5};
+
+struct LaneConst {
+    double coef[5];   // elementary-rate derivative coefficients of this lane's column (w,a,b,a2,b2)
+    int sel[5];       // which staged nodal value multiplies it (7 = constant 1)
+};
+
+__device__ __forceinline__ void lane_consts(const double* P, int c, LaneConst& L) {
+#pragma unroll
+    for (int r = 0; r < 5; ++r) { L.coef[r] = 0.0; L.sel[r] = 7; }
+    const double kW = P[GMPNP_P_KW], kA = P[GMPNP_P_KA], kB = P[GMPNP_P_KB];
+    const double kA2 = P[GMPNP_P_KA2], kB2 = P[GMPNP_P_KB2];
+    if (c == 0) { L.coef[0] = kW; L.sel[0] = 1; }
+    else if (c == 1) { L.coef[0] = kW; L.sel[0] = 0; L.coef[1] = kA; L.sel[1] = 2; L.coef[2] = kB; L.sel[2] = 4; }
+    else if (c == 2) { L.coef[1] = kA; L.sel[1] = 1; L.coef[4] = kB2; L.sel[4] = 7; }
+    else if (c == 3) { L.coef[3] = kA2; L.sel[3] = 7; }
+    else if (c == 4) { L.coef[2] = kB; L.sel[2] = 1; }
+}
+
+// Element blocks of one cell for this lane.
+//   lane c<7 : cab[i] = dF_e[a,i]/dU[b,c]   (column c of block (a,b))
+//   lane 7   : c00 = F_e[0,:], c11 = F_e[1,:]
+struct CellCols { double c00[NC], c01[NC], c10[NC], c11[NC]; };
+
+__device__ __forceinline__ void cell_columns(const double* __restrict__ P, const double* __restrict__ sU,
+                                             const LaneConst& L, int c, double h,
+                                             const double (&U0)[NC], const double (&U1)[NC],
+                                             const double (&N0)[NC], const double (&N1)[NC],
+                                             bool want_jac, CellCols& o) {
+    const double ih = 1.0 / h;
+    double g[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) g[i] = (U1[i] - U0[i]) * ih;
+    double G = 0.0;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) G += P[GMPNP_P_NU + i] * g[i];
+    const double gp = g[NS];
+    const double kappa = P[GMPNP_P_KAPPA];
+    // grad phi_0 = -ih, grad phi_1 = +ih
+    const double Ga0 = -G * ih, Ga1 = G * ih;
+    const double gpa0 = -gp * ih, gpa1 = gp * ih;
+
+    if (c < NS) {
+        if (!want_jac) return;
+        // ---- species column j = c --------------------------------------------------
+        double mD0 = 0.0, mD1 = 0.0;
+        double iUD[NS], m20[NS], m21[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) { iUD[i] = 0.0; m20[i] = 0.0; m21[i] = 0.0; }
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const double l1 = GX3[q], l0 = 1.0 - l1, W = GW3[q] * h;
+            double uq[NS];
+            double S = 0.0;
+#pragma unroll
+            for (int i = 0; i < NS; ++i) { uq[i] = l0 * U0[i] + l1 * U1[i]; S += P[GMPNP_P_NU + i] * uq[i]; }
+            const double D = 1.0 / (1.0 - S);
+            const double WD = W * D, WD2 = WD * D;
+            mD0 += WD * l0; mD1 += WD * l1;
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+                const double t = uq[i];
+                iUD[i] += WD * t; m20[i] += WD2 * l0 * t; m21[i] += WD2 * l1 * t;
+            }
+        }
+        const double nuj = P[GMPNP_P_NU + c];
+        const double zj = P[GMPNP_P_Z + c];
+        const double ih2 = ih * ih;
+        const double Md = h * (1.0 / 3.0), Mo = h * (1.0 / 6.0), mb = 0.5 * h;
+        // reaction moments  E_r[ab] = coef_r * int phi_a phi_b u_sel
+        double E00[5], E01[5], E11[5];
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+            const double v0 = sU[L.sel[r]], v1 = sU[8 + L.sel[r]];
+            const double ch = L.coef[r] * h;
+            E00[r] = ch * (0.25 * v0 + (1.0 / 12.0) * v1);
+            E01[r] = ch * ((1.0 / 12.0) * (v0 + v1));
+            E11[r] = ch * ((1.0 / 12.0) * v0 + 0.25 * v1);
+        }
+        const double s0 = P[GMPNP_P_S], s1 = P[GMPNP_P_S + 1], s2 = P[GMPNP_P_S + 2];
+        const double s3 = P[GMPNP_P_S + 3], s4 = P[GMPNP_P_S + 4];
+        auto rx = [&](const double (&E)[5], double (&R)[5]) {
+            R[0] = s0 * E[0];
+            R[1] = s1 * (E[0] + E[1] + E[2] - E[3] - E[4]);
+            R[2] = s2 * (E[1] + E[4] - E[3] - E[2]);
+            R[3] = s3 * (E[3] - E[1]);
+            R[4] = s4 * (E[2] - E[4]);
+        };
+        double R00[5], R01[5], R11[5];
+        rx(E00, R00); rx(E01, R01); rx(E11, R11);
+        // diagonal (i == j) extras per block
+        const double d00 = kappa * Md + ih + zj * gpa0 * mb + Ga0 * mD0;
+        const double d01 = kappa * Mo - ih + zj * gpa0 * mb + Ga0 * mD1;
+        const double d10 = kappa * Mo - ih + zj * gpa1 * mb + Ga1 * mD0;
+        const double d11 = kappa * Md + ih + zj * gpa1 * mb + Ga1 * mD1;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            const double k = ih2 * iUD[i];
+            double v00 = nuj * (Ga0 * m20[i] + k);
+            double v01 = nuj * (Ga0 * m21[i] - k);
+            double v10 = nuj * (Ga1 * m20[i] - k);
+            double v11 = nuj * (Ga1 * m21[i] + k);
+            if (i < 5) { v00 += R00[i]; v01 += R01[i]; v10 += R01[i]; v11 += R11[i]; }
+            const bool dg = (i == c);
+            o.c00[i] = v00 + (dg ? d00 : 0.0);
+            o.c01[i] = v01 + (dg ? d01 : 0.0);
+            o.c10[i] = v10 + (dg ? d10 : 0.0);
+            o.c11[i] = v11 + (dg ? d11 : 0.0);
+        }
+        // Poisson row:  -eps'_j (gp.grad a) m_b + q z_j c0_j M_ab
+        double depsj = 0.0;
+        if (c == 0) depsj = (6.0 - P[GMPNP_P_EPSW]) / 55.0 * P[GMPNP_P_EPSH];
+        if (c == NS - 1) depsj = (6.0 - P[GMPNP_P_EPSW]) / 55.0 * P[GMPNP_P_EPSC];
+        const double qz = P[GMPNP_P_Q] * P[GMPNP_P_ZC0 + c];
+        o.c00[NS] = -depsj * gpa0 * mb + qz * Md;
+        o.c01[NS] = -depsj * gpa0 * mb + qz * Mo;
+        o.c10[NS] = -depsj * gpa1 * mb + qz * Mo;
+        o.c11[NS] = -depsj * gpa1 * mb + qz * Md;
+    } else if (c == NS) {
+        if (!want_jac) return;
+        // ---- potential column ------------------------------------------------------
+        const double ih2 = ih * ih;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            const double iU = 0.5 * h * (U0[i] + U1[i]);
+            const double v = P[GMPNP_P_Z + i] * ih2 * iU;
+            o.c00[i] = v; o.c11[i] = v; o.c01[i] = -v; o.c10[i] = -v;
+        }
+        const double wm = P[GMPNP_P_EPSC] * 0.5 * (U0[NS - 1] + U1[NS - 1]) + P[GMPNP_P_EPSH] * 0.5 * (U0[0] + U1[0]);
+        const double epsm = P[GMPNP_P_EPSW] * ((55.0 - wm) / 55.0) + 6.0 * (wm / 55.0);
+        const double v = -ih2 * h * epsm;
+        o.c00[NS] = v; o.c11[NS] = v; o.c01[NS] = -v; o.c10[NS] = -v;
+    } else {
+        // ---- residual (lane 7), 2-point Gauss ----------------------------------------
+        double sUD[NS], R0[5], R1[5];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) sUD[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) { R0[i] = 0.0; R1[i] = 0.0; }
+        const double kW = P[GMPNP_P_KW], kA = P[GMPNP_P_KA], kB = P[GMPNP_P_KB];
+        const double kA2 = P[GMPNP_P_KA2], kB2 = P[GMPNP_P_KB2], kw1 = P[GMPNP_P_KW1];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const double l1 = GX2[q], l0 = 1.0 - l1, W = GW2[q] * h;
+            double uq[NS];
+            double S = 0.0;
+#pragma unroll
+            for (int i = 0; i < NS; ++i) { uq[i] = l0 * U0[i] + l1 * U1[i]; S += P[GMPNP_P_NU + i] * uq[i]; }
+            const double WD = W / (1.0 - S);
+#pragma unroll
+            for (int i = 0; i < NS; ++i) sUD[i] += WD * uq[i];
+            const double w = kW * uq[0] * uq[1], a = kA * uq[1] * uq[2], b = kB * uq[4] * uq[1];
+            const double a2 = kA2 * uq[3], b2 = kB2 * uq[2];
+            double mr[5];
+            mr[0] = P[GMPNP_P_S] * (w - kw1);
+            mr[1] = P[GMPNP_P_S + 1] * (w + a + b - kw1 - a2 - b2);
+            mr[2] = P[GMPNP_P_S + 2] * (a + b2 - a2 - b);
+            mr[3] = P[GMPNP_P_S + 3] * (a2 - a);
+            mr[4] = P[GMPNP_P_S + 4] * (b - b2);
+#pragma unroll
+            for (int i = 0; i < 5; ++i) { R0[i] += W * l0 * mr[i]; R1[i] += W * l1 * mr[i]; }
+        }
+        double rho0 = 0.0, rho1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            const double d0 = U0[i] - N0[i], d1 = U1[i] - N1[i];
+            const double sUi = 0.5 * h * (U0[i] + U1[i]);
+            const double zi = P[GMPNP_P_Z + i];
+            double f0 = kappa * h * ((1.0 / 3.0) * d0 + (1.0 / 6.0) * d1) - g[i] + zi * gpa0 * sUi + Ga0 * sUD[i];
+            double f1 = kappa * h * ((1.0 / 6.0) * d0 + (1.0 / 3.0) * d1) + g[i] + zi * gpa1 * sUi + Ga1 * sUD[i];
+            if (i < 5) { f0 += R0[i]; f1 += R1[i]; }
+            o.c00[i] = f0; o.c11[i] = f1;
+            rho0 += P[GMPNP_P_ZC0 + i] * U0[i];
+            rho1 += P[GMPNP_P_ZC0 + i] * U1[i];
+        }
+        const double wm = P[GMPNP_P_EPSC] * 0.5 * (U0[NS - 1] + U1[NS - 1]) + P[GMPNP_P_EPSH] * 0.5 * (U0[0] + U1[0]);
+        const double epsm = P[GMPNP_P_EPSW] * ((55.0 - wm) / 55.0) + 6.0 * (wm / 55.0);
+        const double qh = P[GMPNP_P_Q] * h;
+        o.c00[NS] = -gpa0 * h * epsm + qh * ((1.0 / 3.0) * rho0 + (1.0 / 6.0) * rho1);
+        o.c11[NS] = -gpa1 * h * epsm + qh * ((1.0 / 6.0) * rho0 + (1.0 / 3.0) * rho1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// group helpers
+// ---------------------------------------------------------------------------------------
+struct Group {
+    int c;            // lane in group (column id)
+    unsigned mask;    // participation mask of the 8 lanes
+    int base;         // first lane of the group inside the warp
+    double* sm;       // per-group shared memory
+};
+
+// stage the 7 nodal values of `node` (lane c<7 loads component c) into sU[slot][0..6] and
+// give every lane a register copy
+__device__ __forceinline__ void load_node(const Group& g, const double* __restrict__ up, long node,
+                                          int slot, double (&U)[NC]) {
+    double* sU = g.sm + SM_U + slot * 8;
+    if (g.c < NC) sU[g.c] = up[node * NC + g.c];
+    else sU[7] = 1.0;
+    __syncwarp(g.mask);
+#pragma unroll
+    for (int i = 0; i < NC; ++i) U[i] = sU[i];
+    __syncwarp(g.mask);
+}
+
+// One forward sweep over the block rows: assemble row k just in time, eliminate, store
+// (C'_k, d'_k).  Returns ||b||_2^2 (valid in every lane).  `factor` = false does the
+// residual only (no Jacobian columns, no elimination, no stores).
+template <bool PIVOT>
+__device__ double forward_sweep(const Group& g, const LaneConst& L, const double* __restrict__ x, int n,
+                                const double* __restrict__ up, const double* __restrict__ unp,
+                                double* __restrict__ ws, bool factor, int& singular) {
+    const double* P = g.sm + SM_P;
+    double* sA = g.sm + SM_A;
+    double* sM = g.sm + SM_M;
+    int* sI = reinterpret_cast<int*>(sM + 7);     // pivot row + singular flag
+    const int c = g.c;
+    const bool use_un = (P[GMPNP_P_KAPPA] != 0.0);   // steady equations never read u_n
+    double U0[NC], U1[NC], N0[NC], N1[NC];
+    double X[NC];                 // previous row's C' column (lanes<7) / d' (lane 7), permuted row order
+    int pinv[NC];                 // register slot i holds solution row pinv[i]
+    double P10[NC], P11[NC];      // previous cell: block (1,0) and (1,1) columns; lane 7: F1 in P11
+#pragma unroll
+    for (int i = 0; i < NC; ++i) { X[i] = 0.0; pinv[i] = i; P10[i] = 0.0; P11[i] = 0.0; N0[i] = 0.0; N1[i] = 0.0; }
+    load_node(g, up, 0, 1, U1);
+    if (c == 7 && use_un) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) N1[i] = unp[i];
+    }
+    double x1 = x[0];
+    double rsq = 0.0;
+    for (int k = 0; k < n; ++k) {
+        // shift node k+1 -> node k
+#pragma unroll
+        for (int i = 0; i < NC; ++i) { U0[i] = U1[i]; N0[i] = N1[i]; }
+        const double x0 = x1;
+        CellCols cc;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) { cc.c00[i] = 0.0; cc.c01[i] = 0.0; cc.c10[i] = 0.0; cc.c11[i] = 0.0; }
+        if (k + 1 < n) {
+            // stage node k in slot 0 (copy of slot 1) and node k+1 in slot 1
+            if (c < NC) g.sm[SM_U + c] = U0[c]; else g.sm[SM_U + 7] = 1.0;
+            load_node(g, up, k + 1, 1, U1);
+            if (c == 7 && use_un) {
+#pragma unroll
+                for (int i = 0; i < NC; ++i) N1[i] = unp[(long)(k + 1) * NC + i];
+            }
+            x1 = x[k + 1];
+            cell_columns(P, g.sm + SM_U, L, c, x1 - x0, U0, U1, N0, N1, factor, cc);
+        }
+        // ---- row k: A = P10, B = P11 + c00, C = c01, d = F1prev + F0 ------------------
+        double B[NC], Y[NC];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) { B[i] = P11[i] + cc.c00[i]; Y[i] = cc.c01[i]; }
+        if (c == 7) {
+#pragma unroll
+            for (int i = 0; i < NC; ++i) Y[i] = B[i];       // lane 7: rhs lives in Y
+            // point fluxes `J_i v_i ds` at both end points (1D:553, 738)
+            if (k == 0 || k == n - 1) {
+#pragma unroll
+                for (int i = 0; i < NS; ++i) Y[i] += P[GMPNP_P_JFLUX + i];
+            }
+        }
+        // Dirichlet rows (1D:350-355): x=1 all components = (1,..,1,0); x=0 potential = V
+        const bool last = (k == n - 1);
+        if (last) {
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                if (c < NC) { B[i] = (i == c) ? 1.0 : 0.0; Y[i] = 0.0; P10[i] = 0.0; }
+                else Y[i] = U0[i] - ((i < NS) ? 1.0 : 0.0);
+            }
+        }
+        if (k == 0) {
+            if (c < NC) { B[NS] = (c == NS) ? 1.0 : 0.0; Y[NS] = 0.0; }
+            else Y[NS] = U0[NS] - P[GMPNP_P_V];
+        }
+        if (c == 7) {
+#pragma unroll
+            for (int i = 0; i < NC; ++i) rsq += Y[i] * Y[i];
+        }
+        if (factor) {
+            // ---- B' = B - A C'_{k-1},  d' = d - A d'_{k-1} --------------------------------
+            if (k > 0) {
+                if (c < NC) {
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) sA[c * 8 + i] = P10[i];
+                }
+                __syncwarp(g.mask);
+                double t[NC];
+#pragma unroll
+                for (int i = 0; i < NC; ++i) t[i] = 0.0;
+#pragma unroll
+                for (int s = 0; s < NC; ++s) {           // register slot s holds solution row pinv[s]
+                    const double* col = sA + pinv[s] * 8;
+                    const double xs = X[s];
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) t[i] += col[i] * xs;
+                }
+                __syncwarp(g.mask);
+                if (c < NC) {
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) B[i] -= t[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) Y[i] -= t[i];
+                }
+            }
+            // ---- Gauss-Jordan on [B' | C | d'] with implicit row pivoting -----------------
+            unsigned used = 0u;
+#pragma unroll
+            for (int j = 0; j < NC; ++j) {
+                int p = j;
+                if (PIVOT) {
+                    double best = -1.0;
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) {
+                        const double a = fabs(B[i]);
+                        const bool ok = !((used >> i) & 1u) && (a > best);
+                        if (ok) { best = a; p = i; }
+                    }
+                }
+                double piv = B[0];
+#pragma unroll
+                for (int i = 1; i < NC; ++i) if (i == p) piv = B[i];
+                const double inv = 1.0 / piv;
+                if (c == j) {
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) sM[i] = (i == p) ? inv : B[i] * inv;
+                    sI[0] = p;
+                    sI[1] = (!(fabs(piv) > 0.0) || !isfinite(inv)) ? 1 : 0;
+                }
+                __syncwarp(g.mask);
+                double m[NC];
+#pragma unroll
+                for (int i = 0; i < NC; ++i) m[i] = sM[i];
+                p = sI[0];
+                singular |= sI[1];
+                __syncwarp(g.mask);
+                used |= (1u << p);
+                double vb = B[0], vy = Y[0];
+#pragma unroll
+                for (int i = 1; i < NC; ++i) if (i == p) { vb = B[i]; vy = Y[i]; }
+#pragma unroll
+                for (int i = 0; i < NC; ++i) {
+                    const bool ip = (i == p);
+                    B[i] = ip ? vb * m[i] : B[i] - m[i] * vb;
+                    Y[i] = ip ? vy * m[i] : Y[i] - m[i] * vy;
+                }
+                // solution row j lives in register slot p
+#pragma unroll
+                for (int i = 0; i < NC; ++i) if (i == p) pinv[i] = j;
+            }
+            // ---- store (C'_k | d'_k), natural row order -----------------------------------
+            double* w = ws + (long)k * 56;
+#pragma unroll
+            for (int i = 0; i < NC; ++i) w[pinv[i] * 8 + c] = Y[i];
+#pragma unroll
+            for (int i = 0; i < NC; ++i) X[i] = Y[i];
+        }
+#pragma unroll
+        for (int i = 0; i < NC; ++i) { P10[i] = cc.c10[i]; P11[i] = cc.c11[i]; }
+    }
+    // broadcast the residual norm from lane 7
+    rsq = __shfl_sync(g.mask, rsq, g.base + 7);
+    return rsq;
+}
+
+// Back substitution x_k = d'_k - C'_k x_{k+1} and update u <- u - relax * x.
+// Returns max|dx| and max|u_new| (valid in every lane).
+__device__ void backward_sweep(const Group& g, int n, double* __restrict__ up, const double* __restrict__ ws,
+                               double relax, double& dxmax, double& umax) {
+    const int c = g.c;
+    double xn[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) xn[i] = 0.0;
+    double mdx = 0.0, mu = 0.0;
+    const int row = (c < NC) ? c : 0;
+    double r[8];
+    {
+        const double2* src = reinterpret_cast<const double2*>(ws + (long)(n - 1) * 56 + row * 8);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) { double2 t = src[v]; r[2 * v] = t.x; r[2 * v + 1] = t.y; }
+    }
+    for (int k = n - 1; k >= 0; --k) {
+        double rn[8];
+        if (k > 0) {       // prefetch next row while this one is reduced
+            const double2* src = reinterpret_cast<const double2*>(ws + (long)(k - 1) * 56 + row * 8);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) { double2 t = src[v]; rn[2 * v] = t.x; rn[2 * v + 1] = t.y; }
+        }
+        double xi = r[7];
+#pragma unroll
+        for (int j = 0; j < NC; ++j) xi -= r[j] * xn[j];
+        if (c < NC) {
+            const long a = (long)k * NC + c;
+            const double un = up[a] - relax * xi;
+            up[a] = un;
+            mdx = fmax(mdx, fabs(xi));
+            mu = fmax(mu, fabs(un));
+        }
+#pragma unroll
+        for (int j = 0; j < NC; ++j) xn[j] = __shfl_sync(g.mask, xi, g.base + j);
+        if (k > 0) {
+#pragma unroll
+            for (int v = 0; v < 8; ++v) r[v] = rn[v];
+        }
+    }
+#pragma unroll
+    for (int o = 4; o >= 1; o >>= 1) {
+        mdx = fmax(mdx, __shfl_xor_sync(g.mask, mdx, o));
+        mu = fmax(mu, __shfl_xor_sync(g.mask, mu, o));
+    }
+    dxmax = mdx; umax = mu;
+}
+
+struct NewtonOut { int iters; double r0, r; int status; };
+
+// dolfin NewtonSolver semantics for one problem handled by one group.
+template <bool PIVOT>
+__device__ NewtonOut newton_solve(const Group& g, const LaneConst& L, const double* x, int n, double* up,
+                                  const double* unp, double* ws, const gmpnp_newton_opts& o) {
+    NewtonOut out;
+    int singular = 0;
+    double rsq = forward_sweep<PIVOT>(g, L, x, n, up, unp, ws, true, singular);
+    double r = sqrt(rsq);
+    out.r0 = r;
+    int k = 0;
+    bool conv = (o.criterion == 0) ? (r < o.atol) : false;
+    bool bad = !isfinite(r) || singular;
+    while (!conv && !bad && k < o.maxit) {
+        double dxmax, umax;
+        backward_sweep(g, n, up, ws, o.relax, dxmax, umax);
+        ++k;
+        if (o.criterion == 1) {
+            conv = dxmax <= o.xtol * fmax(1.0, umax);
+            if (!isfinite(dxmax)) bad = true;
+            if (conv || bad) break;
+        }
+        rsq = forward_sweep<PIVOT>(g, L, x, n, up, unp, ws, true, singular);
+        r = sqrt(rsq);
+        if (!isfinite(r) || singular) bad = true;
+        if (o.criterion == 0) conv = (r / out.r0 < o.rtol) || (r < o.atol);
+    }
+    out.iters = k;
+    out.r = r;
+    out.status = bad ? GMPNP_NOT_FINITE : (conv ? GMPNP_CONVERGED : GMPNP_MAXIT);
+    return out;
+}
+
+__device__ __forceinline__ bool group_setup(Group& g, int batch, int& prob, double* smem) {
+    const int lane = threadIdx.x & 31;
+    g.c = lane & 7;
+    g.base = lane & ~7;
+    g.mask = 0xFFu << g.base;
+    const int gid = threadIdx.x >> 3;
+    g.sm = smem + gid * SM_GROUP;
+    prob = blockIdx.x * GROUPS_PER_BLOCK + gid;
+    return prob < batch;
+}
+
+__device__ __forceinline__ void load_params(const Group& g, const double* __restrict__ params, int prob) {
+    for (int i = g.c; i < GMPNP_NPAR; i += 8) g.sm[SM_P + i] = params[(long)prob * GMPNP_NPAR + i];
+    __syncwarp(g.mask);
+}
+
+// mode 0: single Newton solve (gmpnp_newton_1d)
+// mode 1: pseudo-time march  (gmpnp_march_1d): n_stage steps, H_OHP controller, u_n <- u
+// mode 2: steady continuation (gmpnp_steady_continuation_1d): kappa = 0, V from Vpath
+template <bool PIVOT>
+__global__ void __launch_bounds__(THREADS)
+newton1d_kernel(int mode, int batch, int n, const double* __restrict__ x, const double* __restrict__ params,
+                double* __restrict__ u, double* __restrict__ un_rw, const double* __restrict__ un_ro,
+                double* __restrict__ wsall, gmpnp_newton_opts opts, int n_stage,
+                const double* __restrict__ Vpath, double* __restrict__ hist, int* __restrict__ iters,
+                double* __restrict__ r0out, double* __restrict__ rout, double* __restrict__ hfrac_out,
+                int* __restrict__ stage_out, int* __restrict__ status) {
+    extern __shared__ double smem[];
+    Group g; int prob;
+    if (!group_setup(g, batch, prob, smem)) return;
+    load_params(g, params, prob);
+    double* P = g.sm + SM_P;
+    double* up = u + (long)prob * n * NC;
+    double* ws = wsall + (long)prob * n * 56;
+    LaneConst L;
+    lane_consts(P, g.c, L);
+    if (mode == 0) {
+        const double* unp = un_ro + (long)prob * n * NC;
+        NewtonOut o = newton_solve<PIVOT>(g, L, x, n, up, unp, ws, opts);
+        if (g.c == 0) {
+            if (iters) iters[prob] = o.iters;
+            if (r0out) r0out[prob] = o.r0;
+            if (rout) rout[prob] = o.r;
+            if (status) status[prob] = o.status;
+        }
+        return;
+    }
+    if (mode == 1) {
+        double* unp = un_rw + (long)prob * n * NC;
+        double frac = P[GMPNP_P_HFRAC];
+        const double hohp = P[GMPNP_P_HOHP];
+        int st = GMPNP_CONVERGED, done = 0;
+        for (int s = 0; s < n_stage; ++s) {
+            NewtonOut o = newton_solve<PIVOT>(g, L, x, n, up, unp, ws, opts);
+            if (g.c == 0 && iters) iters[(long)prob * n_stage + s] = o.iters;
+            if (o.status != GMPNP_CONVERGED) { st = o.status; break; }
+            ++done;
+            __syncwarp(g.mask);
+            // u_n <- u (1D:796) and history row
+            for (long i = g.c; i < (long)n * NC; i += 8) {
+                const double v = up[i];
+                unp[i] = v;
+                if (hist) hist[((long)prob * n_stage + s) * n * NC + i] = v;
+            }
+            __syncwarp(g.mask);
+            if (hohp >= 0.0) {
+                // proton-current controller, 1D:766-793
+                const double f = up[0];
+                if (f < 0) frac = frac / 1.1;
+                else if (f < (hohp - 0.05)) frac = frac / 1.05;
+                else if (f < (hohp - 0.025)) frac = frac / 1.01;
+                else if (f > hohp && f <= (hohp + 0.4) && frac <= 1.0) frac = frac * 1.04;
+                else if (f > (hohp + 0.4) && frac <= 1.0) frac = frac * 1.15;
+                __syncwarp(g.mask);
+                if (g.c == 0) {
+                    P[GMPNP_P_JFLUX + 1] = -1.0 * P[GMPNP_P_JOHPRE] * (1 - frac);
+                    P[GMPNP_P_JFLUX + 0] = P[GMPNP_P_JHPRE] * frac;
+                }
+                __syncwarp(g.mask);
+            }
+        }
+        if (g.c == 0) {
+            if (status) status[prob] = st;
+            if (hfrac_out) hfrac_out[prob] = frac;
+            if (stage_out) stage_out[prob] = done;
+        }
+        return;
+    }
+    // mode 2: steady continuation
+    {
+        if (g.c == 0) P[GMPNP_P_KAPPA] = 0.0;
+        __syncwarp(g.mask);
+        int st = GMPNP_CONVERGED, done = 0;
+        for (int s = 0; s < n_stage; ++s) {
+            if (g.c == 0) P[GMPNP_P_V] = Vpath[(long)prob * n_stage + s];
+            __syncwarp(g.mask);
+            // kappa = 0: u_n is never read for its value; pass u itself
+            NewtonOut o = newton_solve<PIVOT>(g, L, x, n, up, up, ws, opts);
+            if (g.c == 0 && iters) iters[(long)prob * n_stage + s] = o.iters;
+            if (g.c == 0 && rout) rout[prob] = o.r;
+            if (o.status != GMPNP_CONVERGED) { st = o.status; break; }
+            ++done;
+        }
+        if (g.c == 0) {
+            if (status) status[prob] = st;
+            if (stage_out) stage_out[prob] = done;
+        }
+    }
+}
+
+// Materialised residual + block-tridiagonal Jacobian (gmpnp_assemble_1d): one group per
+// (problem, node row).  Used for kernel-parity tests against the oracle.
+__global__ void __launch_bounds__(THREADS)
+assemble1d_kernel(int batch, int n, const double* __restrict__ x, const double* __restrict__ params,
+                  const double* __restrict__ u, const double* __restrict__ un,
+                  double* __restrict__ F, double* __restrict__ J) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31;
+    Group g;
+    g.c = lane & 7; g.base = lane & ~7; g.mask = 0xFFu << g.base;
+    const int gid = threadIdx.x >> 3;
+    g.sm = smem + gid * SM_GROUP;
+    const long item = (long)blockIdx.x * GROUPS_PER_BLOCK + gid;
+    if (item >= (long)batch * n) return;
+    const int prob = (int)(item / n), k = (int)(item % n);
+    load_params(g, params, prob);
+    const double* P = g.sm + SM_P;
+    LaneConst L;
+    lane_consts(P, g.c, L);
+    const double* up = u + (long)prob * n * NC;
+    const double* unp = un + (long)prob * n * NC;
+    const int c = g.c;
+    double A[NC], B[NC], C[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) { A[i] = 0.0; B[i] = 0.0; C[i] = 0.0; }
+    double Um[NC], U0[NC], U1[NC], Nm[NC], N0[NC], N1[NC];
+    load_node(g, up, k, 1, U0);
+#pragma unroll
+    for (int i = 0; i < NC; ++i) N0[i] = unp[(long)k * NC + i];
+    if (k > 0) {
+        load_node(g, up, k - 1, 0, Um);
+#pragma unroll
+        for (int i = 0; i < NC; ++i) Nm[i] = unp[(long)(k - 1) * NC + i];
+        CellCols cc;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) { cc.c00[i] = 0; cc.c01[i] = 0; cc.c10[i] = 0; cc.c11[i] = 0; }
+        cell_columns(P, g.sm + SM_U, L, c, x[k] - x[k - 1], Um, U0, Nm, N0, true, cc);
+#pragma unroll
+        for (int i = 0; i < NC; ++i) { A[i] = cc.c10[i]; B[i] += cc.c11[i]; }
+    }
+    __syncwarp(g.mask);
+    if (k + 1 < n) {
+        if (c < NC) g.sm[SM_U + c] = U0[c]; else g.sm[SM_U + 7] = 1.0;
+        load_node(g, up, k + 1, 1, U1);
+#pragma unroll
+        for (int i = 0; i < NC; ++i) N1[i] = unp[(long)(k + 1) * NC + i];
+        CellCols cc;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) { cc.c00[i] = 0; cc.c01[i] = 0; cc.c10[i] = 0; cc.c11[i] = 0; }
+        cell_columns(P, g.sm + SM_U, L, c, x[k + 1] - x[k], U0, U1, N0, N1, true, cc);
+#pragma unroll
+        for (int i = 0; i < NC; ++i) { B[i] += cc.c00[i]; C[i] = cc.c01[i]; }
+    }
+    if (c == 7) {
+        if (k == 0 || k == n - 1) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) B[i] += P[GMPNP_P_JFLUX + i];
+        }
+        if (k == n - 1) {
+#pragma unroll
+            for (int i = 0; i < NC; ++i) B[i] = U0[i] - ((i < NS) ? 1.0 : 0.0);
+        }
+        if (k == 0) B[NS] = U0[NS] - P[GMPNP_P_V];
+        if (F) {
+#pragma unroll
+            for (int i = 0; i < NC; ++i) F[((long)prob * n + k) * NC + i] = B[i];
+        }
+    } else if (c < NC) {
+        if (k == n - 1) {
+#pragma unroll
+            for (int i = 0; i < NC; ++i) { A[i] = 0.0; C[i] = 0.0; B[i] = (i == c) ? 1.0 : 0.0; }
+        }
+        if (k == 0) { A[NS] = 0.0; C[NS] = 0.0; B[NS] = (c == NS) ? 1.0 : 0.0; }
+        if (J) {
+            double* Jr = J + ((long)prob * n + k) * 147;
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                Jr[i * 7 + c] = A[i];
+                Jr[49 + i * 7 + c] = B[i];
+                Jr[98 + i * 7 + c] = C[i];
+            }
+        }
+    }
+}
+
+// L2 projection of -dphi/dx onto P1 (dolfin project(-grad(u_p), W), 1D:802-803): tridiagonal
+// consistent-mass solve, one thread per problem (post-processing, off the hot path).
+__global__ void field1d_kernel(int batch, int n, const double* __restrict__ x, const double* __restrict__ u,
+                               double* __restrict__ field, double* __restrict__ scratch) {
+    const int prob = blockIdx.x * blockDim.x + threadIdx.x;
+    if (prob >= batch) return;
+    const double* up = u + (long)prob * n * NC;
+    double* f = field + (long)prob * n;
+    double* cp = scratch + (long)prob * n;
+    // rows: (h_{k-1}/6) g_{k-1} + ((h_{k-1}+h_k)/3) g_k + (h_k/6) g_{k+1} = b_k
+    double cprev = 0.0, dprev = 0.0;
+    for (int k = 0; k < n; ++k) {
+        const double hm = (k > 0) ? x[k] - x[k - 1] : 0.0;
+        const double hp = (k + 1 < n) ? x[k + 1] - x[k] : 0.0;
+        double b = 0.0;
+        if (k > 0) b += -0.5 * (up[(long)k * NC + NS] - up[(long)(k - 1) * NC + NS]);
+        if (k + 1 < n) b += -0.5 * (up[(long)(k + 1) * NC + NS] - up[(long)k * NC + NS]);
+        const double a = hm / 6.0, d = (hm + hp) / 3.0, cc = hp / 6.0;
+        const double den = d - a * cprev;
+        cprev = cc / den;
+        dprev = (b - a * dprev) / den;
+        cp[k] = cprev;
+        f[k] = dprev;
+    }
+    for (int k = n - 2; k >= 0; --k) f[k] -= cp[k] * f[k + 1];
+}
+
+}  // namespace edl1d
+
+// ---------------------------------------------------------------------------------------
+// host launchers (called from capi.cu)
+// ---------------------------------------------------------------------------------------
+int edl1d_launch_newton(gmpnp_handle* h, int mode, double* d_u, double* d_un_rw, const double* d_un_ro,
+                        const gmpnp_newton_opts* opts, int n_stage, const double* d_Vpath, double* d_hist,
+                        int* d_iters, double* d_r0, double* d_r, double* d_hfrac, int* d_stage,
+                        int* d_status, cudaStream_t st) {
+    using namespace edl1d;
+    const int blocks = (h->batch + GROUPS_PER_BLOCK - 1) / GROUPS_PER_BLOCK;
+    const size_t smem = (size_t)GROUPS_PER_BLOCK * SM_GROUP * sizeof(double);
+    if (opts->pivot)
+        newton1d_kernel<true><<<blocks, THREADS, smem, st>>>(mode, h->batch, h->n_nodes, h->d_x, h->d_params, d_u,
+            d_un_rw, d_un_ro, h->d_ws, *opts, n_stage, d_Vpath, d_hist, d_iters, d_r0, d_r, d_hfrac, d_stage, d_status);
+    else
+        newton1d_kernel<false><<<blocks, THREADS, smem, st>>>(mode, h->batch, h->n_nodes, h->d_x, h->d_params, d_u,
+            d_un_rw, d_un_ro, h->d_ws, *opts, n_stage, d_Vpath, d_hist, d_iters, d_r0, d_r, d_hfrac, d_stage, d_status);
+    h->launches++;
+    GMPNP_CUDA_TRY(h, cudaGetLastError());
+    return GMPNP_OK;
+}
+
+int edl1d_launch_assemble(gmpnp_handle* h, const double* d_u, const double* d_un, double* d_F, double* d_J,
+                          cudaStream_t st) {
+    using namespace edl1d;
+    const long items = (long)h->batch * h->n_nodes;
+    const int blocks = (int)((items + GROUPS_PER_BLOCK - 1) / GROUPS_PER_BLOCK);
+    const size_t smem = (size_t)GROUPS_PER_BLOCK * SM_GROUP * sizeof(double);
+    assemble1d_kernel<<<blocks, THREADS, smem, st>>>(h->batch, h->n_nodes, h->d_x, h->d_params, d_u, d_un, d_F, d_J);
+    h->launches++;
+    GMPNP_CUDA_TRY(h, cudaGetLastError());
+    return GMPNP_OK;
+}
+
+int edl1d_launch_field(gmpnp_handle* h, const double* d_u, double* d_field, cudaStream_t st) {
+    using namespace edl1d;
+    const int threads = 64;
+    const int blocks = (h->batch + threads - 1) / threads;
+    // the elimination workspace doubles as scratch (n doubles per problem needed)
+    field1d_kernel<<<blocks, threads, 0, st>>>(h->batch, h->n_nodes, h->d_x, d_u, d_field, h->d_ws);
+    h->launches++;
+    GMPNP_CUDA_TRY(h, cudaGetLastError());
+    return GMPNP_OK;
+}

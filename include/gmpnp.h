@@ -1,0 +1,176 @@
+/*
+ * gmpnp.h -- C-ABI of the B200-native GMPNP hot path (libgmpnp.so).
+ *
+ * The reference (divyabohra/GMPNP) has no FFI: its hot path is the Python call
+ *     solve(F == 0, u, bcs, solver_parameters=...)
+ * at 1D/MPNP_CO2ER_EDL.py:737-742 and 3D/MPNP_CO2ER_pore.py:789-799, executed inside the
+ * pseudo-time loops 1D:633-796 / 3D:782-858.  This library is what a maintainer would
+ * bind (ctypes) at exactly those call sites, with the loop hoisted
+ * inside.  Everything is fp64.  Conventions:
+ *   - plain C, no C++/torch types; `int` status returns (0 = ok, <0 = API/CUDA error,
+ *     see gmpnp_strerror); numerical outcomes are reported per problem in `status[]`;
+ *   - all `d_*` pointers are caller-owned DEVICE buffers (e.g. torch tensors' data_ptr());
+ *     `h_*` pointers are host buffers; `stream` is a cudaStream_t passed as void*;
+ *   - a handle owns only its mesh copy, parameter records and elimination workspace;
+ *     handles are independent (thread-compatible per handle), there are no globals.
+ *
+ * Unknown layout: node-major interleaved, u[problem][node][comp], comp = species in the
+ * reference's order (1D:117 / 3D:138) with the potential last (1D:303, 3D:407).
+ */
+#ifndef GMPNP_H
+#define GMPNP_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gmpnp_handle gmpnp_handle;
+
+/* ---- packed per-problem parameter record: double[GMPNP_NPAR] ------------------------
+ * Host code (gmpnp_b200/params.py, mirroring 1D:81-213,368-375 and 3D:115-324) fills it. */
+#define GMPNP_NPAR 64
+#define GMPNP_P_NS      0   /* number of species (6 in 1D, 8 in 3D)                          */
+#define GMPNP_P_Z       1   /* [8] charges z_i                       (1D:158, 3D:233)         */
+#define GMPNP_P_NU      9   /* [8] scale_vol_i = a_i^3 c0_i N_A      (1D:200, 3D:287); 0=PNP  */
+#define GMPNP_P_ZC0    17   /* [8] z_i * c0_i  (Poisson source, 1D:422-427)                   */
+#define GMPNP_P_S      25   /* [5] scale_R of H, OH, HCO3, CO32, CO2 (1D:190, 3D:277)         */
+#define GMPNP_P_KW     30   /* kw2*c0_H*c0_OH      (1D:384)                                   */
+#define GMPNP_P_KA     31   /* ka1*c0_OH*c0_HCO3   (1D:389)                                   */
+#define GMPNP_P_KB     32   /* kb1*c0_CO2*c0_OH    (1D:390)                                   */
+#define GMPNP_P_KA2    33   /* ka2*c0_CO32         (1D:391)                                   */
+#define GMPNP_P_KB2    34   /* kb2*c0_HCO3         (1D:391-392)                               */
+#define GMPNP_P_KW1    35   /* kw1                                                            */
+#define GMPNP_P_EPSW   36   /* eps_rel of water    (1D:413)                                   */
+#define GMPNP_P_EPSH   37   /* n_water_H  *c0_H  *1e-3 (1D:414-415)                           */
+#define GMPNP_P_EPSC   38   /* n_water_cat*c0_cat*1e-3                                        */
+#define GMPNP_P_KAPPA  39   /* coefficient of (u-u_n) v dx: 1/(dt*L_D) 1D:458, 1/dt 3D:534; 0=steady */
+#define GMPNP_P_V      40   /* scaled potential at the OHP (1D:354) / pore wall (3D:462)      */
+#define GMPNP_P_JFLUX  41   /* [8] 1D point fluxes J_i of `J_i v_i ds` (1D:553, 738)          */
+#define GMPNP_P_ICAT   49   /* index of the cation species (= ns-1)                           */
+#define GMPNP_P_Q      50   /* q = F^2 L^2/(eps0 R T)   (1D:193, 3D:280)                      */
+#define GMPNP_P_JOHPRE 51   /* J_OH_prefactor*current_OHP_ss  (H_OHP controller, 1D:789-791)  */
+#define GMPNP_P_JHPRE  52   /* J_H_prefactor *current_OHP_ss  (1D:793)                        */
+#define GMPNP_P_HOHP   53   /* H_OHP target; < 0 disables the controller (1D:770)             */
+#define GMPNP_P_HFRAC  54   /* current_H_frac initial value (1D:167-170)                      */
+
+/* ---- Newton options (dolfin NewtonSolver semantics) ------------------ */
+typedef struct gmpnp_newton_opts {
+    double rtol;        /* relative_tolerance  (1e-4 at 1D:361, 3D:794)                    */
+    double atol;        /* absolute_tolerance  (1e-4 at 1D:362, 3D:795)                    */
+    double relax;       /* relaxation_parameter (1.0 in 1D, 0.9 at 3D:796)                 */
+    double xtol;        /* increment criterion: ||dx||_inf <= xtol*max(1,||x||_inf)        */
+    int    maxit;       /* maximum_iterations  (50)                                        */
+    int    criterion;   /* 0 = residual (reference), 1 = increment (steady mode)           */
+    int    pivot;       /* 1 = partial pivoting inside the 7x7 blocks (default), 0 = none  */
+    int    lin_maxit;   /* 3D: max GMRES iterations per Newton step                        */
+    int    lin_restart; /* 3D: GMRES restart length                                        */
+    double lin_rtol;    /* 3D: GMRES relative residual tolerance                           */
+} gmpnp_newton_opts;
+
+/* per-problem status codes written to status[] */
+#define GMPNP_CONVERGED        0
+#define GMPNP_MAXIT            1   /* dolfin would raise RuntimeError here                   */
+#define GMPNP_NOT_FINITE       2   /* NaN/Inf in residual or singular pivot                  */
+#define GMPNP_LINEAR_FAILED    3   /* 3D: GMRES did not reach lin_rtol                       */
+
+/* API error codes */
+#define GMPNP_OK               0
+#define GMPNP_ERR_ARG         -1
+#define GMPNP_ERR_CUDA        -2
+#define GMPNP_ERR_ALLOC       -3
+#define GMPNP_ERR_STATE       -4
+
+const char* gmpnp_strerror(int code);
+const char* gmpnp_last_cuda_error(const gmpnp_handle* h);
+int  gmpnp_version(void);
+void gmpnp_destroy(gmpnp_handle* h);
+
+/* ------------------------------------------------------------------------------------
+ * 1D planar EDL (replaces the FEniCS work behind 1D/MPNP_CO2ER_EDL.py:737-742)
+ * ---------------------------------------------------------------------------------- */
+
+/* `h_x`: the n_nodes sorted vertex coordinates of the interval mesh (Mesh(), 1D:231-234;
+ * cell k = nodes (k,k+1)).  All `batch` problems of a handle share the mesh.            */
+int gmpnp_create_1d(gmpnp_handle** out, int device, const double* h_x, int n_nodes,
+                    int n_species, int batch);
+
+/* Packed parameter records, h_params[batch][GMPNP_NPAR] (host pointer; copied).           */
+int gmpnp_set_params(gmpnp_handle* h, const double* h_params, int batch);
+
+/* Residual and block-tridiagonal Jacobian at (u, u_n), Dirichlet rows applied exactly as
+ * dolfin does (identity row, residual x-g; 1D:350-355).  Testable alone.
+ *   d_F [batch][n][7], d_J [batch][n][3][7][7] (sub-, main-, super-diagonal block of each
+ *   node row, row-major inside a block).  Either output may be NULL.                      */
+int gmpnp_assemble_1d(gmpnp_handle* h, const double* d_u, const double* d_un,
+                      double* d_F, double* d_J, void* stream);
+
+/* One reference `solve(F == 0, u, bcs)` per problem: Newton from the incoming d_u.
+ * Outputs (device, may be NULL): iters[batch], r0[batch], r[batch], status[batch].        */
+int gmpnp_newton_1d(gmpnp_handle* h, double* d_u, const double* d_un,
+                    const gmpnp_newton_opts* opts, int* d_iters, double* d_r0, double* d_r,
+                    int* d_status, void* stream);
+
+/* The reference's pseudo-time loop (1D:633-796): n_steps times { solve; H_OHP controller
+ * (1D:766-793); u_n <- u }.  d_un is updated in place.  d_hist (optional)
+ * [batch][n_steps][n][7] receives u after every step; d_iters (optional) [batch][n_steps];
+ * d_hfrac (optional) [batch] final current_H_frac.  A failed step stops that problem only. */
+int gmpnp_march_1d(gmpnp_handle* h, double* d_u, double* d_un, int n_steps,
+                   const gmpnp_newton_opts* opts, double* d_hist, int* d_iters,
+                   double* d_hfrac, int* d_status, void* stream);
+
+/* Steady equations (kappa forced to 0) with voltage continuation: for s < n_V the OHP
+ * potential is d_Vpath[problem][s] and Newton restarts from the previous stage's solution.
+ * d_iters (optional) [batch][n_V]; d_stage (optional) [batch] = number of stages completed. */
+int gmpnp_steady_continuation_1d(gmpnp_handle* h, double* d_u, const double* d_Vpath, int n_V,
+                                 const gmpnp_newton_opts* opts, int* d_iters, int* d_stage,
+                                 int* d_status, void* stream);
+
+/* L2 projection of -d(phi)/dx onto P1 (dolfin project(-grad(u_p), W), 1D:802-803) for
+ * every problem: d_field[batch][n].                                                       */
+int gmpnp_field_1d(gmpnp_handle* h, const double* d_u, double* d_field, void* stream);
+
+/* number of kernels this handle has launched so far (for bench.py's gpu_launches)          */
+long long gmpnp_launch_count(const gmpnp_handle* h);
+
+/* ------------------------------------------------------------------------------------
+ * 3D pore (replaces the FEniCS work behind 3D/MPNP_CO2ER_pore.py:789-799)
+ * ---------------------------------------------------------------------------------- */
+
+/* Mesh (Mesh(), 3D:329-332) and Dirichlet DOF list (DirichletBC, 3D:460-467, already
+ * de-duplicated so that the last BC wins).  Values are per problem (gmpnp_set_dirichlet). */
+int gmpnp_create_3d(gmpnp_handle** out, int device, const double* h_xyz, int n_vert,
+                    const int* h_tets, int n_tet, const int* h_dir_dof, int n_dir,
+                    int n_species, int batch);
+
+/* Dirichlet values, h_vals[batch][n_dir] (host pointer; copied).                          */
+int gmpnp_set_dirichlet_3d(gmpnp_handle* h, const double* h_vals, int batch);
+
+/* Sparsity of the BSR-9 Jacobian: number of block rows / blocks, and copies of row_ptr
+ * (n_vert+1) / col_idx (n_blocks) for the caller (host pointers, may be NULL).            */
+int gmpnp_pattern_3d(const gmpnp_handle* h, int* n_blocks, int* h_row_ptr, int* h_col_idx);
+
+/* Residual d_F[batch][n_vert][9] and BSR values d_J[batch][n_blocks][9][9] at (u, u_n),
+ * Dirichlet rows applied.  Either output may be NULL.                                     */
+int gmpnp_assemble_3d(gmpnp_handle* h, const double* d_u, const double* d_un,
+                      double* d_F, double* d_J, void* stream);
+
+/* y = J x with the BSR values of the last assembly kept in the handle, or with d_J if
+ * given: d_x, d_y [batch][n_vert][9].                                                     */
+int gmpnp_spmv_3d(gmpnp_handle* h, const double* d_J, const double* d_x, double* d_y,
+                  void* stream);
+
+/* One reference `solve(F == 0, u, bcs)` per problem: damped Newton, each step solved by
+ * restarted GMRES with per-node 9x9 block-Jacobi.  d_lin_iters (optional) [batch] = total
+ * GMRES iterations.                                                                       */
+int gmpnp_newton_3d(gmpnp_handle* h, double* d_u, const double* d_un,
+                    const gmpnp_newton_opts* opts, int* d_iters, double* d_r0, double* d_r,
+                    int* d_lin_iters, int* d_status, void* stream);
+
+/* Median over the vertices of component `comp` for every problem (np.median, 3D:817-820):
+ * d_med[batch].                                                                            */
+int gmpnp_median_3d(gmpnp_handle* h, const double* d_u, int comp, double* d_med, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GMPNP_H */

@@ -1,0 +1,16 @@
+"""CPU oracle for the GMPNP hot path -- TEST INFRASTRUCTURE, not product code.
+
+A NumPy/SciPy restatement of the discrete equations the reference scripts hand to
+FEniCS (1D/MPNP_CO2ER_EDL.py:381-595, 737-742; 3D/MPNP_CO2ER_pore.py:503-769,
+789-799) together with FFC's quadrature-degree conventions and dolfin's
+NewtonSolver semantics.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
+legs may import it; nothing under ``gmpnp_b200/`` does.
+
+PARITY UNPINNED: the arithmetic of the reference lives in un-vendored third-party
+packages (fenics-dolfin/ffc/ufl/fiat 2019.1.0, petsc 3.12.3, mumps 5.2.1,
+suitesparse 5.6.0 -- environment.yml:21-27,78,86,110) that can be neither imported
+nor built in this container, and the reference has no tests or golden outputs for
+this path.  The only numbers it holds are the five soft (field_OHP, eps_rel_OHP)
+pairs in 1D/Stern_CO2ER.py:66-68, which this oracle brackets (tests/test_oracle_1d.py).
+"""

@@ -1,0 +1,198 @@
+"""Global assembly, Dirichlet handling and Newton drivers of the oracle (test infrastructure).
+
+* assembly / scatter: what dolfin's SystemAssembler does for ``solve(F == 0, u, bcs)``
+  (1D/MPNP_CO2ER_EDL.py:737-742, 3D/MPNP_CO2ER_pore.py:789-799);
+* Dirichlet sets: 1D:237-254, 350-355; 3D:460-467 (list order, later BC wins);
+* Newton: dolfin 2019.1 ``NewtonSolver`` semantics as written out in SURVEY App. C;
+* march: the reference's pseudo-time loop 1D:633-796 / 3D:782-858 (incl. the H_OHP ladder
+  1D:766-793 and the Sechenov median update 3D:817-838);
+* steady: the time term dropped, voltage continuation, tight increment criterion.
+
+DOF numbering: node-major, ``dof = ncomp * vertex + component``.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from . import forms, quadrature
+
+
+class Discretisation:
+    """Mesh + fixed sparsity data for one (mesh, ncomp) pair."""
+
+    def __init__(self, x, cells, ncomp):
+        self.x = np.asarray(x, dtype=np.float64)
+        if self.x.ndim == 1:
+            self.x = self.x[:, None]
+        self.cells = np.asarray(cells, dtype=np.int64)
+        self.ncomp = ncomp
+        self.dim = self.x.shape[1]
+        self.nv = self.x.shape[0]
+        self.ndof = ncomp * self.nv
+        self.g, self.vol = forms.geometry(self.x, self.cells)
+        self.ruleF, self.ruleJ = quadrature.rules_for_dim(self.dim)
+        dofs = (self.cells[:, :, None] * ncomp + np.arange(ncomp)[None, None, :])   # [c, a, i]
+        self.cell_dofs = dofs
+        nloc = dofs.shape[1] * ncomp
+        d = dofs.reshape(len(self.cells), nloc)
+        self.rows = np.repeat(d, nloc, axis=1).ravel()
+        self.cols = np.tile(d, (1, nloc)).ravel()
+
+    def gather(self, u):
+        return u.reshape(self.nv, self.ncomp)[self.cells]          # [c, a, i]
+
+    def residual(self, u, un, prm, point_flux=None):
+        Fe = forms.element_residual(self.gather(u), self.gather(un), self.g, self.vol, prm, self.ruleF)
+        F = np.zeros(self.ndof, dtype=Fe.dtype)
+        np.add.at(F, self.cell_dofs.ravel(), Fe.ravel())
+        if point_flux is not None:          # 1D `J_i * v_i * ds`: point evaluation at BOTH ends (1D:553, 738)
+            ns = self.ncomp - 1
+            for node in (0, self.nv - 1):
+                F[node * self.ncomp: node * self.ncomp + ns] += point_flux[:ns]
+        return F
+
+    def jacobian(self, u, prm):
+        Je = forms.element_jacobian(self.gather(u), self.g, self.vol, prm, self.ruleJ)
+        A = sp.coo_matrix((Je.ravel(), (self.rows, self.cols)), shape=(self.ndof, self.ndof))
+        return A.tocsr()
+
+
+def apply_bc_residual(b, x, bc_dofs, bc_vals):
+    """b[dof] = x[dof] - g; bcs given in application order (later wins automatically)."""
+    b[bc_dofs] = x[bc_dofs] - bc_vals
+    return b
+
+
+def apply_bc_matrix(A, bc_dofs):
+    """Dirichlet rows -> identity rows."""
+    A = A.tolil(copy=False) if False else A
+    mask = np.zeros(A.shape[0], dtype=bool)
+    mask[bc_dofs] = True
+    keep = sp.diags((~mask).astype(np.float64))
+    return (keep @ A + sp.diags(mask.astype(np.float64))).tocsc()
+
+
+def bc_1d(nv, ncomp, V):
+    """1D Dirichlet set: bulk (1,...,1,0) on all components at x=1, potential V at x=0
+    (1D:350-355).  Returns (dofs, values) in application order."""
+    last = (nv - 1) * ncomp
+    dofs = list(range(last, last + ncomp)) + [ncomp - 1]
+    vals = [1.0] * (ncomp - 1) + [0.0] + [V]
+    return np.array(dofs, dtype=np.int64), np.array(vals, dtype=np.float64)
+
+
+def newton(disc, prm, u, un, bc_dofs, bc_vals, point_flux=None, rtol=1e-4, atol=1e-4, maxit=50,
+           relax=1.0, criterion="residual", xtol=1e-12, history=None):
+    """dolfin NewtonSolver.  Returns (u, iterations, converged, r0, r).
+
+    criterion 'residual': stop when ||b||/||b0|| < rtol or ||b|| < atol (reference).
+    criterion 'increment': stop when ||dx||_inf <= xtol * max(1, ||x||_inf)  (steady mode)."""
+    x = u.copy()
+    b = apply_bc_residual(disc.residual(x, un, prm, point_flux), x, bc_dofs, bc_vals)
+    r0 = float(np.linalg.norm(b))
+    r = r0
+    k = 0
+    conv = (r < atol) if criterion == "residual" else False
+    while not conv and k < maxit:
+        A = apply_bc_matrix(disc.jacobian(x, prm), bc_dofs)
+        dx = spla.splu(A).solve(b)
+        x = x - relax * dx
+        k += 1
+        b = apply_bc_residual(disc.residual(x, un, prm, point_flux), x, bc_dofs, bc_vals)
+        r = float(np.linalg.norm(b))
+        if history is not None:
+            history.append((k, r, float(np.abs(dx).max())))
+        if criterion == "residual":
+            conv = (r / r0 < rtol) or (r < atol)
+        else:
+            conv = float(np.abs(dx).max()) <= xtol * max(1.0, float(np.abs(x).max()))
+        if not np.isfinite(r):
+            break
+    return x, k, conv, r0, r
+
+
+def h_ohp_ladder(frac, H_OHP_frac, H_OHP):
+    """Proton-current controller of 1D:770-782."""
+    if H_OHP_frac < 0:
+        frac = frac / 1.1
+    elif H_OHP_frac < (H_OHP - 0.05):
+        frac = frac / 1.05
+    elif H_OHP_frac < (H_OHP - 0.025):
+        frac = frac / 1.01
+    elif (H_OHP_frac > H_OHP and H_OHP_frac <= (H_OHP + 0.4) and frac <= 1.0):
+        frac = frac * 1.04
+    elif H_OHP_frac > (H_OHP + 0.4) and frac <= 1.0:
+        frac = frac * 1.15
+    return frac
+
+
+def march_1d(x, prm, n_steps, H_OHP=None, rtol=1e-4, atol=1e-4, maxit=50):
+    """The reference's 1D pseudo-time loop (1D:633-796): u starts at 0, u_n at (1,..,1,0)."""
+    x = np.asarray(x, dtype=np.float64).reshape(-1)
+    nv = len(x)
+    cells = np.stack([np.arange(nv - 1), np.arange(1, nv)], axis=1)
+    ncomp = prm.ns + 1
+    disc = Discretisation(x, cells, ncomp)
+    bc_dofs, bc_vals = bc_1d(nv, ncomp, prm.V)
+    u = np.zeros(disc.ndof)
+    un = np.tile(np.array([1.0] * prm.ns + [0.0]), nv)
+    hist = [un.reshape(nv, ncomp).copy()]
+    its = []
+    flux = prm.jflux.copy()
+    frac = prm.extras.get("current_H_frac", 0.0)
+    for _ in range(n_steps):
+        u, k, conv, r0, r = newton(disc, prm, u, un, bc_dofs, bc_vals, point_flux=flux,
+                                   rtol=rtol, atol=atol, maxit=maxit)
+        if not conv:
+            raise RuntimeError("Newton solver did not converge")
+        its.append(k)
+        hist.append(u.reshape(nv, ncomp).copy())
+        if H_OHP is not None:
+            frac = h_ohp_ladder(frac, u[0], H_OHP)
+            e = prm.extras
+            flux[1] = -1.0 * e["J_OH_prefactor"] * e["current_OHP_ss"] * (1 - frac)
+            flux[0] = e["J_H_prefactor"] * e["current_OHP_ss"] * frac
+        un = u.copy()
+    return np.array(hist), its, frac
+
+
+def steady_1d(x, prm, V_path, u0=None, xtol=1e-12, maxit=50):
+    """Steady equations (kappa = 0) with voltage continuation along ``V_path``.
+    Starts from the bulk state unless ``u0`` is given.  Returns (u[nv, ncomp] at the last V,
+    list of Newton counts)."""
+    x = np.asarray(x, dtype=np.float64).reshape(-1)
+    nv = len(x)
+    cells = np.stack([np.arange(nv - 1), np.arange(1, nv)], axis=1)
+    ncomp = prm.ns + 1
+    disc = Discretisation(x, cells, ncomp)
+    ps = prm.with_(kappa=0.0)
+    u = np.tile(np.array([1.0] * prm.ns + [0.0]), nv) if u0 is None else np.asarray(u0, float).reshape(-1).copy()
+    its = []
+    for V in V_path:
+        pv = ps.with_(V=float(V))
+        bc_dofs, bc_vals = bc_1d(nv, ncomp, float(V))
+        u, k, conv, r0, r = newton(disc, pv, u, u, bc_dofs, bc_vals, point_flux=pv.jflux,
+                                   criterion="increment", xtol=xtol, maxit=maxit)
+        if not conv:
+            raise RuntimeError(f"steady Newton failed at V={V} after {k} its (r={r})")
+        its.append(k)
+    return u.reshape(nv, ncomp), its
+
+
+def p1_gradient_projection_1d(x, f):
+    """L2 projection of df/dx onto P1 (dolfin ``project(grad(f), W)``, 1D:802-803):
+    solve M g = b with the consistent P1 mass matrix."""
+    x = np.asarray(x, dtype=np.float64).reshape(-1)
+    h = np.diff(x)
+    n = len(x)
+    slope = np.diff(f) / h
+    b = np.zeros(n)
+    b[:-1] += 0.5 * h * slope
+    b[1:] += 0.5 * h * slope
+    main = np.zeros(n)
+    main[:-1] += h / 3
+    main[1:] += h / 3
+    M = sp.diags([h / 6, main, h / 6], [-1, 0, 1]).tocsc()
+    return spla.splu(M).solve(b)

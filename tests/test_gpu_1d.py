@@ -1,0 +1,248 @@
+"""Parity of the CUDA 1D path (through the C-ABI) against the oracle and the golden vectors."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, admissible_state
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda", 0)
+
+
+def _t(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=_dev())
+
+
+def rel_l2(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def test_assemble_matches_golden_entrywise(lib):
+    """Kernel parity: every F and J entry, relative 1e-12 of the row scale."""
+    from gmpnp_b200 import params, solver1d
+    g = np.load(os.path.join(GOLDEN, "assemble_1d.npz"))
+    prm = params.params_1d()
+    s = solver1d.Solver1D(g["x"], batch=3)
+    s.set_params([prm, prm, prm])
+    u = _t(np.stack([g["u"]] * 3))
+    un = _t(np.stack([g["un"]] * 3))
+    F, J = s.assemble(u, un)
+    torch.cuda.synchronize()
+    F, J = F.cpu().numpy(), J.cpu().numpy()
+    for b in range(3):
+        scale = np.abs(g["J"]).max(axis=(1, 3), keepdims=True)           # per block-row scale
+        assert np.abs(J[b] - g["J"]).max() <= 1e-12 * np.abs(g["J"]).max()
+        assert (np.abs(J[b] - g["J"]) <= 1e-11 * scale).all()
+        assert np.abs(F[b] - g["F"]).max() <= 1e-11 * np.abs(g["F"]).max()
+        rows = np.abs(g["F"]) > 1e-6 * np.abs(g["F"]).max()
+        assert (np.abs(F[b] - g["F"])[rows] <= 1e-9 * np.abs(g["F"])[rows]).all()
+    # structural zeros stay exactly zero (neutral species x potential column: z = 0)
+    assert np.all(J[0][1:-1, :, 4, 6] == 0.0)
+    # Dirichlet rows are identity rows
+    assert np.array_equal(J[0][-1, 1], np.eye(7)) and np.all(J[0][-1, 0] == 0)
+    assert np.array_equal(J[0][0, 1, 6], np.eye(7)[6]) and np.all(J[0][0, 2, 6] == 0)
+
+
+def test_assemble_random_states_vs_oracle(lib):
+    from gmpnp_b200 import meshio, params, solver1d
+    from oracle import solver as osolver
+    m = meshio.graded_interval(40, 0.01, 23)
+    x = m.x[:, 0]
+    n = len(x)
+    plist = [params.params_1d(concentration_elec=c, cation=cat, voltage_multiplier=V, model=mod)
+             for c, cat, V, mod in ((0.1, "K", -1.0, "MPNP"), (0.5, "Cs", -7.0, "MPNP"),
+                                    (1.0, "K", -12.5, "MPNP"), (0.1, "Li", -3.0, "PNP"))]
+    rng = np.random.default_rng(1)
+    us = np.stack([admissible_state(rng, n, 6, p.nu if p.nu.any() else np.full(6, 1e-3)) for p in plist])
+    uns = np.stack([admissible_state(rng, n, 6, np.full(6, 1e-3)) for p in plist])
+    s = solver1d.Solver1D(x, batch=len(plist))
+    s.set_params(plist)
+    F, J = s.assemble(_t(us), _t(uns))
+    F, J = F.cpu().numpy(), J.cpu().numpy()
+    disc = osolver.Discretisation(x, m.cells, 7)
+    for b, p in enumerate(plist):
+        bd, bv = osolver.bc_1d(n, 7, p.V)
+        Fo = osolver.apply_bc_residual(disc.residual(us[b].ravel(), uns[b].ravel(), p, p.jflux), us[b].ravel(), bd, bv)
+        A = osolver.apply_bc_matrix(disc.jacobian(us[b].ravel(), p), bd).toarray()
+        assert np.abs(F[b].ravel() - Fo).max() <= 1e-11 * np.abs(Fo).max()
+        for k in range(n):
+            for o, kk in enumerate((k - 1, k, k + 1)):
+                if 0 <= kk < n:
+                    blk = A[7 * k:7 * k + 7, 7 * kk:7 * kk + 7]
+                    assert np.abs(J[b, k, o] - blk).max() <= 1e-12 * max(np.abs(A[7 * k:7 * k + 7]).max(), 1e-300)
+
+
+def test_single_newton_solve_matches_oracle(lib):
+    """One reference solve(): same start vector, same stopping rule -> same count, same iterate."""
+    from gmpnp_b200 import meshio, params, solver1d
+    from oracle import solver as osolver
+    m = meshio.load_mesh("1D_variable_1um_mesh_1090")
+    x = m.x[:, 0]
+    n = len(x)
+    Vs = [-1.0, -5.0, -12.5]
+    plist = [params.params_1d(L_n=1e-6, voltage_multiplier=V) for V in Vs]
+    s = solver1d.Solver1D(x, batch=len(Vs))
+    s.set_params(plist)
+    u = torch.zeros(len(Vs), n, 7, dtype=torch.float64, device=_dev())
+    un = solver1d.bulk_state(len(Vs), n, _dev())
+    out = s.newton(u, un)
+    torch.cuda.synchronize()
+    disc = osolver.Discretisation(x, m.cells, 7)
+    for b, p in enumerate(plist):
+        bd, bv = osolver.bc_1d(n, 7, p.V)
+        uo, k, conv, r0, r = osolver.newton(disc, p, np.zeros(disc.ndof), un[b].cpu().numpy().ravel(), bd, bv,
+                                            point_flux=p.jflux)
+        assert conv and int(out["status"][b]) == 0
+        assert int(out["iters"][b]) == k
+        assert abs(float(out["r0"][b]) - r0) <= 1e-10 * r0
+        got = u[b].cpu().numpy()
+        for c in range(7):
+            assert rel_l2(got[:, c], uo.reshape(n, 7)[:, c]) < 1e-8
+
+
+def test_march_matches_golden_1um(lib):
+    from gmpnp_b200 import meshio, params, solver1d
+    g = np.load(os.path.join(GOLDEN, "march_1um.npz"))
+    m = meshio.load_mesh("1D_variable_1um_mesh_1090")
+    prm = params.params_1d(L_n=1e-6)
+    s = solver1d.Solver1D(m.x[:, 0], batch=2)
+    s.set_params([prm, prm])
+    u = torch.zeros(2, s.n, 7, dtype=torch.float64, device=_dev())
+    un = solver1d.bulk_state(2, s.n, _dev())
+    out = s.march(u, un, 5, history=True)
+    torch.cuda.synchronize()
+    assert out["status"].tolist() == [0, 0]
+    assert out["iters"][0].tolist() == g["its"].tolist()
+    assert out["iters"][1].tolist() == g["its"].tolist()
+    hist = out["history"].cpu().numpy()
+    for step in range(5):
+        for c in range(7):
+            assert rel_l2(hist[0, step, :, c], g["hist"][step + 1][:, c]) < 1e-8
+    assert np.array_equal(hist[0], hist[1])                      # batch positions are bit-identical
+    assert np.array_equal(un[0].cpu().numpy(), hist[0, -1])      # u_n <- u
+
+
+def test_march_with_h_ohp_controller(lib):
+    from gmpnp_b200 import meshio, params, solver1d
+    g = np.load(os.path.join(GOLDEN, "march_1um_HOHP.npz"))
+    m = meshio.load_mesh("1D_variable_1um_mesh_1090")
+    prm = params.params_1d(L_n=1e-6, H_OHP=1.1)
+    prm.extras["H_OHP"] = 1.1
+    s = solver1d.Solver1D(m.x[:, 0], batch=1)
+    s.set_params([prm])
+    u = torch.zeros(1, s.n, 7, dtype=torch.float64, device=_dev())
+    un = solver1d.bulk_state(1, s.n, _dev())
+    out = s.march(u, un, 5)
+    torch.cuda.synchronize()
+    assert out["iters"][0].tolist() == g["its"].tolist()
+    assert abs(float(out["hfrac"][0]) - float(g["frac"])) <= 1e-15
+    got = u[0].cpu().numpy()
+    for c in range(7):
+        assert rel_l2(got[:, c], g["last"][:, c]) < 1e-8
+
+
+def test_config1_march_first_steps(lib):
+    """BASELINE config 1: 50 um mesh, V=-1, K+: Newton counts 7,3,3 and the state after 3 steps."""
+    from gmpnp_b200 import meshio, params, solver1d
+    g = np.load(os.path.join(GOLDEN, "march_50um.npz"))
+    m = meshio.load_mesh("1D_variable_50um_mesh_5990")
+    prm = params.params_1d()
+    s = solver1d.Solver1D(m.x[:, 0], batch=1)
+    s.set_params([prm])
+    u = torch.zeros(1, s.n, 7, dtype=torch.float64, device=_dev())
+    un = solver1d.bulk_state(1, s.n, _dev())
+    out = s.march(u, un, 3)
+    assert out["iters"][0].tolist() == g["its"].tolist()
+    got = u[0].cpu().numpy()
+    for c in range(7):
+        assert rel_l2(got[:, c], g["last"][:, c]) < 1e-8
+
+
+def test_steady_continuation_matches_golden_50um(lib):
+    """Steady parity: rel-L2 per field <= 1e-8 at V = -1, -2.5, -5, -7.5, -10, -12.5,
+    each reached by its own continuation path inside one batched launch."""
+    from gmpnp_b200 import meshio, params, solver1d
+    from gmpnp_b200._lib import NewtonOpts
+    g = np.load(os.path.join(GOLDEN, "steady_50um.npz"))
+    m = meshio.load_mesh("1D_variable_50um_mesh_5990")
+    targets = [-1.0, -2.5, -5.0, -7.5, -10.0, -12.5]
+    nV = 25
+    Vpath = np.zeros((len(targets), nV))
+    for b, V in enumerate(targets):
+        steps = int(round(abs(V) / 0.5))
+        Vpath[b, :steps] = -0.5 * np.arange(1, steps + 1)
+        Vpath[b, steps:] = V
+    prm = params.params_1d()
+    s = solver1d.Solver1D(m.x[:, 0], batch=len(targets))
+    s.set_params([prm] * len(targets))
+    u = solver1d.bulk_state(len(targets), s.n, _dev())
+    out = s.steady(u, Vpath, NewtonOpts.steady(xtol=1e-12))
+    torch.cuda.synchronize()
+    assert out["status"].tolist() == [0] * len(targets), out
+    got = u.cpu().numpy()
+    for b, V in enumerate(targets):
+        ref = g[f"u_{V}"]
+        for c in range(7):
+            assert rel_l2(got[b, :, c], ref[:, c]) < 1e-8, (V, c)
+    # Newton counts along the -12.5 ladder within +-1 of the oracle's
+    its = out["iters"][-1].cpu().numpy()
+    assert np.abs(its - g["its"]).max() <= 1, (its, g["its"])
+    # OHP metrics through the device field projection (1D:802-805)
+    f = s.field(u).cpu().numpy()
+    for b, V in enumerate(targets):
+        field = f[b, 0] * prm.thermal_voltage / prm.length * 1e-9
+        assert abs(field - g[f"ohp_{V}"][0]) <= 1e-8 * abs(g[f"ohp_{V}"][0])
+
+
+def test_pivoting_off_agrees(lib):
+    from gmpnp_b200 import meshio, params, solver1d
+    from gmpnp_b200._lib import NewtonOpts
+    m = meshio.load_mesh("1D_variable_5um_mesh_1490")
+    prm = params.params_1d(L_n=5e-6, concentration_elec=0.5)
+    res = []
+    for piv in (1, 0):
+        s = solver1d.Solver1D(m.x[:, 0], batch=1)
+        s.set_params([prm])
+        u = solver1d.bulk_state(1, s.n, _dev())
+        o = NewtonOpts.steady()
+        o.pivot = piv
+        out = s.steady(u, np.array([[-1.0, -2.0, -3.0]]), o)
+        assert out["status"].tolist() == [0]
+        res.append(u.cpu().numpy())
+    assert rel_l2(res[1], res[0]) < 1e-9
+
+
+def test_failure_is_reported_per_problem_not_fatal(lib):
+    """A hopeless problem (jump straight to -12.5 with 3 iterations) reports maxit/not-finite; its
+    neighbour in the same warp still converges (never abort the batch)."""
+    from gmpnp_b200 import meshio, params, solver1d
+    from gmpnp_b200._lib import NewtonOpts
+    m = meshio.load_mesh("1D_variable_1um_mesh_1090")
+    prm = params.params_1d(L_n=1e-6)
+    s = solver1d.Solver1D(m.x[:, 0], batch=2)
+    s.set_params([prm, prm])
+    u = solver1d.bulk_state(2, s.n, _dev())
+    o = NewtonOpts.steady(maxit=3)
+    out = s.steady(u, np.array([[-12.5], [-0.25]]), o)
+    st = out["status"].tolist()
+    assert st[0] in (1, 2) and st[1] in (0, 1)
+    o2 = NewtonOpts.steady()
+    u = solver1d.bulk_state(2, s.n, _dev())
+    out = s.steady(u, np.array([[-0.25], [-0.25]]), o2)
+    assert out["status"].tolist() == [0, 0]
+
+
+def test_invalid_state_is_an_error(lib):
+    from gmpnp_b200 import solver1d
+    from gmpnp_b200._lib import GmpnpError
+    s = solver1d.Solver1D(np.linspace(0, 1, 9), batch=1)
+    u = solver1d.bulk_state(1, 9, _dev())
+    with pytest.raises(GmpnpError):
+        s.newton(u, u.clone())           # parameters not set
