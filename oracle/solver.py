@@ -196,3 +196,57 @@ def p1_gradient_projection_1d(x, f):
     main[1:] += h / 3
     M = sp.diags([h / 6, main, h / 6], [-1, 0, 1]).tocsc()
     return spla.splu(M).solve(b)
+
+
+# ---------------------------------------------------------------------------------------------
+# 3D pore
+# ---------------------------------------------------------------------------------------------
+
+def march_3d(mesh_x, mesh_cells, prm, bc_dofs, bc_kind, n_steps, rtol=1e-4, atol=1e-4, maxit=50, relax=0.9,
+             sechenov=None):
+    """The reference's 3D loop (3D:782-858): u starts at 0, u_n at (1,..,1,0); damped Newton
+    (relaxation 0.9, 3D:796); after every step the CO2 entry value is re-evaluated from the MEDIANS of
+    the nodal OH/HCO3/CO32/cation values (3D:817-838) via ``sechenov(med_OH, med_HCO3, med_CO32, med_cat)``.
+    Returns (history [n_steps+1, nv, 9], Newton counts, list of CO2 entry values used)."""
+    ncomp = prm.ns + 1
+    disc = Discretisation(mesh_x, mesh_cells, ncomp)
+    nv = disc.nv
+    eq = prm.extras["eq_scaled"]
+    co2 = float(eq[0])
+    table = lambda c: np.array([0.0, prm.V, c, eq[1], eq[2]])
+    u = np.zeros(disc.ndof)
+    un = np.tile(np.array([1.0] * prm.ns + [0.0]), nv)
+    hist = [un.reshape(nv, ncomp).copy()]
+    its, co2s = [], []
+    for _ in range(n_steps):
+        vals = table(co2)[bc_kind.astype(np.int64)]
+        co2s.append(co2)
+        u, k, conv, r0, r = newton(disc, prm, u, un, bc_dofs, vals, rtol=rtol, atol=atol, maxit=maxit, relax=relax)
+        if not conv:
+            raise RuntimeError("Newton solver did not converge")
+        its.append(k)
+        U = u.reshape(nv, ncomp)
+        hist.append(U.copy())
+        if sechenov is not None:
+            co2 = sechenov(np.median(U[:, 1]), np.median(U[:, 2]), np.median(U[:, 3]), np.median(U[:, prm.ns - 1]))
+        un = u.copy()
+    return np.array(hist), its, co2s
+
+
+def steady_3d(mesh_x, mesh_cells, prm, bc_dofs, bc_kind, V_path, co2_entry, u0=None, xtol=1e-12, maxit=50):
+    """Steady 3D equations (kappa = 0) with voltage continuation, full Newton steps, fixed CO2 entry value."""
+    ncomp = prm.ns + 1
+    disc = Discretisation(mesh_x, mesh_cells, ncomp)
+    nv = disc.nv
+    eq = prm.extras["eq_scaled"]
+    ps = prm.with_(kappa=0.0)
+    u = np.tile(np.array([1.0] * prm.ns + [0.0]), nv) if u0 is None else np.asarray(u0, float).reshape(-1).copy()
+    its = []
+    for V in V_path:
+        vals = np.array([0.0, float(V), co2_entry, eq[1], eq[2]])[bc_kind.astype(np.int64)]
+        u, k, conv, r0, r = newton(disc, ps.with_(V=float(V)), u, u, bc_dofs, vals, criterion="increment",
+                                   xtol=xtol, maxit=maxit)
+        if not conv:
+            raise RuntimeError(f"steady Newton failed at V={V} after {k} its (r={r})")
+        its.append(k)
+    return u.reshape(nv, ncomp), its
