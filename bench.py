@@ -1,0 +1,274 @@
+#!/usr/bin/env python
+"""Benchmark of the GMPNP hot path: steady solves/sec on the 1D parameter sweep (BASELINE.json
+config 2: {K,Cs} x 256 voltages x {0.1,0.5,1.0} M x 5 meshes = 7680 steady problems per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" = one pass of the hot path over the whole batch: every sweep point goes from the bulk
+state to its converged steady solution (voltage continuation + Newton, all inside the CUDA
+kernels).  Prints ONE JSON line (see the task contract): `value` = solves/s with inputs resident
+in HBM, `e2e` = the same through the public host API with host buffers (H2D of parameters and
+continuation paths, D2H of every solution profile inside the timed region), `roofline` for the
+fused assemble+eliminate kernel, `cpu_baseline` = the oracle on the box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "GMPNP steady solves/sec (1D sweep)"
+UNIT = "solves/s"
+WORKLOAD = "config2: 1D GMPNP sweep {K,Cs} x 256 V x {0.1,0.5,1.0} M KHCO3 x 5 meshes = 7680 steady solves per GPU"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--voltages", type=int, default=256, help="voltage points per chain (256 = config 2)")
+    ap.add_argument("--cpu-sample", type=int, default=16, help="sweep points timed on the CPU baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle (port of the reference's algorithm class: P1 assembly + sparse LU + Newton)
+# --------------------------------------------------------------------------------------------
+def _cpu_solve_point(args):
+    cation, conc, L_n, V = args
+    import numpy as np
+    from gmpnp_b200 import meshio, params
+    from gmpnp_b200.sweep import voltage_paths
+    from oracle import solver as osolver
+    os.environ["OMP_NUM_THREADS"] = "1"
+    mesh = meshio.load_mesh(params.mesh_name_1d(L_n))
+    prm = params.params_1d(concentration_elec=conc, cation=cation, L_n=L_n, voltage_multiplier=V)
+    path = voltage_paths(np.array([V]), 0.5)[0]
+    path = path[~np.isnan(path)]
+    t = time.perf_counter()
+    try:
+        u, its = osolver.steady_1d(mesh.x[:, 0], prm, path, xtol=1e-12, xtol_path=1e-3)
+        ok = True
+    except RuntimeError:
+        its, ok = [], False
+    return time.perf_counter() - t, sum(its), ok
+
+
+def cpu_sample_points(n_sample, n_voltages):
+    import numpy as np
+    from gmpnp_b200.sweep import config2_points
+    pts = config2_points(n_voltages)
+    rng = np.random.default_rng(0)
+    sel = rng.choice(len(pts), size=min(n_sample, len(pts)), replace=False)
+    return [(pts[i].cation, pts[i].conc, pts[i].L_n, pts[i].V) for i in sorted(sel)]
+
+
+def run_cpu(n_sample, n_voltages, cores=None):
+    import multiprocessing as mp
+    cores = cores or (os.cpu_count() or 1)
+    cores = max(1, min(cores, n_sample))
+    work = cpu_sample_points(n_sample, n_voltages)
+    t = time.perf_counter()
+    with mp.get_context("spawn").Pool(cores) as pool:
+        res = pool.map(_cpu_solve_point, work, chunksize=1)
+    wall = time.perf_counter() - t
+    n_ok = sum(1 for r in res if r[2])
+    return dict(value=len(work) / wall, unit=UNIT, cores=cores, kind="port",
+                sample=f"{len(work)} of the {7680 if n_voltages == 256 else 30 * n_voltages} sweep points (seed 0), "
+                       f"oracle steady_1d (NumPy assembly + SuperLU), {n_ok} converged, wall {wall:.1f} s",
+                newton_iterations=int(sum(r[1] for r in res)))
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        run_cpu(min(args.cpu_sample, os.cpu_count() or 1), args.voltages)
+    info = None
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        info = run_cpu(args.cpu_sample, args.voltages)
+        vals.append(info["value"])
+    T = (time.perf_counter() - t0) / max(1, args.steps)
+    v = sum(vals) / len(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": T * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "CPU oracle port (FEniCS is not installable here); each step "
+                       "= a bounded sample of the sweep on all host cores"},
+            "cpu_baseline": dict(info, value=v),
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [s.strip() for s in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm), "power_w_max": max(float(s[2]) for s in self.samples)}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_arm(args)
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from gmpnp_b200 import sweep
+    from gmpnp_b200.solver1d import NC
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # weak scaling: every rank owns one full config-2 sweep (independent sweep points, no collective
+    # on the data path; one gather of the per-point summaries at the end)
+    pts = sweep.config2_points(args.voltages)
+    sw = sweep.Sweep1D(pts, device=local)
+    n_local = sw.n_points
+
+    # pinned host staging for the e2e arm
+    h_params = [torch.as_tensor(g["packed"]).pin_memory() for g in sw.groups]
+    h_paths = [torch.as_tensor(g["path"]).pin_memory() for g in sw.groups]
+    h_out = [torch.empty(g["solver"].batch, g["solver"].n, NC, dtype=torch.float64).pin_memory() for g in sw.groups]
+    h2d = sum(t.numel() * 8 for t in h_params) + sum(t.numel() * 8 for t in h_paths)
+    d2h = sum(t.numel() * 8 for t in h_out)
+
+    sw.upload()
+    launches0 = sum(g["solver"].launch_count() for g in sw.groups)
+    # ---- resident arm ---------------------------------------------------------------------
+    for _ in range(args.warmup):
+        outs = sw.solve_resident()
+    barrier()
+    launches1 = sum(g["solver"].launch_count() for g in sw.groups)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        outs = sw.solve_resident()
+    ev1.record()
+    barrier()
+    sampler.stop_flag = True
+    ms = ev0.elapsed_time(ev1) / args.steps
+    launches2 = sum(g["solver"].launch_count() for g in sw.groups)
+    n_its, alg_bytes = sw.newton_iterations(outs)
+    status = np.concatenate([o["status"].cpu().numpy() for o in outs])
+    n_conv = int((status == 0).sum())
+
+    # ---- e2e arm: host buffers in, host buffers out, through the public API ---------------
+    def e2e_step():
+        for g, hp, hv in zip(sw.groups, h_params, h_paths):
+            g["solver"].set_params(hp.numpy())                  # H2D of the parameter records
+            g["d_path"].copy_(hv, non_blocking=True)            # H2D of the continuation paths
+        o = sw.solve_resident()
+        for g, ho in zip(sw.groups, h_out):
+            ho.copy_(g["u"], non_blocking=True)                 # D2H of every solution profile
+        torch.cuda.synchronize()
+        return o
+
+    e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cnt = torch.tensor([n_local, n_conv, n_its, alg_bytes], dtype=torch.float64, device=dev)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        n_total, n_conv_total, n_its_total, bytes_total = [float(v) for v in cnt.tolist()]
+    else:
+        n_total, n_conv_total, n_its_total, bytes_total = n_local, n_conv, n_its, alg_bytes
+    ms, ms_e2e = [float(v) for v in t.tolist()]
+
+    if rank == 0:
+        peaks = {}
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk):
+            peaks = json.load(open(pk))
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = (bytes_total / world) / (ms * 1e-3) / 1e9       # per-GPU GB/s of the kernel
+        prof = os.path.join(ROOT, "profiles", "traffic.json")
+        traffic = json.load(open(prof)).get("newton1d_dram_bytes_per_launch") if os.path.exists(prof) else None
+        line = {
+            "metric": METRIC, "value": n_total / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD if args.voltages == 256 else f"reduced sweep ({args.voltages} V/chain)",
+                       "points_per_gpu": n_local, "converged": int(n_conv_total),
+                       "newton_iterations_per_step": int(n_its_total),
+                       "continuation": "dV<=0.5 V_T, xtol 1e-12 (final) / 1e-3 (path)",
+                       "cache": "working set (elimination workspace 10.7 GB/GPU) >> 126 MB L2, no flush needed",
+                       "parallelism": f"sweep points sharded, {world} GPU(s), no data-path collective"},
+            "e2e": {"value": n_total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches2 - launches1),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                         "kernel": "edl1d::newton1d_kernel (5 concurrent launches = one step)",
+                         "algorithmic_bytes_per_step": bytes_total / world},
+            "clocks": sampler.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = run_cpu(args.cpu_sample, args.voltages)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

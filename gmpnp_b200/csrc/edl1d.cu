@@ -575,8 +575,14 @@ newton1d_kernel(int mode, int batch, int n, const double* __restrict__ x, const 
         if (g.c == 0) P[GMPNP_P_KAPPA] = 0.0;
         __syncwarp(g.mask);
         int st = GMPNP_CONVERGED, done = 0;
+        const double xtol_final = opts.xtol;
         for (int s = 0; s < n_stage; ++s) {
-            if (g.c == 0) P[GMPNP_P_V] = Vpath[(long)prob * n_stage + s];
+            const double Vs = Vpath[(long)prob * n_stage + s];
+            if (isnan(Vs)) break;                       // ragged path: this problem is done
+            const bool final_stage = (s + 1 == n_stage) || isnan(Vpath[(long)prob * n_stage + s + 1]);
+            opts.xtol = (final_stage || !(opts.xtol_path > 0.0)) ? xtol_final : opts.xtol_path;
+            __syncwarp(g.mask);
+            if (g.c == 0) P[GMPNP_P_V] = Vs;
             __syncwarp(g.mask);
             // kappa = 0: u_n is never read for its value; pass u itself
             NewtonOut o = newton_solve<PIVOT>(g, L, x, n, up, up, ws, opts);

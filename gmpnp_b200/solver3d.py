@@ -1,0 +1,214 @@
+"""Host-side mirror of the 3D pore hot path (batched problems that share one tet mesh).
+
+Maps on the C-ABI (include/gmpnp.h) and on the reference call sites:
+
+* ``assemble``  -> FFC kernels + SystemAssembler for the forms 3D/MPNP_CO2ER_pore.py:503-769
+* ``spmv``      -> the matrix-vector product inside the linear solve (MUMPS in the reference, 3D:792;
+                   restarted GMRES + block-Jacobi/coarse preconditioner here)
+* ``newton``    -> ``solve(F == 0, u, bcs, {newton, relaxation 0.9})`` 3D:789-799
+* ``march``     -> the pseudo-time loop 3D:782-858 with the Sechenov median update 3D:817-838
+* ``steady``    -> steady equations (kappa = 0) with voltage continuation and the Sechenov fixed point
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, marking, params as _params
+from ._lib import NewtonOpts, check, ptr
+
+NC = 9
+
+
+def bulk_state(batch: int, n: int, device) -> torch.Tensor:
+    """u = (1,...,1,0): the reference's initial u_n (3D:427-432)."""
+    u = torch.ones(batch, n, NC, dtype=torch.float64, device=device)
+    u[:, :, NC - 1] = 0.0
+    return u
+
+
+class Solver3D:
+    def __init__(self, mesh, dir_dofs: np.ndarray, batch: int = 1, device: int = 0):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.GmpnpError("CUDA device required: the GMPNP hot path has no CPU fallback")
+        self.device = torch.device("cuda", int(device))
+        self.mesh = mesh
+        xyz = np.ascontiguousarray(mesh.x, dtype=np.float64)
+        tets = np.ascontiguousarray(mesh.cells, dtype=np.int32)
+        self.dir_dofs = np.ascontiguousarray(dir_dofs, dtype=np.int32)
+        self.n = int(xyz.shape[0])
+        self.n_tet = int(tets.shape[0])
+        self.batch = int(batch)
+        self._h = C.c_void_p()
+        check(self.lib.gmpnp_create_3d(C.byref(self._h), self.device.index,
+                                       xyz.ctypes.data_as(C.POINTER(C.c_double)), self.n,
+                                       tets.ctypes.data_as(C.POINTER(C.c_int)), self.n_tet,
+                                       self.dir_dofs.ctypes.data_as(C.POINTER(C.c_int)), len(self.dir_dofs), 8,
+                                       self.batch), self._h)
+        nb = C.c_int()
+        check(self.lib.gmpnp_pattern_3d(self._h, C.byref(nb), None, None), self._h)
+        self.n_blocks = nb.value
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.gmpnp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def pattern(self):
+        rp = np.zeros(self.n + 1, dtype=np.int32)
+        ci = np.zeros(self.n_blocks, dtype=np.int32)
+        check(self.lib.gmpnp_pattern_3d(self._h, None, rp.ctypes.data_as(C.POINTER(C.c_int)),
+                                        ci.ctypes.data_as(C.POINTER(C.c_int))), self._h)
+        return rp, ci
+
+    def set_params(self, plist):
+        P = np.ascontiguousarray(plist, dtype=np.float64) if isinstance(plist, np.ndarray) \
+            else np.stack([p.pack() for p in plist])
+        assert P.shape == (self.batch, _params.NPAR)
+        check(self.lib.gmpnp_set_params(self._h, P.ctypes.data_as(C.POINTER(C.c_double)), self.batch), self._h)
+
+    def set_dirichlet(self, vals: np.ndarray):
+        vals = np.ascontiguousarray(vals, dtype=np.float64).reshape(self.batch, len(self.dir_dofs))
+        check(self.lib.gmpnp_set_dirichlet_3d(self._h, vals.ctypes.data_as(C.POINTER(C.c_double)), self.batch),
+              self._h)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _chk(self, t):
+        assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+        assert tuple(t.shape) == (self.batch, self.n, NC), tuple(t.shape)
+
+    def assemble(self, u, un, want_F=True, want_J=True):
+        self._chk(u); self._chk(un)
+        F = torch.empty(self.batch, self.n, NC, dtype=torch.float64, device=self.device) if want_F else None
+        J = torch.empty(self.batch, self.n_blocks, NC, NC, dtype=torch.float64, device=self.device) if want_J else None
+        check(self.lib.gmpnp_assemble_3d(self._h, ptr(u), ptr(un), ptr(F), ptr(J), self._stream()), self._h)
+        return F, J
+
+    def spmv(self, J, x):
+        self._chk(x)
+        y = torch.empty_like(x)
+        check(self.lib.gmpnp_spmv_3d(self._h, ptr(J), ptr(x), ptr(y), self._stream()), self._h)
+        return y
+
+    def newton(self, u, un, opts: NewtonOpts | None = None):
+        opts = opts or NewtonOpts.reference_3d()
+        self._chk(u); self._chk(un)
+        dev = self.device
+        it = torch.zeros(self.batch, dtype=torch.int32, device=dev)
+        st = torch.zeros(self.batch, dtype=torch.int32, device=dev)
+        li = torch.zeros(self.batch, dtype=torch.int32, device=dev)
+        r0 = torch.zeros(self.batch, dtype=torch.float64, device=dev)
+        r = torch.zeros(self.batch, dtype=torch.float64, device=dev)
+        check(self.lib.gmpnp_newton_3d(self._h, ptr(u), ptr(un), C.byref(opts), ptr(it), ptr(r0), ptr(r), ptr(li),
+                                       ptr(st), self._stream()), self._h)
+        return dict(iters=it, r0=r0, r=r, lin_iters=li, status=st)
+
+    def median(self, u, comp: int):
+        self._chk(u)
+        med = torch.empty(self.batch, dtype=torch.float64, device=self.device)
+        check(self.lib.gmpnp_median_3d(self._h, ptr(u), int(comp), ptr(med), self._stream()), self._h)
+        return med
+
+    def launch_count(self) -> int:
+        return int(self.lib.gmpnp_launch_count(self._h))
+
+
+class PoreProblem:
+    """One pore geometry + a batch of parameter points: Dirichlet sets per the reference's marking
+    (3D:335-379, 460-467) and the drivers built on :class:`Solver3D`."""
+
+    def __init__(self, mesh, L: float, R: float, plist, device: int = 0):
+        self.mesh, self.L, self.R = mesh, L, R
+        self.plist = list(plist)
+        self.dofs, self.kind, self.info = marking.dirichlet_sets(mesh, L, R)
+        self.solver = Solver3D(mesh, self.dofs, batch=len(self.plist), device=device)
+        self.solver.set_params(self.plist)
+        self.device = self.solver.device
+
+    def dirichlet_values(self, co2_scaled, V=None):
+        vals = []
+        for b, p in enumerate(self.plist):
+            eq = p.extras["eq_scaled"]
+            v = p.V if V is None else V[b]
+            vals.append(marking.dirichlet_values(self.kind, v, co2_scaled[b], eq[1], eq[2]))
+        return np.stack(vals)
+
+    def march(self, n_steps: int, opts: NewtonOpts | None = None, history=True):
+        """The reference's loop (3D:782-858): u = 0, u_n = (1,..,1,0); per step one damped Newton solve,
+        then the CO2 entry Dirichlet value is re-evaluated from the nodal MEDIANS (3D:817-838)."""
+        opts = opts or NewtonOpts.reference_3d()
+        s = self.solver
+        B = s.batch
+        u = torch.zeros(B, s.n, NC, dtype=torch.float64, device=self.device)
+        un = bulk_state(B, s.n, self.device)
+        co2 = [float(p.extras["eq_scaled"][0]) for p in self.plist]
+        hist, its, lin, co2s = [un.cpu().numpy().copy()], [], [], []
+        for _ in range(n_steps):
+            s.set_dirichlet(self.dirichlet_values(co2))
+            co2s.append(list(co2))
+            out = s.newton(u, un, opts)
+            st = out["status"].cpu().numpy()
+            if (st != 0).any():
+                raise RuntimeError(f"Newton solver did not converge: status {st.tolist()}")   # dolfin raises too
+            its.append(out["iters"].cpu().numpy().copy())
+            lin.append(out["lin_iters"].cpu().numpy().copy())
+            med = [s.median(u, c).cpu().numpy() for c in (1, 2, 3, 7)]
+            co2 = [_params.sechenov_co2_scaled(p, med[0][b], med[1][b], med[2][b], med[3][b])
+                   for b, p in enumerate(self.plist)]
+            if history:
+                hist.append(u.cpu().numpy().copy())
+            un.copy_(u)
+        return dict(u=u, history=np.array(hist) if history else None, iters=np.array(its), lin_iters=np.array(lin),
+                    co2_entry=np.array(co2s))
+
+    def steady(self, V_path: np.ndarray, co2_scaled=None, opts: NewtonOpts | None = None, u0=None,
+               sechenov_fixed_point: bool = False, fp_tol: float = 1e-12, fp_maxit: int = 30):
+        """Steady equations with voltage continuation (V_path [batch, nV]); optionally iterate the
+        Sechenov CO2 entry value to its fixed point at the final voltage."""
+        opts = opts or NewtonOpts.steady()
+        s = self.solver
+        B = s.batch
+        V_path = np.asarray(V_path, dtype=np.float64).reshape(B, -1)
+        u = bulk_state(B, s.n, self.device) if u0 is None else u0
+        co2 = [float(p.extras["eq_scaled"][0]) for p in self.plist] if co2_scaled is None else list(co2_scaled)
+        its = []
+        packed = np.stack([p.pack() for p in self.plist])
+        packed[:, _params.P_KAPPA] = 0.0
+
+        def solve_at(V):
+            P = packed.copy()
+            P[:, _params.P_V] = V
+            s.set_params(P)
+            s.set_dirichlet(self.dirichlet_values(co2, V))
+            out = s.newton(u, u, opts)
+            st = out["status"].cpu().numpy()
+            if (st != 0).any():
+                raise RuntimeError(f"steady Newton failed at V={V}: status {st.tolist()}")
+            its.append(out["iters"].cpu().numpy().copy())
+            return out
+
+        for k in range(V_path.shape[1]):
+            solve_at(V_path[:, k])
+        n_fp = 0
+        if sechenov_fixed_point:
+            for n_fp in range(1, fp_maxit + 1):
+                med = [s.median(u, c).cpu().numpy() for c in (1, 2, 3, 7)]
+                new = [_params.sechenov_co2_scaled(p, med[0][b], med[1][b], med[2][b], med[3][b])
+                       for b, p in enumerate(self.plist)]
+                delta = max(abs(a - b) / abs(a) for a, b in zip(new, co2))
+                co2 = new
+                if delta <= fp_tol:
+                    break
+                solve_at(V_path[:, -1])
+        return dict(u=u, iters=np.array(its), co2_entry=np.array(co2), fixed_point_iterations=n_fp)

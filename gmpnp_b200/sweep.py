@@ -1,0 +1,182 @@
+"""Batched parameter sweeps of the 1D steady problem (BASELINE.json config 2).
+
+The reference runs one sweep point per process ("submit multiple jobs on a computational
+cluster", README.md:37; one ``solve_EDL`` call per CLI invocation, 1D/MPNP_CO2ER_EDL.py:1105).
+Here a sweep is a batch: every point is an independent steady problem with its own voltage
+continuation path, all points that share a mesh go through ONE kernel launch, and the sweep
+shards across GPUs by point with no data-path collective (results are gathered at the end).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import meshio, params as _params
+from ._lib import NewtonOpts
+from .solver1d import Solver1D, bulk_state, pack_1d, NC
+
+CONFIG2_CATIONS = ("K", "Cs")
+CONFIG2_CONCS = (0.1, 0.5, 1.0)
+CONFIG2_LN = (1e-6, 5e-6, 10e-6, 50e-6, 200e-6)
+CONFIG2_NV = 256
+CONFIG2_VMAX = -12.5
+
+
+@dataclass
+class SweepPoint:
+    cation: str
+    conc: float
+    L_n: float
+    V: float
+    index: int = 0
+
+
+def config2_points(n_voltages: int = CONFIG2_NV, meshes=CONFIG2_LN, concs=CONFIG2_CONCS,
+                   cations=CONFIG2_CATIONS, vmax: float = CONFIG2_VMAX):
+    """{K, Cs} x n_voltages (V_k = vmax (k+1)/n) x {0.1, 0.5, 1.0} M x 5 meshes (SURVEY 8d cfg 2)."""
+    pts = []
+    for L_n in meshes:
+        for k in range(n_voltages):
+            V = vmax * (k + 1) / n_voltages
+            for conc in concs:
+                for cat in cations:
+                    pts.append(SweepPoint(cat, conc, L_n, V, len(pts)))
+    return pts
+
+
+def shard(points, rank: int, world: int):
+    """Static shard by sweep point: every rank gets the same mix of meshes and voltages."""
+    return points[rank::world]
+
+
+def voltage_paths(Vs: np.ndarray, dv_max: float) -> np.ndarray:
+    """Ragged continuation paths, NaN-terminated: point b walks 0 -> V_b in ceil(|V_b|/dv_max) equal steps."""
+    Vs = np.asarray(Vs, dtype=np.float64)
+    nst = np.maximum(1, np.ceil(np.abs(Vs) / dv_max - 1e-12).astype(int))
+    nV = int(nst.max())
+    path = np.full((len(Vs), nV), np.nan)
+    for b, (V, n) in enumerate(zip(Vs, nst)):
+        path[b, :n] = V * np.arange(1, n + 1) / n
+    return path
+
+
+class Sweep1D:
+    """All sweep points of one rank, grouped by mesh into one :class:`Solver1D` each."""
+
+    def __init__(self, points, device: int = 0, utilities_dir=None, dv_max: float = 0.5,
+                 xtol: float = 1e-12, xtol_path: float = 1e-3, maxit: int = 50):
+        self.points = list(points)
+        self.device = torch.device("cuda", int(device))
+        self.dv_max, self.xtol, self.xtol_path, self.maxit = dv_max, xtol, xtol_path, maxit
+        self.groups = []
+        by_mesh = {}
+        for i, p in enumerate(self.points):
+            by_mesh.setdefault(p.L_n, []).append(i)
+        pcache = {}
+        # longest mesh first and, inside a mesh, longest continuation path first (LPT order: the
+        # block scheduler hands out blocks in index order, so the critical-path problems start at t=0);
+        # neighbours in a warp still get similar path lengths
+        for L_n, idx in sorted(by_mesh.items(), key=lambda kv: -meshio.load_mesh(_params.mesh_name_1d(kv[0]), utilities_dir).num_vertices):
+            idx = sorted(idx, key=lambda i: (-abs(self.points[i].V), self.points[i].conc, self.points[i].cation))
+            mesh = meshio.load_mesh(_params.mesh_name_1d(L_n), utilities_dir)
+            plist = []
+            for i in idx:
+                p = self.points[i]
+                key = (p.cation, p.conc, L_n)
+                if key not in pcache:
+                    pcache[key] = pack_1d(_params.params_1d(concentration_elec=p.conc, cation=p.cation, L_n=L_n,
+                                                            voltage_multiplier=0.0, utilities_dir=utilities_dir))
+                rec = pcache[key].copy()
+                rec[_params.P_V] = p.V
+                plist.append(rec)
+            packed = np.stack(plist)
+            solver = Solver1D(mesh.x[:, 0], batch=len(idx), device=self.device.index)
+            path = voltage_paths(np.array([self.points[i].V for i in idx]), dv_max)
+            self.groups.append(dict(L_n=L_n, idx=np.array(idx), solver=solver, packed=packed, path=path,
+                                    stream=torch.cuda.Stream(self.device)))
+        self.n_points = len(self.points)
+
+    # -- device-resident solve (inputs already in HBM) -----------------------------------------
+    def upload(self):
+        for g in self.groups:
+            g["solver"].set_params(g["packed"])
+            g["d_path"] = torch.as_tensor(g["path"], device=self.device)
+            g["u"] = torch.empty(g["solver"].batch, g["solver"].n, NC, dtype=torch.float64, device=self.device)
+
+    def solve_resident(self):
+        """One pass of the hot path over the whole batch: every point from the bulk state to its
+        converged steady solution.  One launch per mesh, on concurrent streams."""
+        opts = NewtonOpts.steady(xtol=self.xtol, maxit=self.maxit, xtol_path=self.xtol_path)
+        cur = torch.cuda.current_stream(self.device)
+        outs = []
+        for g in self.groups:
+            st = g["stream"]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                u = g["u"]
+                u.fill_(1.0)
+                u[:, :, NC - 1] = 0.0
+                outs.append(g["solver"].steady(u, g["d_path"], opts))
+        for g in self.groups:
+            cur.wait_stream(g["stream"])
+        self.last = outs
+        return outs
+
+    def retry_failed(self, outs, max_rounds: int = 3):
+        """Points whose Newton failed (status != 0) are re-run from bulk with a halved voltage step
+        (failure handling: per-problem status, never abort the batch)."""
+        n_retry = 0
+        for g, out in zip(self.groups, outs):
+            status = out["status"].cpu().numpy()
+            bad = np.nonzero(status != 0)[0]
+            dv = self.dv_max
+            rounds = 0
+            while len(bad) and rounds < max_rounds:
+                dv *= 0.5
+                rounds += 1
+                n_retry += len(bad)
+                Vs = np.array([self.points[g["idx"][b]].V for b in bad])
+                sub = Solver1D(g["solver"].x, batch=len(bad), device=self.device.index)
+                sub.set_params(g["packed"][bad])
+                u = bulk_state(len(bad), sub.n, self.device)
+                o = sub.steady(u, voltage_paths(Vs, dv),
+                               NewtonOpts.steady(xtol=self.xtol, maxit=self.maxit, xtol_path=self.xtol_path))
+                st = o["status"].cpu().numpy()
+                ok = st == 0
+                g["u"][torch.as_tensor(bad[ok], device=self.device)] = u[torch.as_tensor(np.nonzero(ok)[0], device=self.device)]
+                out["status"][torch.as_tensor(bad[ok], device=self.device)] = 0
+                bad = bad[~ok]
+                sub.close()
+        return n_retry
+
+    def newton_iterations(self, outs):
+        """Total Newton iterations and the algorithmic HBM bytes they imply (1072 B per node per
+        iteration for the fused assemble+eliminate sweep pair)."""
+        its, nbytes = 0, 0
+        for g, out in zip(self.groups, outs):
+            k = int(out["iters"].sum().item())
+            its += k
+            nbytes += k * 1072 * g["solver"].n
+        return its, nbytes
+
+    def results(self, outs):
+        """Gather per-point summaries on the host: status, OHP nodal values, OHP field."""
+        res = np.zeros((self.n_points, 10))
+        for g, out in zip(self.groups, outs):
+            s = g["solver"]
+            f = s.field(g["u"])[:, 0].cpu().numpy()
+            u0 = g["u"][:, 0, :].cpu().numpy()
+            st = out["status"].cpu().numpy()
+            it = out["iters"].sum(dim=1).cpu().numpy()
+            res[g["idx"], 0] = st
+            res[g["idx"], 1] = it
+            res[g["idx"], 2:9] = u0
+            res[g["idx"], 9] = f
+        return res
+
+    def close(self):
+        for g in self.groups:
+            g["solver"].close()

@@ -65,6 +65,8 @@ typedef struct gmpnp_newton_opts {
     int    lin_maxit;   /* 3D: max GMRES iterations per Newton step                        */
     int    lin_restart; /* 3D: GMRES restart length                                        */
     double lin_rtol;    /* 3D: GMRES relative residual tolerance                           */
+    double xtol_path;   /* continuation: increment tolerance of the intermediate stages
+                           (<= 0: use xtol everywhere); the final stage always uses xtol    */
 } gmpnp_newton_opts;
 
 /* per-problem status codes written to status[] */
@@ -120,6 +122,7 @@ int gmpnp_march_1d(gmpnp_handle* h, double* d_u, double* d_un, int n_steps,
 
 /* Steady equations (kappa forced to 0) with voltage continuation: for s < n_V the OHP
  * potential is d_Vpath[problem][s] and Newton restarts from the previous stage's solution.
+ * A NaN entry ends that problem's path early (ragged paths in one batch).
  * d_iters (optional) [batch][n_V]; d_stage (optional) [batch] = number of stages completed. */
 int gmpnp_steady_continuation_1d(gmpnp_handle* h, double* d_u, const double* d_Vpath, int n_V,
                                  const gmpnp_newton_opts* opts, int* d_iters, int* d_stage,

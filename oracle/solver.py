@@ -158,7 +158,7 @@ def march_1d(x, prm, n_steps, H_OHP=None, rtol=1e-4, atol=1e-4, maxit=50):
     return np.array(hist), its, frac
 
 
-def steady_1d(x, prm, V_path, u0=None, xtol=1e-12, maxit=50):
+def steady_1d(x, prm, V_path, u0=None, xtol=1e-12, maxit=50, xtol_path=0.0):
     """Steady equations (kappa = 0) with voltage continuation along ``V_path``.
     Starts from the bulk state unless ``u0`` is given.  Returns (u[nv, ncomp] at the last V,
     list of Newton counts)."""
@@ -170,11 +170,13 @@ def steady_1d(x, prm, V_path, u0=None, xtol=1e-12, maxit=50):
     ps = prm.with_(kappa=0.0)
     u = np.tile(np.array([1.0] * prm.ns + [0.0]), nv) if u0 is None else np.asarray(u0, float).reshape(-1).copy()
     its = []
-    for V in V_path:
+    V_path = list(V_path)
+    for s_, V in enumerate(V_path):
         pv = ps.with_(V=float(V))
         bc_dofs, bc_vals = bc_1d(nv, ncomp, float(V))
+        tol = xtol if (s_ + 1 == len(V_path) or not xtol_path > 0) else xtol_path
         u, k, conv, r0, r = newton(disc, pv, u, u, bc_dofs, bc_vals, point_flux=pv.jflux,
-                                   criterion="increment", xtol=xtol, maxit=maxit)
+                                   criterion="increment", xtol=tol, maxit=maxit)
         if not conv:
             raise RuntimeError(f"steady Newton failed at V={V} after {k} its (r={r})")
         its.append(k)

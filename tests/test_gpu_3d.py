@@ -1,0 +1,170 @@
+"""Parity of the CUDA 3D pore path (through the C-ABI) against the oracle and the golden vectors."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, admissible_state, cube_tet_mesh
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda", 0)
+
+
+def _t(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=_dev())
+
+
+def rel_l2(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def bsr_to_dense(J, rp, ci, n):
+    A = np.zeros((n * 9, n * 9))
+    for r in range(n):
+        for s in range(rp[r], rp[r + 1]):
+            A[9 * r:9 * r + 9, 9 * ci[s]:9 * ci[s] + 9] = J[s]
+    return A
+
+
+def test_assemble_3d_matches_golden_entrywise(lib):
+    from gmpnp_b200 import meshio, params, solver3d
+    g = np.load(os.path.join(GOLDEN, "assemble_3d.npz"))
+    mesh = meshio.Mesh(x=g["x"], cells=g["cells"])
+    prm = params.params_3d(L=50e-9, R=5e-9)
+    s = solver3d.Solver3D(mesh, g["dofs"].astype(np.int32), batch=2)
+    s.set_params([prm, prm])
+    s.set_dirichlet(np.stack([g["vals"], g["vals"]]))
+    u, un = _t(np.stack([g["u"]] * 2)), _t(np.stack([g["un"]] * 2))
+    F, J = s.assemble(u, un)
+    torch.cuda.synchronize()
+    rp, ci = s.pattern()
+    n = mesh.num_vertices
+    A = bsr_to_dense(J[0].cpu().numpy(), rp, ci, n)
+    Ao = g["A"]
+    rowscale = np.abs(Ao).max(axis=1, keepdims=True)
+    # the BSR pattern covers every significant non-zero of the oracle matrix
+    assert np.all((np.abs(A) > 0)[np.abs(Ao) > 1e-12 * rowscale])
+    assert (np.abs(A - Ao) <= 1e-11 * rowscale).all()
+    Fo = g["F"]
+    assert np.abs(F[0].cpu().numpy() - Fo).max() <= 1e-11 * np.abs(Fo).max()
+    assert torch.equal(J[0], J[1]) and torch.equal(F[0], F[1])
+    # SpMV against the dense product
+    x = np.random.default_rng(3).normal(size=(2, n, 9))
+    y = s.spmv(J, _t(x)).cpu().numpy()
+    yo = (Ao @ x[0].ravel()).reshape(n, 9)
+    assert np.abs(y[0] - yo).max() <= 1e-12 * np.abs(yo).max()
+
+
+def test_assemble_3d_vs_oracle_random_params(lib):
+    from gmpnp_b200 import params, solver3d
+    from oracle import solver as osolver
+    mesh = cube_tet_mesh(2, scale=(0.1, 0.1, 1.0))
+    n = mesh.num_vertices
+    plist = [params.params_3d(L=50e-9, R=5e-9, voltage_multiplier=-2.0),
+             params.params_3d(L=100e-9, R=5e-9, concentration_elec=0.5, time_step=1e-5)]
+    rng = np.random.default_rng(5)
+    us = np.stack([admissible_state(rng, n, 8, p.nu, V=-5.0) for p in plist])
+    uns = np.stack([admissible_state(rng, n, 8, p.nu, V=-5.0) for p in plist])
+    dofs = np.array([8, 17, 9 * (n - 1) + 8, 9 * (n - 1) + 4], dtype=np.int32)
+    vals = np.array([[0.0, 0.0, -2.0, 2.8], [0.0, 0.0, -1.0, 3.0]])
+    s = solver3d.Solver3D(mesh, dofs, batch=2)
+    s.set_params(plist)
+    s.set_dirichlet(vals)
+    F, J = s.assemble(_t(us), _t(uns))
+    rp, ci = s.pattern()
+    disc = osolver.Discretisation(mesh.x, mesh.cells, 9)
+    for b, p in enumerate(plist):
+        Fo = osolver.apply_bc_residual(disc.residual(us[b].ravel(), uns[b].ravel(), p), us[b].ravel(),
+                                       dofs.astype(np.int64), vals[b])
+        Ao = osolver.apply_bc_matrix(disc.jacobian(us[b].ravel(), p), dofs.astype(np.int64)).toarray()
+        A = bsr_to_dense(J[b].cpu().numpy(), rp, ci, n)
+        assert (np.abs(A - Ao) <= 1e-11 * np.abs(Ao).max(axis=1, keepdims=True)).all()
+        assert np.abs(F[b].cpu().numpy().ravel() - Fo).max() <= 1e-11 * np.abs(Fo).max()
+
+
+def test_newton_3d_small_mesh_vs_oracle(lib):
+    """Damped Newton (relaxation 0.9) + GMRES on a small box: same count, same iterate as the oracle's LU."""
+    from gmpnp_b200 import params, solver3d
+    from gmpnp_b200._lib import NewtonOpts
+    from oracle import solver as osolver
+    mesh = cube_tet_mesh(3, scale=(0.1, 0.1, 1.0))
+    n = mesh.num_vertices
+    prm = params.params_3d(L=50e-9, R=5e-9)
+    z = mesh.x[:, 2]
+    r2 = (mesh.x[:, 0] - 0.05) ** 2 + (mesh.x[:, 1] - 0.05) ** 2
+    dofs, vals = [], []
+    for v in range(n):
+        if z[v] < 1e-12:
+            dofs += [9 * v + 8, 9 * v + 4, 9 * v + 5, 9 * v + 6]; vals += [0.0, 2.87, 100.0, 100.0]
+        elif z[v] > 1 - 1e-12:
+            dofs += [9 * v + 8]; vals += [0.0]
+        elif r2[v] > 0.0012:
+            dofs += [9 * v + 8]; vals += [-1.0]
+    dofs = np.array(dofs, dtype=np.int32); vals = np.array(vals)
+    s = solver3d.Solver3D(mesh, dofs, batch=1)
+    s.set_params([prm]); s.set_dirichlet(vals[None])
+    u = torch.zeros(1, n, 9, dtype=torch.float64, device=_dev())
+    un = solver3d.bulk_state(1, n, _dev())
+    out = s.newton(u, un, NewtonOpts.reference_3d())
+    disc = osolver.Discretisation(mesh.x, mesh.cells, 9)
+    uo, k, conv, r0, r = osolver.newton(disc, prm, np.zeros(disc.ndof), un[0].cpu().numpy().ravel(),
+                                        dofs.astype(np.int64), vals, relax=0.9)
+    assert conv and int(out["status"][0]) == 0
+    assert int(out["iters"][0]) == k
+    assert abs(float(out["r0"][0]) - r0) <= 1e-10 * r0
+    got = u[0].cpu().numpy()
+    for c in range(9):
+        assert rel_l2(got[:, c], uo.reshape(n, 9)[:, c]) < 1e-8
+
+
+def test_median_matches_numpy(lib):
+    from gmpnp_b200 import meshio, solver3d
+    mesh = meshio.load_mesh("L_50_R_5")
+    s = solver3d.Solver3D(mesh, np.array([8], dtype=np.int32), batch=2)
+    u = torch.rand(2, s.n, 9, dtype=torch.float64, device=_dev())
+    for comp in (1, 7):
+        med = s.median(u, comp).cpu().numpy()
+        assert np.array_equal(med, np.median(u[:, :, comp].cpu().numpy(), axis=1))
+    mesh2 = meshio.load_mesh("L_50_R_2")          # even vertex count: mean of the two middle values
+    assert mesh2.num_vertices % 2 == 0
+    s2 = solver3d.Solver3D(mesh2, np.array([8], dtype=np.int32), batch=1)
+    u2 = torch.rand(1, s2.n, 9, dtype=torch.float64, device=_dev())
+    assert np.array_equal(s2.median(u2, 3).cpu().numpy(), np.median(u2[:, :, 3].cpu().numpy(), axis=1))
+
+
+def test_config3_reference_march_two_steps(lib):
+    """BASELINE config 3: L_50_R_5, as-executed BCs, relaxation 0.9: Newton counts and iterates of the first
+    two reference time steps, incl. the Sechenov CO2 entry update between them."""
+    from gmpnp_b200 import meshio, params, solver3d
+    g = np.load(os.path.join(GOLDEN, "march_3d_L50R5.npz"))
+    mesh = meshio.load_mesh("L_50_R_5")
+    prm = params.params_3d(L=50e-9, R=5e-9)
+    pp = solver3d.PoreProblem(mesh, 50e-9, 5e-9, [prm])
+    assert pp.info["phi_V_verts"] == 1372 and pp.info["entry_gas_verts"] == 71
+    out = pp.march(2)
+    assert np.abs(out["iters"][:, 0] - g["its"]).max() <= 1, (out["iters"], g["its"])
+    assert np.allclose(out["co2_entry"][:, 0], g["co2"], rtol=1e-9)
+    for step, key in ((1, "step1"), (2, "step2")):
+        for c in range(9):
+            assert rel_l2(out["history"][step][0][:, c], g[key][:, c]) < 1e-7, (step, c)
+
+
+def test_config3_steady_matches_golden(lib):
+    from gmpnp_b200 import meshio, params, solver3d
+    from gmpnp_b200._lib import NewtonOpts
+    g = np.load(os.path.join(GOLDEN, "steady_3d_L50R5.npz"))
+    mesh = meshio.load_mesh("L_50_R_5")
+    prm = params.params_3d(L=50e-9, R=5e-9)
+    pp = solver3d.PoreProblem(mesh, 50e-9, 5e-9, [prm])
+    o = NewtonOpts.steady(xtol=1e-11)
+    out = pp.steady(np.array([[-0.5, -1.0]]), opts=o)
+    got = out["u"][0].cpu().numpy()
+    for c in range(9):
+        assert rel_l2(got[:, c], g["u"][:, c]) < 1e-8, c
+    assert np.abs(out["iters"][:, 0] - g["its"]).max() <= 1
