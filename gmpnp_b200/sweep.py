@@ -52,6 +52,29 @@ def shard(points, rank: int, world: int):
     return points[rank::world]
 
 
+def gather_results(local: "torch.Tensor", local_index: "torch.Tensor", n_total: int, world: int):
+    """The one collective of a sharded sweep: all ranks contribute their per-point summary rows
+    (``local`` [n_local, k]) and the global point indices they own; every rank gets the assembled
+    [n_total, k] table.  Works on the gloo (CPU tensors) and nccl (CUDA tensors) backends."""
+    import torch.distributed as dist
+    if world == 1 or not dist.is_initialized():
+        out = torch.zeros(n_total, local.shape[1], dtype=local.dtype, device=local.device)
+        out[local_index.long()] = local
+        return out
+    n_max = (n_total + world - 1) // world
+    k = local.shape[1]
+    pad = torch.full((n_max, k + 1), -1.0, dtype=torch.float64, device=local.device)
+    pad[: local.shape[0], :k] = local.to(torch.float64)
+    pad[: local.shape[0], k] = local_index.to(torch.float64)
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad)
+    out = torch.zeros(n_total, k, dtype=torch.float64, device=local.device)
+    for b in bufs:
+        valid = b[:, k] >= 0
+        out[b[valid, k].long()] = b[valid, :k]
+    return out
+
+
 def voltage_paths(Vs: np.ndarray, dv_max: float) -> np.ndarray:
     """Ragged continuation paths, NaN-terminated: point b walks 0 -> V_b in ceil(|V_b|/dv_max) equal steps."""
     Vs = np.asarray(Vs, dtype=np.float64)
@@ -67,10 +90,12 @@ class Sweep1D:
     """All sweep points of one rank, grouped by mesh into one :class:`Solver1D` each."""
 
     def __init__(self, points, device: int = 0, utilities_dir=None, dv_max: float = 0.5,
-                 xtol: float = 1e-12, xtol_path: float = 1e-3, maxit: int = 50):
+                 xtol: float = 1e-12, xtol_path: float = 1e-1, maxit: int = 50, jac_rule: int = 1,
+                 pivot: int = 1):
         self.points = list(points)
         self.device = torch.device("cuda", int(device))
         self.dv_max, self.xtol, self.xtol_path, self.maxit = dv_max, xtol, xtol_path, maxit
+        self.jac_rule, self.pivot = jac_rule, pivot
         self.groups = []
         by_mesh = {}
         for i, p in enumerate(self.points):
@@ -99,6 +124,11 @@ class Sweep1D:
                                     stream=torch.cuda.Stream(self.device)))
         self.n_points = len(self.points)
 
+    def opts(self):
+        o = NewtonOpts.steady(xtol=self.xtol, maxit=self.maxit, xtol_path=self.xtol_path, jac_rule=self.jac_rule)
+        o.pivot = self.pivot
+        return o
+
     # -- device-resident solve (inputs already in HBM) -----------------------------------------
     def upload(self):
         for g in self.groups:
@@ -109,7 +139,7 @@ class Sweep1D:
     def solve_resident(self):
         """One pass of the hot path over the whole batch: every point from the bulk state to its
         converged steady solution.  One launch per mesh, on concurrent streams."""
-        opts = NewtonOpts.steady(xtol=self.xtol, maxit=self.maxit, xtol_path=self.xtol_path)
+        opts = self.opts()
         cur = torch.cuda.current_stream(self.device)
         outs = []
         for g in self.groups:
@@ -142,8 +172,7 @@ class Sweep1D:
                 sub = Solver1D(g["solver"].x, batch=len(bad), device=self.device.index)
                 sub.set_params(g["packed"][bad])
                 u = bulk_state(len(bad), sub.n, self.device)
-                o = sub.steady(u, voltage_paths(Vs, dv),
-                               NewtonOpts.steady(xtol=self.xtol, maxit=self.maxit, xtol_path=self.xtol_path))
+                o = sub.steady(u, voltage_paths(Vs, dv), self.opts())
                 st = o["status"].cpu().numpy()
                 ok = st == 0
                 g["u"][torch.as_tensor(bad[ok], device=self.device)] = u[torch.as_tensor(np.nonzero(ok)[0], device=self.device)]

@@ -67,6 +67,11 @@ typedef struct gmpnp_newton_opts {
     double lin_rtol;    /* 3D: GMRES relative residual tolerance                           */
     double xtol_path;   /* continuation: increment tolerance of the intermediate stages
                            (<= 0: use xtol everywhere); the final stage always uses xtol    */
+    int    jac_rule;    /* quadrature of the Jacobian: 0 = FFC's choice (degree 4: 3-point Gauss in 1D,
+                           14-point Keast in 3D -- the reference's iteration path), 1 = the residual's
+                           rule (exact derivative of the discrete F: quadratic convergence; same
+                           converged solution, which depends on F's rule only)              */
+    int    reserved;
 } gmpnp_newton_opts;
 
 /* per-problem status codes written to status[] */

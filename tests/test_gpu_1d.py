@@ -207,6 +207,36 @@ def test_steady_continuation_matches_golden_50um(lib):
         assert abs(field - g[f"ohp_{V}"][0]) <= 1e-8 * abs(g[f"ohp_{V}"][0])
 
 
+def test_consistent_jacobian_same_solution_fewer_iterations(lib):
+    """jac_rule=1 (Jacobian integrated with the residual's rule = exact derivative of the discrete F)
+    converges to the same discrete solution -- which depends on F's rule only -- in
+    fewer Newton iterations than the FFC rule pair."""
+    from gmpnp_b200 import meshio, params, solver1d
+    from gmpnp_b200._lib import NewtonOpts
+    g = np.load(os.path.join(GOLDEN, "steady_50um.npz"))
+    m = meshio.load_mesh("1D_variable_50um_mesh_5990")
+    prm = params.params_1d()
+    targets = [-5.0, -12.5]
+    Vpath = np.full((2, 25), np.nan)
+    for b, V in enumerate(targets):
+        steps = int(round(abs(V) / 0.5))
+        Vpath[b, :steps] = -0.5 * np.arange(1, steps + 1)
+    its = {}
+    for rule in (0, 1):
+        s = solver1d.Solver1D(m.x[:, 0], batch=2)
+        s.set_params([prm, prm])
+        u = solver1d.bulk_state(2, s.n, _dev())
+        out = s.steady(u, Vpath, NewtonOpts.steady(xtol=1e-12, xtol_path=1e-3, jac_rule=rule))
+        assert out["status"].tolist() == [0, 0]
+        assert out["stages"].tolist() == [10, 25]
+        got = u.cpu().numpy()
+        for b, V in enumerate(targets):
+            for c in range(7):
+                assert rel_l2(got[b, :, c], g[f"u_{V}"][:, c]) < 1e-8, (rule, V, c)
+        its[rule] = int(out["iters"].sum())
+    assert its[1] < its[0], its
+
+
 def test_pivoting_off_agrees(lib):
     from gmpnp_b200 import meshio, params, solver1d
     from gmpnp_b200._lib import NewtonOpts

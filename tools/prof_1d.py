@@ -21,12 +21,13 @@ ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--pivot", type=int, default=1)
 ap.add_argument("--dv", type=float, default=0.5)
 ap.add_argument("--xtol_path", type=float, default=1e-3)
+ap.add_argument("--jac_rule", type=int, default=1)
 a = ap.parse_args()
 
 pts = sweep.config2_points(a.voltages, meshes=tuple(a.mesh))
 sw = sweep.Sweep1D(pts, device=0, dv_max=a.dv, xtol_path=a.xtol_path)
 sw.upload()
-opts = NewtonOpts.steady(xtol=1e-12, maxit=50, xtol_path=a.xtol_path)
+opts = NewtonOpts.steady(xtol=1e-12, maxit=50, xtol_path=a.xtol_path, jac_rule=a.jac_rule)
 opts.pivot = a.pivot
 for g in sw.groups:
     s = g["solver"]
