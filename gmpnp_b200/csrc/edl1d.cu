@@ -244,6 +244,11 @@ struct Group {
     unsigned mask;    // participation mask of the 8 lanes
     int base;         // first lane of the group inside the warp
     double* sm;       // per-group shared memory
+    // two-sided elimination: two groups (a "pair", 16 lanes) share one problem
+    int half;         // 0: sweeps down from node 0; 1: sweeps up from node n-1
+    unsigned pmask;   // participation mask of the pair
+    int pbase;        // first lane of the pair
+    double* psm;      // pair-shared merge area [8][8]
 };
 
 // publish this lane's component of a node (already in a register) in sU[slot] and give every lane
@@ -262,62 +267,135 @@ __device__ __forceinline__ void load_node(const Group& g, const double* __restri
     stage_node(g, (g.c < NC) ? up[node * NC + g.c] : 1.0, slot, U);
 }
 
-// One forward sweep over the block rows: assemble row k just in time, eliminate, store
-// (C'_k, d'_k).  Returns ||b||_2^2 (valid in every lane).  `factor` = false does the
-// residual only (no Jacobian columns, no elimination, no stores).
-//
-// Elimination of row k: B' = B - A C'_{k-1}, d' = d - A d'_{k-1}, then Gauss-Jordan on [B' | C | d'].
-// Lane c<7 holds column c of B' and of C, lane 7 holds d'.  Step j broadcasts pivot column j from lane j
-// by shuffles; every lane repeats the (cheap) pivot search so all agree on the pivot row without any
-// shared-memory round trip; rows are swapped physically so later steps index registers statically.
+// Elimination of one block row: B' = B - A X_prev (X_prev = previous row's eliminated coupling block /
+// rhs), then Gauss-Jordan on [B' | C | d'].  Lane c<7 holds column c of A, B' and C (C in Y), lane 7 holds d'
+// (in Y).  Step j broadcasts pivot column j from lane j by shuffles; every lane repeats the (cheap) pivot
+// search so all agree on the pivot row without a shared-memory round trip; rows are swapped physically so
+// all register indexing is static.  On exit Y = eliminated coupling column (lanes<7) / rhs (lane 7).
+template <bool PIVOT>
+__device__ __forceinline__ void eliminate_row(const Group& g, bool with_prev, const double (&A)[NC], double (&B)[NC],
+                                              double (&Y)[NC], const double (&X)[NC], int& singular) {
+    double* sA = g.sm + SM_A;
+    const int c = g.c;
+    if (with_prev) {
+        if (c < NC) {
+#pragma unroll
+            for (int i = 0; i < NC; ++i) sA[c * 8 + i] = A[i];
+        }
+        __syncwarp(g.mask);
+        double t[NC];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) t[i] = 0.0;
+#pragma unroll
+        for (int s = 0; s < NC; ++s) {
+            const double* col = sA + s * 8;
+            const double xs = X[s];
+#pragma unroll
+            for (int i = 0; i < NC; ++i) t[i] += col[i] * xs;
+        }
+        __syncwarp(g.mask);
+        if (c < NC) {
+#pragma unroll
+            for (int i = 0; i < NC; ++i) B[i] -= t[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < NC; ++i) Y[i] -= t[i];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        double pc[NC];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) pc[i] = __shfl_sync(g.mask, B[i], g.base + j);
+        if (PIVOT) {
+            int p = j;
+            double best = fabs(pc[j]);
+#pragma unroll
+            for (int i = j + 1; i < NC; ++i) {
+                const double a = fabs(pc[i]);
+                if (a > best) { best = a; p = i; }
+            }
+#pragma unroll
+            for (int i = j + 1; i < NC; ++i) {
+                const bool sw = (p == i);
+                const double tp = pc[j], tb = B[j], ty = Y[j];
+                pc[j] = sw ? pc[i] : tp; pc[i] = sw ? tp : pc[i];
+                B[j] = sw ? B[i] : tb;   B[i] = sw ? tb : B[i];
+                Y[j] = sw ? Y[i] : ty;   Y[i] = sw ? ty : Y[i];
+            }
+        }
+        const double piv = pc[j];
+        const double inv = 1.0 / piv;
+        if (!(fabs(piv) > 0.0) || !isfinite(inv)) singular = 1;
+        const double bj = B[j] * inv, yj = Y[j] * inv;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            if (i == j) continue;
+            B[i] -= pc[i] * bj;
+            Y[i] -= pc[i] * yj;
+        }
+        B[j] = bj; Y[j] = yj;
+    }
+}
+
+// One elimination sweep over `rows` block rows starting at node `first` and moving in direction `dir`
+// (+1: top half, downwards; -1: bottom half, upwards -- a twisted / "burn at both ends" factorisation, so the
+// two halves of a problem are eliminated concurrently by the two groups of a pair).  Row by row: assemble just
+// in time from the cell behind and the cell ahead (in sweep order), eliminate, store (coupling' | rhs') in
+// ws[node].  The cell ahead always exists because each half stops short of the other end of the domain.
+// A cell is integrated in the sweep's own orientation (local node 0 = current node): the forms only contain
+// products of two gradients, so they are invariant under the reflection.
+// Returns this half's sum of squares of the residual (valid in every lane of the group); X returns the last
+// row's eliminated block column (lanes<7) / rhs (lane 7).
 template <bool PIVOT, int NQJ>
 __device__ double forward_sweep(const Group& g, const LaneConst& L, const double* __restrict__ x, int n,
-                                const double* __restrict__ up, const double* __restrict__ unp,
-                                double* __restrict__ ws, bool factor, int& singular) {
+                                int first, int dir, int rows, const double* __restrict__ up,
+                                const double* __restrict__ unp, double* __restrict__ ws, double (&X)[NC],
+                                int& singular) {
     const double* P = g.sm + SM_P;
-    double* sA = g.sm + SM_A;
     const int c = g.c;
     const bool use_un = (P[GMPNP_P_KAPPA] != 0.0);   // steady equations never read u_n
     double U0[NC], U1[NC], N0[NC], N1[NC];
-    double X[NC];                 // previous row's C' column (lanes<7) / d' (lane 7)
-    double P10[NC], P11[NC];      // previous cell: block (1,0) and (1,1) columns; lane 7: F1 in P11
+    double P10[NC], P11[NC];      // cell behind: block (1,0) and (1,1) columns; lane 7: F1 in P11
 #pragma unroll
     for (int i = 0; i < NC; ++i) { X[i] = 0.0; P10[i] = 0.0; P11[i] = 0.0; N0[i] = 0.0; N1[i] = 0.0; }
-    double mine1 = (c < NC) ? up[c] : 1.0;        // this lane's component of node k+1 (scalar: no dynamic indexing)
+    double mine1 = (c < NC) ? up[(long)first * NC + c] : 1.0;   // this lane's component of the current node
     stage_node(g, mine1, 1, U1);
     if (c == 7 && use_un) {
 #pragma unroll
-        for (int i = 0; i < NC; ++i) N1[i] = unp[i];
+        for (int i = 0; i < NC; ++i) N1[i] = unp[(long)first * NC + i];
     }
-    double x1 = x[0];
-    // software prefetch: node k+1's component and coordinate are requested one row ahead
-    double pre_u = (c < NC && n > 1) ? up[NC + c] : 1.0;
-    double pre_x = (n > 1) ? x[1] : x1;
+    double x1 = x[first];
+    // software prefetch: the node ahead is requested one row early
+    double pre_u = (c < NC) ? up[(long)(first + dir) * NC + c] : 1.0;
+    double pre_x = x[first + dir];
     double rsq = 0.0;
-    for (int k = 0; k < n; ++k) {
+    for (int r = 0; r < rows; ++r) {
+        const int k = first + dir * r;               // current node
 #pragma unroll
         for (int i = 0; i < NC; ++i) { U0[i] = U1[i]; N0[i] = N1[i]; }
         const double x0 = x1;
         CellCols cc;
-#pragma unroll
-        for (int i = 0; i < NC; ++i) { cc.c00[i] = 0.0; cc.c01[i] = 0.0; cc.c10[i] = 0.0; cc.c11[i] = 0.0; }
-        if (k + 1 < n) {
-            g.sm[SM_U + c] = mine1;               // node k -> slot 0
+        {
+            g.sm[SM_U + c] = mine1;                  // current node -> slot 0
             const double mine = pre_u;
             mine1 = mine;
             x1 = pre_x;
-            if (k + 2 < n) {
-                pre_u = (c < NC) ? up[(long)(k + 2) * NC + c] : 1.0;
-                pre_x = x[k + 2];
+            const int k2 = k + 2 * dir;
+            if (k2 >= 0 && k2 < n) {
+                pre_u = (c < NC) ? up[(long)k2 * NC + c] : 1.0;
+                pre_x = x[k2];
             }
             stage_node(g, mine, 1, U1);
             if (c == 7 && use_un) {
 #pragma unroll
-                for (int i = 0; i < NC; ++i) N1[i] = unp[(long)(k + 1) * NC + i];
+                for (int i = 0; i < NC; ++i) N1[i] = unp[(long)(k + dir) * NC + i];
             }
-            cell_columns<NQJ>(P, g.sm + SM_U, L, c, x1 - x0, U0, U1, N0, N1, factor, cc);
+#pragma unroll
+            for (int i = 0; i < NC; ++i) { cc.c00[i] = 0.0; cc.c01[i] = 0.0; cc.c10[i] = 0.0; cc.c11[i] = 0.0; }
+            cell_columns<NQJ>(P, g.sm + SM_U, L, c, fabs(x1 - x0), U0, U1, N0, N1, true, cc);
         }
-        // ---- row k: A = P10, B = P11 + c00, C = c01, d = F1prev + F0 ------------------
+        // ---- row k: A = P10, B = P11 + c00, coupling ahead = c01, d = F1behind + F0 ----------
         double B[NC], Y[NC];
 #pragma unroll
         for (int i = 0; i < NC; ++i) { B[i] = P11[i] + cc.c00[i]; Y[i] = cc.c01[i]; }
@@ -334,7 +412,7 @@ __device__ double forward_sweep(const Group& g, const LaneConst& L, const double
         if (k == n - 1) {
 #pragma unroll
             for (int i = 0; i < NC; ++i) {
-                if (c < NC) { B[i] = (i == c) ? 1.0 : 0.0; Y[i] = 0.0; P10[i] = 0.0; }
+                if (c < NC) { B[i] = (i == c) ? 1.0 : 0.0; Y[i] = 0.0; }
                 else Y[i] = U0[i] - ((i < NS) ? 1.0 : 0.0);
             }
         }
@@ -346,144 +424,143 @@ __device__ double forward_sweep(const Group& g, const LaneConst& L, const double
 #pragma unroll
             for (int i = 0; i < NC; ++i) rsq += Y[i] * Y[i];
         }
-        if (factor) {
-            // ---- B' = B - A C'_{k-1},  d' = d - A d'_{k-1} --------------------------------
-            if (k > 0) {
-                if (c < NC) {
+        eliminate_row<PIVOT>(g, r > 0, P10, B, Y, X, singular);
+        // ---- store (coupling'_k | d'_k) ------------------------------------------------------
+        double* w = ws + (long)k * 56;
 #pragma unroll
-                    for (int i = 0; i < NC; ++i) sA[c * 8 + i] = P10[i];
-                }
-                __syncwarp(g.mask);
-                double t[NC];
+        for (int i = 0; i < NC; ++i) w[i * 8 + c] = Y[i];
 #pragma unroll
-                for (int i = 0; i < NC; ++i) t[i] = 0.0;
-#pragma unroll
-                for (int s = 0; s < NC; ++s) {
-                    const double* col = sA + s * 8;
-                    const double xs = X[s];
-#pragma unroll
-                    for (int i = 0; i < NC; ++i) t[i] += col[i] * xs;
-                }
-                __syncwarp(g.mask);
-                if (c < NC) {
-#pragma unroll
-                    for (int i = 0; i < NC; ++i) B[i] -= t[i];
-                } else {
-#pragma unroll
-                    for (int i = 0; i < NC; ++i) Y[i] -= t[i];
-                }
-            }
-            // ---- Gauss-Jordan on [B' | C | d'] with partial (row) pivoting -----------------
-#pragma unroll
-            for (int j = 0; j < NC; ++j) {
-                double pc[NC];
-#pragma unroll
-                for (int i = 0; i < NC; ++i) pc[i] = __shfl_sync(g.mask, B[i], g.base + j);
-                if (PIVOT) {
-                    int p = j;
-                    double best = fabs(pc[j]);
-#pragma unroll
-                    for (int i = j + 1; i < NC; ++i) {
-                        const double a = fabs(pc[i]);
-                        if (a > best) { best = a; p = i; }
-                    }
-#pragma unroll
-                    for (int i = j + 1; i < NC; ++i) {
-                        const bool sw = (p == i);
-                        const double tp = pc[j], tb = B[j], ty = Y[j];
-                        pc[j] = sw ? pc[i] : tp; pc[i] = sw ? tp : pc[i];
-                        B[j] = sw ? B[i] : tb;   B[i] = sw ? tb : B[i];
-                        Y[j] = sw ? Y[i] : ty;   Y[i] = sw ? ty : Y[i];
-                    }
-                }
-                const double piv = pc[j];
-                const double inv = 1.0 / piv;
-                if (!(fabs(piv) > 0.0) || !isfinite(inv)) singular = 1;
-                const double bj = B[j] * inv, yj = Y[j] * inv;
-#pragma unroll
-                for (int i = 0; i < NC; ++i) {
-                    if (i == j) continue;
-                    B[i] -= pc[i] * bj;
-                    Y[i] -= pc[i] * yj;
-                }
-                B[j] = bj; Y[j] = yj;
-            }
-            // ---- store (C'_k | d'_k) ---------------------------------------------------------
-            double* w = ws + (long)k * 56;
-#pragma unroll
-            for (int i = 0; i < NC; ++i) w[i * 8 + c] = Y[i];
-#pragma unroll
-            for (int i = 0; i < NC; ++i) X[i] = Y[i];
-        }
-#pragma unroll
-        for (int i = 0; i < NC; ++i) { P10[i] = cc.c10[i]; P11[i] = cc.c11[i]; }
+        for (int i = 0; i < NC; ++i) { X[i] = Y[i]; P10[i] = cc.c10[i]; P11[i] = cc.c11[i]; }
     }
-    // broadcast the residual norm from lane 7
+    // broadcast this half's residual sum from lane 7
     rsq = __shfl_sync(g.mask, rsq, g.base + 7);
     return rsq;
 }
 
-// Back substitution x_k = d'_k - C'_k x_{k+1} and update u <- u - relax * x.
-// Returns max|dx| and max|u_new| (valid in every lane).
-__device__ void backward_sweep(const Group& g, int n, double* __restrict__ up, const double* __restrict__ ws,
-                               double relax, double& dxmax, double& umax) {
+// Back substitution x_k = d'_k - coupling'_k x_(k-dir') over `rows` rows starting at node `first`, moving in
+// direction `dir`, seeded with the already known neighbour solution xn; updates u <- u - relax * x and
+// accumulates max|dx|, max|u_new| in this lane.
+__device__ void backward_sweep(const Group& g, int first, int dir, int rows, double (&xn)[NC],
+                               double* __restrict__ up, const double* __restrict__ ws, double relax,
+                               double& mdx, double& mu) {
+    if (rows <= 0) return;
     const int c = g.c;
-    double xn[NC];
-#pragma unroll
-    for (int i = 0; i < NC; ++i) xn[i] = 0.0;
-    double mdx = 0.0, mu = 0.0;
     const int row = (c < NC) ? c : 0;
     double r[8];
     {
-        const double2* src = reinterpret_cast<const double2*>(ws + (long)(n - 1) * 56 + row * 8);
+        const double2* src = reinterpret_cast<const double2*>(ws + (long)first * 56 + row * 8);
 #pragma unroll
         for (int v = 0; v < 4; ++v) { double2 t = src[v]; r[2 * v] = t.x; r[2 * v + 1] = t.y; }
     }
-    double ucur = (c < NC) ? up[(long)(n - 1) * NC + c] : 0.0;
-    for (int k = n - 1; k >= 0; --k) {
+    double ucur = (c < NC) ? up[(long)first * NC + c] : 0.0;
+    for (int q = 0; q < rows; ++q) {
+        const int k = first + dir * q;
         double rn[8];
         double unext = 0.0;
-        if (k > 0) {       // prefetch next row (workspace and u) while this one is reduced
-            const double2* src = reinterpret_cast<const double2*>(ws + (long)(k - 1) * 56 + row * 8);
+        if (q + 1 < rows) {       // prefetch next row (workspace and u) while this one is reduced
+            const double2* src = reinterpret_cast<const double2*>(ws + (long)(k + dir) * 56 + row * 8);
 #pragma unroll
             for (int v = 0; v < 4; ++v) { double2 t = src[v]; rn[2 * v] = t.x; rn[2 * v + 1] = t.y; }
-            if (c < NC) unext = up[(long)(k - 1) * NC + c];
+            if (c < NC) unext = up[(long)(k + dir) * NC + c];
         }
         double xi = r[7];
 #pragma unroll
         for (int j = 0; j < NC; ++j) xi -= r[j] * xn[j];
         if (c < NC) {
-            const long a = (long)k * NC + c;
             const double un = ucur - relax * xi;
-            up[a] = un;
+            up[(long)k * NC + c] = un;
             mdx = fmax(mdx, fabs(xi));
             mu = fmax(mu, fabs(un));
         }
 #pragma unroll
         for (int j = 0; j < NC; ++j) xn[j] = __shfl_sync(g.mask, xi, g.base + j);
-        if (k > 0) {
+        if (q + 1 < rows) {
 #pragma unroll
             for (int v = 0; v < 8; ++v) r[v] = rn[v];
             ucur = unext;
         }
     }
-#pragma unroll
-    for (int o = 4; o >= 1; o >>= 1) {
-        mdx = fmax(mdx, __shfl_xor_sync(g.mask, mdx, o));
-        mu = fmax(mu, __shfl_xor_sync(g.mask, mu, o));
-    }
-    dxmax = mdx; umax = mu;
 }
 
 struct NewtonOut { int iters; double r0, r; int status; };
 
-// dolfin NewtonSolver semantics for one problem handled by one group.
+// Factorisation sweep of both halves + merge.  Top half: rows 0..m-1 (stores C'_k, d'_k); bottom half: rows
+// n-1..m (stores A'_k, d'_k).  The merge eliminates the virtual row (I - A'_m C'_{m-1}) x_m = d'_m - A'_m d'_{m-1}
+// in the top group and broadcasts x_m to the pair.  Returns ||b||^2 of the whole problem.
+template <bool PIVOT, int NQJ>
+__device__ double factor_problem(const Group& g, const LaneConst& L, const double* x, int n, const double* up,
+                                 const double* unp, double* ws, double (&xm)[NC], int& singular) {
+    const int m = n >> 1;
+    double X[NC];
+    const int first = g.half ? n - 1 : 0, dir = g.half ? -1 : 1, rows = g.half ? n - m : m;
+    double rsq = forward_sweep<PIVOT, NQJ>(g, L, x, n, first, dir, rows, up, unp, ws, X, singular);
+    // merge: bottom publishes (A'_m | d'_m)
+    if (g.half) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) g.psm[g.c * 8 + i] = X[i];
+    }
+    __syncwarp(g.pmask);
+    double Y[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) Y[i] = 0.0;
+    if (!g.half) {
+        double A[NC], B[NC];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            A[i] = g.psm[g.c * 8 + i];
+            B[i] = (i == g.c) ? 1.0 : 0.0;
+        }
+        if (g.c == 7) {
+#pragma unroll
+            for (int i = 0; i < NC; ++i) Y[i] = A[i];          // rhs d'_m
+        }
+        eliminate_row<PIVOT>(g, true, A, B, Y, X, singular);
+    }
+    __syncwarp(g.pmask);
+#pragma unroll
+    for (int i = 0; i < NC; ++i) xm[i] = __shfl_sync(g.pmask, Y[i], g.pbase + 7);
+    rsq += __shfl_xor_sync(g.pmask, rsq, 8);
+    singular |= __shfl_xor_sync(g.pmask, singular, 8);
+    return rsq;
+}
+
+// Back substitution of both halves and the Newton update; returns max|dx|, max|u| over the problem.
+__device__ void solve_problem(const Group& g, int n, const double (&xm)[NC], double* up, const double* ws,
+                              double relax, double& dxmax, double& umax) {
+    const int m = n >> 1;
+    double xn[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) xn[i] = xm[i];
+    double mdx = 0.0, mu = 0.0;
+    if (!g.half) {
+        backward_sweep(g, m - 1, -1, m, xn, up, ws, relax, mdx, mu);
+    } else {
+        if (g.c < NC) {                       // row m itself: x_m is known
+            double xi = xm[0];
+#pragma unroll
+            for (int i = 1; i < NC; ++i) if (i == g.c) xi = xm[i];
+            const double un = up[(long)m * NC + g.c] - relax * xi;
+            up[(long)m * NC + g.c] = un;
+            mdx = fabs(xi); mu = fabs(un);
+        }
+        backward_sweep(g, m + 1, 1, n - 1 - m, xn, up, ws, relax, mdx, mu);
+    }
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) {
+        mdx = fmax(mdx, __shfl_xor_sync(g.pmask, mdx, o));
+        mu = fmax(mu, __shfl_xor_sync(g.pmask, mu, o));
+    }
+    dxmax = mdx; umax = mu;
+}
+
+// dolfin NewtonSolver semantics for one problem handled by one pair of groups.
 template <bool PIVOT, int NQJ>
 __device__ NewtonOut newton_solve(const Group& g, const LaneConst& L, const double* x, int n, double* up,
                                   const double* unp, double* ws, const gmpnp_newton_opts& o) {
     NewtonOut out;
     int singular = 0;
-    double rsq = forward_sweep<PIVOT, NQJ>(g, L, x, n, up, unp, ws, true, singular);
+    double xm[NC];
+    double rsq = factor_problem<PIVOT, NQJ>(g, L, x, n, up, unp, ws, xm, singular);
     double r = sqrt(rsq);
     out.r0 = r;
     int k = 0;
@@ -492,7 +569,7 @@ __device__ NewtonOut newton_solve(const Group& g, const LaneConst& L, const doub
     double dx_prev = INFINITY;
     while (!conv && !bad && k < o.maxit) {
         double dxmax, umax;
-        backward_sweep(g, n, up, ws, o.relax, dxmax, umax);
+        solve_problem(g, n, xm, up, ws, o.relax, dxmax, umax);
         ++k;
         if (o.criterion == 1) {
             const double scale = fmax(1.0, umax);
@@ -504,7 +581,8 @@ __device__ NewtonOut newton_solve(const Group& g, const LaneConst& L, const doub
             if (!isfinite(dxmax)) bad = true;
             if (conv || bad) break;
         }
-        rsq = forward_sweep<PIVOT, NQJ>(g, L, x, n, up, unp, ws, true, singular);
+        __syncwarp(g.pmask);        // the other half's u updates must be visible before re-assembly
+        rsq = factor_problem<PIVOT, NQJ>(g, L, x, n, up, unp, ws, xm, singular);
         r = sqrt(rsq);
         if (!isfinite(r) || singular) bad = true;
         if (o.criterion == 0) conv = (r / out.r0 < o.rtol) || (r < o.atol);
@@ -515,14 +593,21 @@ __device__ NewtonOut newton_solve(const Group& g, const LaneConst& L, const doub
     return out;
 }
 
+constexpr int SM_PAIR = 64;                              // doubles of merge area per pair
+constexpr int PROBLEMS_PER_BLOCK = GROUPS_PER_BLOCK / 2;
+
 __device__ __forceinline__ bool group_setup(Group& g, int batch, int& prob, double* smem) {
     const int lane = threadIdx.x & 31;
     g.c = lane & 7;
     g.base = lane & ~7;
     g.mask = 0xFFu << g.base;
+    g.half = (lane >> 3) & 1;
+    g.pbase = lane & ~15;
+    g.pmask = 0xFFFFu << g.pbase;
     const int gid = threadIdx.x >> 3;
     g.sm = smem + gid * SM_GROUP;
-    prob = blockIdx.x * GROUPS_PER_BLOCK + gid;
+    g.psm = smem + GROUPS_PER_BLOCK * SM_GROUP + (threadIdx.x >> 4) * SM_PAIR;
+    prob = blockIdx.x * PROBLEMS_PER_BLOCK + (threadIdx.x >> 4);
     return prob < batch;
 }
 
@@ -551,10 +636,12 @@ newton1d_kernel(int mode, int batch, int n, const double* __restrict__ x, const 
     double* ws = wsall + (long)prob * n * 56;
     LaneConst L;
     lane_consts(P, g.c, L);
+    const bool writer = (g.c == 0 && g.half == 0);
+    const int lane16 = (threadIdx.x & 15);
     if (mode == 0) {
         const double* unp = un_ro + (long)prob * n * NC;
         NewtonOut o = newton_solve<PIVOT, NQJ>(g, L, x, n, up, unp, ws, opts);
-        if (g.c == 0) {
+        if (writer) {
             if (iters) iters[prob] = o.iters;
             if (r0out) r0out[prob] = o.r0;
             if (rout) rout[prob] = o.r;
@@ -569,17 +656,17 @@ newton1d_kernel(int mode, int batch, int n, const double* __restrict__ x, const 
         int st = GMPNP_CONVERGED, done = 0;
         for (int s = 0; s < n_stage; ++s) {
             NewtonOut o = newton_solve<PIVOT, NQJ>(g, L, x, n, up, unp, ws, opts);
-            if (g.c == 0 && iters) iters[(long)prob * n_stage + s] = o.iters;
+            if (writer && iters) iters[(long)prob * n_stage + s] = o.iters;
             if (o.status != GMPNP_CONVERGED) { st = o.status; break; }
             ++done;
-            __syncwarp(g.mask);
+            __syncwarp(g.pmask);
             // u_n <- u (1D:796) and history row
-            for (long i = g.c; i < (long)n * NC; i += 8) {
+            for (long i = lane16; i < (long)n * NC; i += 16) {
                 const double v = up[i];
                 unp[i] = v;
                 if (hist) hist[((long)prob * n_stage + s) * n * NC + i] = v;
             }
-            __syncwarp(g.mask);
+            __syncwarp(g.pmask);
             if (hohp >= 0.0) {
                 // proton-current controller, 1D:766-793
                 const double f = up[0];
@@ -588,15 +675,15 @@ newton1d_kernel(int mode, int batch, int n, const double* __restrict__ x, const 
                 else if (f < (hohp - 0.025)) frac = frac / 1.01;
                 else if (f > hohp && f <= (hohp + 0.4) && frac <= 1.0) frac = frac * 1.04;
                 else if (f > (hohp + 0.4) && frac <= 1.0) frac = frac * 1.15;
-                __syncwarp(g.mask);
+                __syncwarp(g.pmask);
                 if (g.c == 0) {
                     P[GMPNP_P_JFLUX + 1] = -1.0 * P[GMPNP_P_JOHPRE] * (1 - frac);
                     P[GMPNP_P_JFLUX + 0] = P[GMPNP_P_JHPRE] * frac;
                 }
-                __syncwarp(g.mask);
+                __syncwarp(g.pmask);
             }
         }
-        if (g.c == 0) {
+        if (writer) {
             if (status) status[prob] = st;
             if (hfrac_out) hfrac_out[prob] = frac;
             if (stage_out) stage_out[prob] = done;
@@ -606,7 +693,7 @@ newton1d_kernel(int mode, int batch, int n, const double* __restrict__ x, const 
     // mode 2: steady continuation
     {
         if (g.c == 0) P[GMPNP_P_KAPPA] = 0.0;
-        __syncwarp(g.mask);
+        __syncwarp(g.pmask);
         int st = GMPNP_CONVERGED, done = 0;
         const double xtol_final = opts.xtol;
         for (int s = 0; s < n_stage; ++s) {
@@ -614,17 +701,17 @@ newton1d_kernel(int mode, int batch, int n, const double* __restrict__ x, const 
             if (isnan(Vs)) break;                       // ragged path: this problem is done
             const bool final_stage = (s + 1 == n_stage) || isnan(Vpath[(long)prob * n_stage + s + 1]);
             opts.xtol = (final_stage || !(opts.xtol_path > 0.0)) ? xtol_final : opts.xtol_path;
-            __syncwarp(g.mask);
+            __syncwarp(g.pmask);
             if (g.c == 0) P[GMPNP_P_V] = Vs;
-            __syncwarp(g.mask);
+            __syncwarp(g.pmask);
             // kappa = 0: u_n is never read for its value; pass u itself
             NewtonOut o = newton_solve<PIVOT, NQJ>(g, L, x, n, up, up, ws, opts);
-            if (g.c == 0 && iters) iters[(long)prob * n_stage + s] = o.iters;
-            if (g.c == 0 && rout) rout[prob] = o.r;
+            if (writer && iters) iters[(long)prob * n_stage + s] = o.iters;
+            if (writer && rout) rout[prob] = o.r;
             if (o.status != GMPNP_CONVERGED) { st = o.status; break; }
             ++done;
         }
-        if (g.c == 0) {
+        if (writer) {
             if (status) status[prob] = st;
             if (stage_out) stage_out[prob] = done;
         }
@@ -753,8 +840,8 @@ int edl1d_launch_newton(gmpnp_handle* h, int mode, double* d_u, double* d_un_rw,
                         int* d_iters, double* d_r0, double* d_r, double* d_hfrac, int* d_stage,
                         int* d_status, cudaStream_t st) {
     using namespace edl1d;
-    const int blocks = (h->batch + GROUPS_PER_BLOCK - 1) / GROUPS_PER_BLOCK;
-    const size_t smem = (size_t)GROUPS_PER_BLOCK * SM_GROUP * sizeof(double);
+    const int blocks = (h->batch + PROBLEMS_PER_BLOCK - 1) / PROBLEMS_PER_BLOCK;
+    const size_t smem = (size_t)(GROUPS_PER_BLOCK * SM_GROUP + PROBLEMS_PER_BLOCK * SM_PAIR) * sizeof(double);
 #define GMPNP_LAUNCH_NEWTON(PIV, NQ)                                                                         \
     newton1d_kernel<PIV, NQ><<<blocks, THREADS, smem, st>>>(mode, h->batch, h->n_nodes, h->d_x, h->d_params, d_u, \
         d_un_rw, d_un_ro, h->d_ws, *opts, n_stage, d_Vpath, d_hist, d_iters, d_r0, d_r, d_hfrac, d_stage, d_status)
