@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgmpnp.so")
+LIB_PATH = os.environ.get("GMPNP_LIB", os.path.join(_HERE, "libgmpnp.so"))   # override: experiments only
 
 NPAR = 64
 

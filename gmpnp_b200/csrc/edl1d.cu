@@ -37,7 +37,21 @@ __device__ __constant__ double GW2[2] = {0.5, 0.5};
 struct LaneConst {
     double coef[5];   // elementary-rate derivative coefficients of this lane's column (w,a,b,a2,b2)
     int sel[5];       // which staged nodal value multiplies it (7 = constant 1)
+    double rsig[6];   // -R_c = rsig . (w, a, b, a2, b2, kw1): this lane's own reaction row (residual)
 };
+
+// 1/x to within ~1 ulp: hardware seed + two Newton steps (the IEEE division sequence costs ~4x as many
+// instructions; pivots and steric denominators do not need correct rounding)
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
 
 __device__ __forceinline__ void lane_consts(const double* P, int c, LaneConst& L) {
 #pragma unroll
@@ -49,20 +63,32 @@ __device__ __forceinline__ void lane_consts(const double* P, int c, LaneConst& L
     else if (c == 2) { L.coef[1] = kA; L.sel[1] = 1; L.coef[4] = kB2; L.sel[4] = 7; }
     else if (c == 3) { L.coef[3] = kA2; L.sel[3] = 7; }
     else if (c == 4) { L.coef[2] = kB; L.sel[2] = 1; }
+    // own reaction row of the residual (1D:383-410): signs of (w, a, b, a2, b2, kw1), scaled by scale_R
+    const double sg[5][6] = {{1, 0, 0, 0, 0, -1}, {1, 1, 1, -1, -1, -1}, {0, 1, -1, -1, 1, 0},
+                             {0, -1, 0, 1, 0, 0}, {0, 0, 1, 0, -1, 0}};
+#pragma unroll
+    for (int t = 0; t < 6; ++t) L.rsig[t] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        if (c == i) {
+#pragma unroll
+            for (int t = 0; t < 6; ++t) L.rsig[t] = P[GMPNP_P_S + i] * sg[i][t];
+        }
+    }
 }
 
 // Element blocks of one cell for this lane.
-//   lane c<7 : cab[i] = dF_e[a,i]/dU[b,c]   (column c of block (a,b))
-//   lane 7   : c00 = F_e[0,:], c11 = F_e[1,:]
-struct CellCols { double c00[NC], c01[NC], c10[NC], c11[NC]; };
+//   lane c<7 : cab[i] = dF_e[a,i]/dU[b,c]   (column c of block (a,b)), and f0/f1 = F_e[0,c], F_e[1,c]:
+//              every lane integrates the residual row of its own component, so no lane runs a separate
+//              residual pass (lane 7 only collects the rows, see forward_sweep)
+struct CellCols { double c00[NC], c01[NC], c10[NC], c11[NC]; double f0, f1; };
 
 template <int NQJ>
 __device__ __forceinline__ void cell_columns(const double* __restrict__ P, const double* __restrict__ sU,
                                              const LaneConst& L, int c, double h,
                                              const double (&U0)[NC], const double (&U1)[NC],
-                                             const double (&N0)[NC], const double (&N1)[NC],
-                                             bool want_jac, CellCols& o) {
-    const double ih = 1.0 / h;
+                                             double myU0, double myU1, double myN0, double myN1, CellCols& o) {
+    const double ih = fast_rcp(h);
     double g[NC];
 #pragma unroll
     for (int i = 0; i < NC; ++i) g[i] = (U1[i] - U0[i]) * ih;
@@ -74,12 +100,13 @@ __device__ __forceinline__ void cell_columns(const double* __restrict__ P, const
     // grad phi_0 = -ih, grad phi_1 = +ih
     const double Ga0 = -G * ih, Ga1 = G * ih;
     const double gpa0 = -gp * ih, gpa1 = gp * ih;
-    const bool spec = (c < NS) && want_jac;
-    const bool resid = (c == 7);
-    // quadrature accumulators, aliased between the lane roles:
-    //   species column lanes: a0 = int u_i D, a1 = int u_i phi_0 D^2, a2 = int u_i phi_1 D^2, mD0/mD1 = int phi_b D
-    //   residual lane       : a0 = int u_i D, a1[0..4] = int (-R_i) phi_0, a2[0..4] = int (-R_i) phi_1
+    o.f0 = 0.0; o.f1 = 0.0;
+    if (c == 7) return;
+    const double myg = (myU1 - myU0) * ih;
+    // quadrature accumulators: a0 = int u_i D, a1 = int u_i phi_0 D^2, a2 = int u_i phi_1 D^2, mD = int phi_b D
+    // (Jacobian rule); own-row residual sums a0F = int u_c D, R0/R1 = int (-R_c) phi_a (residual rule)
     double a0[NS], a1[NS], a2[NS], mD0 = 0.0, mD1 = 0.0;
+    double a0F = 0.0, R0 = 0.0, R1 = 0.0;
 #pragma unroll
     for (int i = 0; i < NS; ++i) { a0[i] = 0.0; a1[i] = 0.0; a2[i] = 0.0; }
     auto species_acc = [&](double l0, double l1, double W, const double (&uq)[NS], double D) {
@@ -92,59 +119,53 @@ __device__ __forceinline__ void cell_columns(const double* __restrict__ P, const
         }
     };
     auto resid_acc = [&](double l0, double l1, double W, const double (&uq)[NS], double D) {
-        const double WD = W * D;
-#pragma unroll
-        for (int i = 0; i < NS; ++i) a0[i] += WD * uq[i];
+        a0F += W * D * (l0 * myU0 + l1 * myU1);
         const double w = P[GMPNP_P_KW] * uq[0] * uq[1], a = P[GMPNP_P_KA] * uq[1] * uq[2];
         const double b = P[GMPNP_P_KB] * uq[4] * uq[1];
-        const double a2_ = P[GMPNP_P_KA2] * uq[3], b2 = P[GMPNP_P_KB2] * uq[2], kw1 = P[GMPNP_P_KW1];
-        double mr[5];
-        mr[0] = P[GMPNP_P_S] * (w - kw1);
-        mr[1] = P[GMPNP_P_S + 1] * (w + a + b - kw1 - a2_ - b2);
-        mr[2] = P[GMPNP_P_S + 2] * (a + b2 - a2_ - b);
-        mr[3] = P[GMPNP_P_S + 3] * (a2_ - a);
-        mr[4] = P[GMPNP_P_S + 4] * (b - b2);
-#pragma unroll
-        for (int i = 0; i < 5; ++i) { a1[i] += W * l0 * mr[i]; a2[i] += W * l1 * mr[i]; }
+        const double a2_ = P[GMPNP_P_KA2] * uq[3], b2 = P[GMPNP_P_KB2] * uq[2];
+        const double mr = L.rsig[0] * w + L.rsig[1] * a + L.rsig[2] * b + L.rsig[3] * a2_ + L.rsig[4] * b2 +
+                          L.rsig[5] * P[GMPNP_P_KW1];
+        R0 += W * l0 * mr; R1 += W * l1 * mr;
     };
-    if (NQJ == 2) {
-        // consistent Jacobian: J and F share the 2-point rule, so the point evaluations are shared too
-        if (spec || resid) {
+    if (c < NS) {
+        if (NQJ == 2) {
+            // consistent Jacobian: J and F share the 2-point rule, so the point evaluations are shared too
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 const double l1 = GX2[q], l0 = 1.0 - l1, W = GW2[q] * h;
                 double uq[NS], S = 0.0;
 #pragma unroll
                 for (int i = 0; i < NS; ++i) { uq[i] = l0 * U0[i] + l1 * U1[i]; S += P[GMPNP_P_NU + i] * uq[i]; }
-                const double D = 1.0 / (1.0 - S);
-                if (resid) resid_acc(l0, l1, W, uq, D);
-                else species_acc(l0, l1, W, uq, D);
+                const double D = fast_rcp(1.0 - S);
+                species_acc(l0, l1, W, uq, D);
+                resid_acc(l0, l1, W, uq, D);
             }
-        }
-    } else {
-        if (spec) {
+        } else {
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
                 const double l1 = GX3[q], l0 = 1.0 - l1, W = GW3[q] * h;
                 double uq[NS], S = 0.0;
 #pragma unroll
                 for (int i = 0; i < NS; ++i) { uq[i] = l0 * U0[i] + l1 * U1[i]; S += P[GMPNP_P_NU + i] * uq[i]; }
-                species_acc(l0, l1, W, uq, 1.0 / (1.0 - S));
+                species_acc(l0, l1, W, uq, fast_rcp(1.0 - S));
             }
-        } else if (resid) {
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 const double l1 = GX2[q], l0 = 1.0 - l1, W = GW2[q] * h;
                 double uq[NS], S = 0.0;
 #pragma unroll
                 for (int i = 0; i < NS; ++i) { uq[i] = l0 * U0[i] + l1 * U1[i]; S += P[GMPNP_P_NU + i] * uq[i]; }
-                resid_acc(l0, l1, W, uq, 1.0 / (1.0 - S));
+                resid_acc(l0, l1, W, uq, fast_rcp(1.0 - S));
             }
         }
-    }
-
-    if (c < NS) {
-        if (!want_jac) return;
+        // ---- residual row of species c (2-point Gauss; time/source moments in closed form) -----------
+        {
+            const double d0 = myU0 - myN0, d1 = myU1 - myN1;
+            const double sUi = 0.5 * h * (myU0 + myU1);
+            const double zi = P[GMPNP_P_Z + c];
+            o.f0 = kappa * h * ((1.0 / 3.0) * d0 + (1.0 / 6.0) * d1) - myg + zi * gpa0 * sUi + Ga0 * a0F + R0;
+            o.f1 = kappa * h * ((1.0 / 6.0) * d0 + (1.0 / 3.0) * d1) + myg + zi * gpa1 * sUi + Ga1 * a0F + R1;
+        }
         // ---- species column j = c --------------------------------------------------
         const double nuj = P[GMPNP_P_NU + c];
         const double zj = P[GMPNP_P_Z + c];
@@ -192,47 +213,32 @@ __device__ __forceinline__ void cell_columns(const double* __restrict__ P, const
         }
         // Poisson row:  -eps'_j (gp.grad a) m_b + q z_j c0_j M_ab
         double depsj = 0.0;
-        if (c == 0) depsj = (6.0 - P[GMPNP_P_EPSW]) / 55.0 * P[GMPNP_P_EPSH];
-        if (c == NS - 1) depsj = (6.0 - P[GMPNP_P_EPSW]) / 55.0 * P[GMPNP_P_EPSC];
+        if (c == 0) depsj = (6.0 - P[GMPNP_P_EPSW]) * (1.0 / 55.0) * P[GMPNP_P_EPSH];
+        if (c == NS - 1) depsj = (6.0 - P[GMPNP_P_EPSW]) * (1.0 / 55.0) * P[GMPNP_P_EPSC];
         const double qz = P[GMPNP_P_Q] * P[GMPNP_P_ZC0 + c];
         o.c00[NS] = -depsj * gpa0 * mb + qz * Md;
         o.c01[NS] = -depsj * gpa0 * mb + qz * Mo;
         o.c10[NS] = -depsj * gpa1 * mb + qz * Mo;
         o.c11[NS] = -depsj * gpa1 * mb + qz * Md;
-    } else if (c == NS) {
-        if (!want_jac) return;
-        // ---- potential column ------------------------------------------------------
+    } else {
+        // ---- potential column and the Poisson residual row ------------------------------------
         const double ih2 = ih * ih;
+        double rho0 = 0.0, rho1 = 0.0;
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
             const double iU = 0.5 * h * (U0[i] + U1[i]);
             const double v = P[GMPNP_P_Z + i] * ih2 * iU;
             o.c00[i] = v; o.c11[i] = v; o.c01[i] = -v; o.c10[i] = -v;
-        }
-        const double wm = P[GMPNP_P_EPSC] * 0.5 * (U0[NS - 1] + U1[NS - 1]) + P[GMPNP_P_EPSH] * 0.5 * (U0[0] + U1[0]);
-        const double epsm = P[GMPNP_P_EPSW] * ((55.0 - wm) / 55.0) + 6.0 * (wm / 55.0);
-        const double v = -ih2 * h * epsm;
-        o.c00[NS] = v; o.c11[NS] = v; o.c01[NS] = -v; o.c10[NS] = -v;
-    } else {
-        // ---- residual (lane 7) ---------------------------------------------------------
-        double rho0 = 0.0, rho1 = 0.0;
-#pragma unroll
-        for (int i = 0; i < NS; ++i) {
-            const double d0 = U0[i] - N0[i], d1 = U1[i] - N1[i];
-            const double sUi = 0.5 * h * (U0[i] + U1[i]);
-            const double zi = P[GMPNP_P_Z + i];
-            double f0 = kappa * h * ((1.0 / 3.0) * d0 + (1.0 / 6.0) * d1) - g[i] + zi * gpa0 * sUi + Ga0 * a0[i];
-            double f1 = kappa * h * ((1.0 / 6.0) * d0 + (1.0 / 3.0) * d1) + g[i] + zi * gpa1 * sUi + Ga1 * a0[i];
-            if (i < 5) { f0 += a1[i]; f1 += a2[i]; }
-            o.c00[i] = f0; o.c11[i] = f1;
             rho0 += P[GMPNP_P_ZC0 + i] * U0[i];
             rho1 += P[GMPNP_P_ZC0 + i] * U1[i];
         }
         const double wm = P[GMPNP_P_EPSC] * 0.5 * (U0[NS - 1] + U1[NS - 1]) + P[GMPNP_P_EPSH] * 0.5 * (U0[0] + U1[0]);
-        const double epsm = P[GMPNP_P_EPSW] * ((55.0 - wm) / 55.0) + 6.0 * (wm / 55.0);
+        const double epsm = P[GMPNP_P_EPSW] * ((55.0 - wm) * (1.0 / 55.0)) + 6.0 * (wm * (1.0 / 55.0));
+        const double v = -ih2 * h * epsm;
+        o.c00[NS] = v; o.c11[NS] = v; o.c01[NS] = -v; o.c10[NS] = -v;
         const double qh = P[GMPNP_P_Q] * h;
-        o.c00[NS] = -gpa0 * h * epsm + qh * ((1.0 / 3.0) * rho0 + (1.0 / 6.0) * rho1);
-        o.c11[NS] = -gpa1 * h * epsm + qh * ((1.0 / 6.0) * rho0 + (1.0 / 3.0) * rho1);
+        o.f0 = -gpa0 * h * epsm + qh * ((1.0 / 3.0) * rho0 + (1.0 / 6.0) * rho1);
+        o.f1 = -gpa1 * h * epsm + qh * ((1.0 / 6.0) * rho0 + (1.0 / 3.0) * rho1);
     }
 }
 
@@ -315,17 +321,19 @@ __device__ __forceinline__ void eliminate_row(const Group& g, bool with_prev, co
                 const double a = fabs(pc[i]);
                 if (a > best) { best = a; p = i; }
             }
+            if (p != j) {                    // group-uniform; the diagonal is the usual pivot
 #pragma unroll
-            for (int i = j + 1; i < NC; ++i) {
-                const bool sw = (p == i);
-                const double tp = pc[j], tb = B[j], ty = Y[j];
-                pc[j] = sw ? pc[i] : tp; pc[i] = sw ? tp : pc[i];
-                B[j] = sw ? B[i] : tb;   B[i] = sw ? tb : B[i];
-                Y[j] = sw ? Y[i] : ty;   Y[i] = sw ? ty : Y[i];
+                for (int i = j + 1; i < NC; ++i) {
+                    const bool sw = (p == i);
+                    const double tp = pc[j], tb = B[j], ty = Y[j];
+                    pc[j] = sw ? pc[i] : tp; pc[i] = sw ? tp : pc[i];
+                    B[j] = sw ? B[i] : tb;   B[i] = sw ? tb : B[i];
+                    Y[j] = sw ? Y[i] : ty;   Y[i] = sw ? ty : Y[i];
+                }
             }
         }
         const double piv = pc[j];
-        const double inv = 1.0 / piv;
+        const double inv = fast_rcp(piv);
         if (!(fabs(piv) > 0.0) || !isfinite(inv)) singular = 1;
         const double bj = B[j] * inv, yj = Y[j] * inv;
 #pragma unroll
@@ -354,17 +362,16 @@ __device__ double forward_sweep(const Group& g, const LaneConst& L, const double
                                 int& singular) {
     const double* P = g.sm + SM_P;
     const int c = g.c;
+    double* sF = g.sm + SM_M;                        // residual rows of the current node, gathered for lane 7
     const bool use_un = (P[GMPNP_P_KAPPA] != 0.0);   // steady equations never read u_n
-    double U0[NC], U1[NC], N0[NC], N1[NC];
-    double P10[NC], P11[NC];      // cell behind: block (1,0) and (1,1) columns; lane 7: F1 in P11
+    double U0[NC], U1[NC];
+    double P10[NC], P11[NC];      // cell behind: block (1,0) and (1,1) columns
+    double f1_behind = 0.0;       // cell behind: this lane's residual row at the shared node
 #pragma unroll
-    for (int i = 0; i < NC; ++i) { X[i] = 0.0; P10[i] = 0.0; P11[i] = 0.0; N0[i] = 0.0; N1[i] = 0.0; }
+    for (int i = 0; i < NC; ++i) { X[i] = 0.0; P10[i] = 0.0; P11[i] = 0.0; }
     double mine1 = (c < NC) ? up[(long)first * NC + c] : 1.0;   // this lane's component of the current node
     stage_node(g, mine1, 1, U1);
-    if (c == 7 && use_un) {
-#pragma unroll
-        for (int i = 0; i < NC; ++i) N1[i] = unp[(long)first * NC + i];
-    }
+    double myN1 = (c < NC && use_un) ? unp[(long)first * NC + c] : 0.0, myN0 = 0.0;
     double x1 = x[first];
     // software prefetch: the node ahead is requested one row early
     double pre_u = (c < NC) ? up[(long)(first + dir) * NC + c] : 1.0;
@@ -373,8 +380,10 @@ __device__ double forward_sweep(const Group& g, const LaneConst& L, const double
     for (int r = 0; r < rows; ++r) {
         const int k = first + dir * r;               // current node
 #pragma unroll
-        for (int i = 0; i < NC; ++i) { U0[i] = U1[i]; N0[i] = N1[i]; }
+        for (int i = 0; i < NC; ++i) U0[i] = U1[i];
+        myN0 = myN1;
         const double x0 = x1;
+        const double myU0 = mine1;
         CellCols cc;
         {
             g.sm[SM_U + c] = mine1;                  // current node -> slot 0
@@ -387,21 +396,21 @@ __device__ double forward_sweep(const Group& g, const LaneConst& L, const double
                 pre_x = x[k2];
             }
             stage_node(g, mine, 1, U1);
-            if (c == 7 && use_un) {
-#pragma unroll
-                for (int i = 0; i < NC; ++i) N1[i] = unp[(long)(k + dir) * NC + i];
-            }
+            if (c < NC && use_un) myN1 = unp[(long)(k + dir) * NC + c];
 #pragma unroll
             for (int i = 0; i < NC; ++i) { cc.c00[i] = 0.0; cc.c01[i] = 0.0; cc.c10[i] = 0.0; cc.c11[i] = 0.0; }
-            cell_columns<NQJ>(P, g.sm + SM_U, L, c, fabs(x1 - x0), U0, U1, N0, N1, true, cc);
+            cell_columns<NQJ>(P, g.sm + SM_U, L, c, fabs(x1 - x0), U0, U1, myU0, mine, myN0, myN1, cc);
         }
         // ---- row k: A = P10, B = P11 + c00, coupling ahead = c01, d = F1behind + F0 ----------
+        sF[c] = f1_behind + cc.f0;                   // this lane's residual row of node k
+        f1_behind = cc.f1;
+        __syncwarp(g.mask);
         double B[NC], Y[NC];
 #pragma unroll
         for (int i = 0; i < NC; ++i) { B[i] = P11[i] + cc.c00[i]; Y[i] = cc.c01[i]; }
         if (c == 7) {
 #pragma unroll
-            for (int i = 0; i < NC; ++i) Y[i] = B[i];       // lane 7: rhs lives in Y
+            for (int i = 0; i < NC; ++i) Y[i] = sF[i];      // lane 7: rhs lives in Y
             // point fluxes `J_i v_i ds` at both end points (1D:553, 738)
             if (k == 0 || k == n - 1) {
 #pragma unroll
@@ -619,8 +628,11 @@ __device__ __forceinline__ void load_params(const Group& g, const double* __rest
 // mode 0: single Newton solve (gmpnp_newton_1d)
 // mode 1: pseudo-time march  (gmpnp_march_1d): n_stage steps, H_OHP controller, u_n <- u
 // mode 2: steady continuation (gmpnp_steady_continuation_1d): kappa = 0, V from Vpath
+#ifndef GMPNP_NEWTON_MIN_BLOCKS
+#define GMPNP_NEWTON_MIN_BLOCKS 2
+#endif
 template <bool PIVOT, int NQJ>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, GMPNP_NEWTON_MIN_BLOCKS)
 newton1d_kernel(int mode, int batch, int n, const double* __restrict__ x, const double* __restrict__ params,
                 double* __restrict__ u, double* __restrict__ un_rw, const double* __restrict__ un_ro,
                 double* __restrict__ wsall, gmpnp_newton_opts opts, int n_stage,
@@ -740,38 +752,46 @@ assemble1d_kernel(int batch, int n, const double* __restrict__ x, const double* 
     const double* up = u + (long)prob * n * NC;
     const double* unp = un + (long)prob * n * NC;
     const int c = g.c;
+    double* sF = g.sm + SM_M;
     double A[NC], B[NC], C[NC];
 #pragma unroll
     for (int i = 0; i < NC; ++i) { A[i] = 0.0; B[i] = 0.0; C[i] = 0.0; }
-    double Um[NC], U0[NC], U1[NC], Nm[NC], N0[NC], N1[NC];
-    load_node(g, up, k, 1, U0);
-#pragma unroll
-    for (int i = 0; i < NC; ++i) N0[i] = unp[(long)k * NC + i];
+    double Um[NC], U0[NC], U1[NC];
+    const double my0 = (c < NC) ? up[(long)k * NC + c] : 1.0;
+    const double myn0 = (c < NC) ? unp[(long)k * NC + c] : 0.0;
+    stage_node(g, my0, 1, U0);
+    double frow = 0.0;                 // this lane's residual row of node k
     if (k > 0) {
-        load_node(g, up, k - 1, 0, Um);
-#pragma unroll
-        for (int i = 0; i < NC; ++i) Nm[i] = unp[(long)(k - 1) * NC + i];
+        const double mym = (c < NC) ? up[(long)(k - 1) * NC + c] : 1.0;
+        const double mynm = (c < NC) ? unp[(long)(k - 1) * NC + c] : 0.0;
+        stage_node(g, mym, 0, Um);
         CellCols cc;
 #pragma unroll
         for (int i = 0; i < NC; ++i) { cc.c00[i] = 0; cc.c01[i] = 0; cc.c10[i] = 0; cc.c11[i] = 0; }
-        cell_columns<3>(P, g.sm + SM_U, L, c, x[k] - x[k - 1], Um, U0, Nm, N0, true, cc);
+        cell_columns<3>(P, g.sm + SM_U, L, c, x[k] - x[k - 1], Um, U0, mym, my0, mynm, myn0, cc);
 #pragma unroll
         for (int i = 0; i < NC; ++i) { A[i] = cc.c10[i]; B[i] += cc.c11[i]; }
+        frow += cc.f1;
     }
     __syncwarp(g.mask);
     if (k + 1 < n) {
-        if (c < NC) g.sm[SM_U + c] = U0[c]; else g.sm[SM_U + 7] = 1.0;
-        load_node(g, up, k + 1, 1, U1);
-#pragma unroll
-        for (int i = 0; i < NC; ++i) N1[i] = unp[(long)(k + 1) * NC + i];
+        g.sm[SM_U + c] = my0;
+        const double my1 = (c < NC) ? up[(long)(k + 1) * NC + c] : 1.0;
+        const double myn1 = (c < NC) ? unp[(long)(k + 1) * NC + c] : 0.0;
+        stage_node(g, my1, 1, U1);
         CellCols cc;
 #pragma unroll
         for (int i = 0; i < NC; ++i) { cc.c00[i] = 0; cc.c01[i] = 0; cc.c10[i] = 0; cc.c11[i] = 0; }
-        cell_columns<3>(P, g.sm + SM_U, L, c, x[k + 1] - x[k], U0, U1, N0, N1, true, cc);
+        cell_columns<3>(P, g.sm + SM_U, L, c, x[k + 1] - x[k], U0, U1, my0, my1, myn0, myn1, cc);
 #pragma unroll
         for (int i = 0; i < NC; ++i) { B[i] += cc.c00[i]; C[i] = cc.c01[i]; }
+        frow += cc.f0;
     }
+    sF[c] = frow;
+    __syncwarp(g.mask);
     if (c == 7) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) B[i] = sF[i];
         if (k == 0 || k == n - 1) {
 #pragma unroll
             for (int i = 0; i < NS; ++i) B[i] += P[GMPNP_P_JFLUX + i];
