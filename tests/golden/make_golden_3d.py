@@ -40,10 +40,6 @@ def main():
     np.savez_compressed(os.path.join(HERE, "march_3d_L50R5.npz"), step1=hist[1], step2=hist[2], its=np.array(its),
                         co2=np.array(co2s))
 
-    # 3. config 3 steady at V = -1 (continuation -0.5, -1.0), CO2 entry fixed at the Henry value
-    u, its = solver.steady_3d(mesh.x, mesh.cells, p3, dofs.astype(np.int64), kind, [-0.5, -1.0],
-                              float(p3.extras["eq_scaled"][0]), xtol=1e-11)
-    np.savez_compressed(os.path.join(HERE, "steady_3d_L50R5.npz"), u=u, its=np.array(its))
 
 
 if __name__ == "__main__":

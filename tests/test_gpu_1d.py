@@ -286,3 +286,32 @@ def test_invalid_state_is_an_error(lib):
     u = solver1d.bulk_state(1, 9, _dev())
     with pytest.raises(GmpnpError):
         s.newton(u, u.clone())           # parameters not set
+
+
+def test_solve_EDL_drop_in_writes_reference_outputs(lib, tmp_path):
+    """The drop-in `solve_EDL` (1D:66-989): same files, keys and array shapes as the reference writes."""
+    import json
+    from gmpnp_b200 import edl1d
+    meta = edl1d.solve_EDL(L_n=1.0e-6, out_dir=str(tmp_path), n_steps=4)
+    d = meta["output_dir"]
+    un = np.load(os.path.join(d, "arrays_unscaled.npz"))
+    assert set(un.files) == {"H", "OH", "HCO3", "CO32", "CO2", "cat", "p", "coor", "tau", "field_values"}
+    assert un["H"].shape == (5, 1091) and un["coor"].shape == (1091, 1) and un["field_values"].shape == (1091,)
+    assert np.all(un["H"][0] == 1.0) and np.all(un["p"][0] == 0.0)              # row 0 = initial state
+    sc = np.load(os.path.join(d, "arrays_scaled.npz"))
+    assert {"x", "psi", "t_H", "c_H", "t_cat", "c_cat", "eps_rel", "field_values", "charge_density"} <= set(sc.files)
+    md = json.load(open(os.path.join(d, "metadata.json")))
+    for k in ("concentration_elec", "cation", "model", "stabilization", "voltage_multiplier", "H2_FE", "L_n_EDL",
+              "time_constant", "time_step", "total_sim_time", "mesh_number", "mesh_structure", "eps_rel_OHP",
+              "field_OHP", "current_OHP_ss", "current_H", "H_OHP_vs_bulk", "potential_OHP", "pH_OHP",
+              "CO2_OHP_frac", "pH_overpotential", "CO2_overpotential", "end_time"):   # 1D:962-985
+        assert k in md, k
+    assert md["mesh_number"] == 1090 and md["mesh_structure"] == "variable_1um"
+    g = np.load(os.path.join(GOLDEN, "march_1um.npz"))
+    assert md["newton_iterations"] == g["its"][:4].tolist()
+    assert rel_l2(un["cat"][4], g["hist"][4][:, 5]) < 1e-8
+    # steady mode through the same entry point
+    m2 = edl1d.solve_EDL(voltage_multiplier=-2.5, mode="steady", write=False)
+    gs = np.load(os.path.join(GOLDEN, "steady_50um.npz"))
+    assert abs(m2["field_OHP"] - gs["ohp_-2.5"][0]) <= 1e-7 * abs(gs["ohp_-2.5"][0])
+    assert abs(m2["eps_rel_OHP"] - gs["ohp_-2.5"][1]) <= 1e-9 * gs["ohp_-2.5"][1]
