@@ -22,8 +22,18 @@ constexpr int NC = 7;
 constexpr int SM_P = 0;       // params            [64]
 constexpr int SM_U = 64;      // staged nodal vals [2][8]  (slot 7 holds the constant 1.0)
 constexpr int SM_A = 80;      // sub-diagonal block, column-major [7][8]
-constexpr int SM_M = 136;     // multipliers + pivot row [8]
-constexpr int SM_GROUP = 144; // doubles per group
+constexpr int SM_M = 136;     // residual rows of the current node [8]
+constexpr int SM_X = 144;     // back-substitution: solution of the neighbour row, double-buffered [2][8]
+constexpr int SM_PC = 160;    // Gauss-Jordan: pivot column broadcast, double-buffered [2][8]
+constexpr int SM_GROUP = 176; // doubles per group
+// Multi-row staging ring (cp.async, RING rows ahead of the row being processed), per group:
+//   forward sweep : fu[RING][8] = (u_0..u_6 of a node, 1.0), fn[RING][8] = (u_n,0..6 of the node, x of the node)
+//   backward sweep: bw[RING][4][8] double2 = the lane's own 64-B workspace row, bu[RING][8] = the lane's u component
+// The two sweeps alias the same memory.  One row of global-load latency (~1 us) is several backward rows long,
+// and a register prefetch gets spilled by the 255-register forward body, so the rows are staged through
+// shared memory instead of registers.
+constexpr int RING = 8;
+constexpr int SM_RING = RING * 72;  // doubles per group
 constexpr int GROUPS_PER_BLOCK = 16;
 constexpr int THREADS = GROUPS_PER_BLOCK * 8;
 
@@ -39,6 +49,18 @@ struct LaneConst {
     int sel[5];       // which staged nodal value multiplies it (7 = constant 1)
     double rsig[6];   // -R_c = rsig . (w, a, b, a2, b2, kw1): this lane's own reaction row (residual)
 };
+
+__device__ __forceinline__ void cp_async8(double* dst_smem, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst_smem, const double* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // 1/x to within ~1 ulp: hardware seed + two Newton steps (the IEEE division sequence costs ~4x as many
 // instructions; pivots and steric denominators do not need correct rounding)
@@ -84,8 +106,8 @@ __device__ __forceinline__ void lane_consts(const double* P, int c, LaneConst& L
 struct CellCols { double c00[NC], c01[NC], c10[NC], c11[NC]; double f0, f1; };
 
 template <int NQJ>
-__device__ __forceinline__ void cell_columns(const double* __restrict__ P, const double* __restrict__ sU,
-                                             const LaneConst& L, int c, double h,
+__device__ __forceinline__ void cell_columns(const double* __restrict__ P, const double* __restrict__ sU0,
+                                             const double* __restrict__ sU1, const LaneConst& L, int c, double h,
                                              const double (&U0)[NC], const double (&U1)[NC],
                                              double myU0, double myU1, double myN0, double myN1, CellCols& o) {
     const double ih = fast_rcp(h);
@@ -175,7 +197,7 @@ __device__ __forceinline__ void cell_columns(const double* __restrict__ P, const
         double E00[5], E01[5], E11[5];
 #pragma unroll
         for (int r = 0; r < 5; ++r) {
-            const double v0 = sU[L.sel[r]], v1 = sU[8 + L.sel[r]];
+            const double v0 = sU0[L.sel[r]], v1 = sU1[L.sel[r]];
             const double ch = L.coef[r] * h;
             E00[r] = ch * (0.25 * v0 + (1.0 / 12.0) * v1);
             E01[r] = ch * ((1.0 / 12.0) * (v0 + v1));
@@ -250,6 +272,7 @@ struct Group {
     unsigned mask;    // participation mask of the 8 lanes
     int base;         // first lane of the group inside the warp
     double* sm;       // per-group shared memory
+    double* ring;     // per-group staging ring (SM_RING doubles, 16-B aligned)
     // two-sided elimination: two groups (a "pair", 16 lanes) share one problem
     int half;         // 0: sweeps down from node 0; 1: sweeps up from node n-1
     unsigned pmask;   // participation mask of the pair
@@ -310,9 +333,19 @@ __device__ __forceinline__ void eliminate_row(const Group& g, bool with_prev, co
     }
 #pragma unroll
     for (int j = 0; j < NC; ++j) {
+        // pivot column j: published by its owner lane in shared memory (double-buffered: one group
+        // barrier per step), read back by every lane as a broadcast
         double pc[NC];
-#pragma unroll
-        for (int i = 0; i < NC; ++i) pc[i] = __shfl_sync(g.mask, B[i], g.base + j);
+        {
+            double2* pcs = reinterpret_cast<double2*>(g.sm + SM_PC + (j & 1) * 8);
+            if (c == j) {
+                pcs[0] = make_double2(B[0], B[1]); pcs[1] = make_double2(B[2], B[3]);
+                pcs[2] = make_double2(B[4], B[5]); pcs[3] = make_double2(B[6], 0.0);
+            }
+            __syncwarp(g.mask);
+            const double2 p0 = pcs[0], p1 = pcs[1], p2 = pcs[2], p3 = pcs[3];
+            pc[0] = p0.x; pc[1] = p0.y; pc[2] = p1.x; pc[3] = p1.y; pc[4] = p2.x; pc[5] = p2.y; pc[6] = p3.x;
+        }
         if (PIVOT) {
             int p = j;
             double best = fabs(pc[j]);
@@ -364,18 +397,47 @@ __device__ double forward_sweep(const Group& g, const LaneConst& L, const double
     const int c = g.c;
     double* sF = g.sm + SM_M;                        // residual rows of the current node, gathered for lane 7
     const bool use_un = (P[GMPNP_P_KAPPA] != 0.0);   // steady equations never read u_n
+    double* fu = g.ring;                             // [RING][8]: u of a node, slot 7 = 1.0
+    double* fn = g.ring + RING * 8;                  // [RING][8]: u_n of a node, slot 7 = x of the node
+    // stage node first + dir*j into ring slot j % RING (always commits, so group counting stays uniform)
+    auto issue = [&](int j) {
+        const int node = first + dir * j;
+        if (node >= 0 && node < n) {
+            const int s8 = (j & (RING - 1)) * 8;
+            if (c < NC) {
+                cp_async8(fu + s8 + c, up + (long)node * NC + c);
+                if (use_un) cp_async8(fn + s8 + c, unp + (long)node * NC + c);
+            } else {
+                cp_async8(fn + s8 + 7, x + node);
+            }
+        }
+        cp_async_commit();
+    };
+    if (c == 7) {
+#pragma unroll
+        for (int j = 0; j < RING; ++j) fu[j * 8 + 7] = 1.0;
+    }
+#pragma unroll
+    for (int j = 0; j < RING; ++j) issue(j);
     double U0[NC], U1[NC];
     double P10[NC], P11[NC];      // cell behind: block (1,0) and (1,1) columns
     double f1_behind = 0.0;       // cell behind: this lane's residual row at the shared node
 #pragma unroll
     for (int i = 0; i < NC; ++i) { X[i] = 0.0; P10[i] = 0.0; P11[i] = 0.0; }
-    double mine1 = (c < NC) ? up[(long)first * NC + c] : 1.0;   // this lane's component of the current node
-    stage_node(g, mine1, 1, U1);
-    double myN1 = (c < NC && use_un) ? unp[(long)first * NC + c] : 0.0, myN0 = 0.0;
-    double x1 = x[first];
-    // software prefetch: the node ahead is requested one row early
-    double pre_u = (c < NC) ? up[(long)(first + dir) * NC + c] : 1.0;
-    double pre_x = x[first + dir];
+    // read one staged node: all components (broadcast), its coordinate, this lane's own component and u_n
+    auto read_node = [&](int j, double (&U)[NC], double& xk, double& mine, double& myN) {
+        const int s8 = (j & (RING - 1)) * 8;
+        const double2* q = reinterpret_cast<const double2*>(fu + s8);
+        const double2 q0 = q[0], q1 = q[1], q2 = q[2];
+        U[0] = q0.x; U[1] = q0.y; U[2] = q1.x; U[3] = q1.y; U[4] = q2.x; U[5] = q2.y; U[6] = fu[s8 + 6];
+        xk = fn[s8 + 7];
+        mine = fu[s8 + c];                           // lane 7 reads the constant 1.0
+        myN = (c < NC && use_un) ? fn[s8 + c] : 0.0;
+    };
+    cp_async_wait<RING - 1>();
+    __syncwarp(g.mask);
+    double mine1, myN1, x1, myN0 = 0.0;
+    read_node(0, U1, x1, mine1, myN1);
     double rsq = 0.0;
     for (int r = 0; r < rows; ++r) {
         const int k = first + dir * r;               // current node
@@ -386,25 +448,19 @@ __device__ double forward_sweep(const Group& g, const LaneConst& L, const double
         const double myU0 = mine1;
         CellCols cc;
         {
-            g.sm[SM_U + c] = mine1;                  // current node -> slot 0
-            const double mine = pre_u;
-            mine1 = mine;
-            x1 = pre_x;
-            const int k2 = k + 2 * dir;
-            if (k2 >= 0 && k2 < n) {
-                pre_u = (c < NC) ? up[(long)k2 * NC + c] : 1.0;
-                pre_x = x[k2];
-            }
-            stage_node(g, mine, 1, U1);
-            if (c < NC && use_un) myN1 = unp[(long)(k + dir) * NC + c];
+            cp_async_wait<RING - 2>();               // node r+1 has landed (groups 0 .. r+RING-1 are in flight)
+            __syncwarp(g.mask);
+            read_node(r + 1, U1, x1, mine1, myN1);
 #pragma unroll
             for (int i = 0; i < NC; ++i) { cc.c00[i] = 0.0; cc.c01[i] = 0.0; cc.c10[i] = 0.0; cc.c11[i] = 0.0; }
-            cell_columns<NQJ>(P, g.sm + SM_U, L, c, fabs(x1 - x0), U0, U1, myU0, mine, myN0, myN1, cc);
+            cell_columns<NQJ>(P, fu + (r & (RING - 1)) * 8, fu + ((r + 1) & (RING - 1)) * 8, L, c, fabs(x1 - x0), U0, U1,
+                              myU0, mine1, myN0, myN1, cc);
         }
         // ---- row k: A = P10, B = P11 + c00, coupling ahead = c01, d = F1behind + F0 ----------
         sF[c] = f1_behind + cc.f0;                   // this lane's residual row of node k
         f1_behind = cc.f1;
         __syncwarp(g.mask);
+        issue(r + RING);                             // slot of node r is free: every lane is past its reads
         double B[NC], Y[NC];
 #pragma unroll
         for (int i = 0; i < NC; ++i) { B[i] = P11[i] + cc.c00[i]; Y[i] = cc.c01[i]; }
@@ -441,6 +497,8 @@ __device__ double forward_sweep(const Group& g, const LaneConst& L, const double
 #pragma unroll
         for (int i = 0; i < NC; ++i) { X[i] = Y[i]; P10[i] = cc.c10[i]; P11[i] = cc.c11[i]; }
     }
+    cp_async_wait<0>();
+    __syncwarp(g.mask);
     // broadcast this half's residual sum from lane 7
     rsq = __shfl_sync(g.mask, rsq, g.base + 7);
     return rsq;
@@ -454,41 +512,51 @@ __device__ void backward_sweep(const Group& g, int first, int dir, int rows, dou
                                double& mdx, double& mu) {
     if (rows <= 0) return;
     const int c = g.c;
-    const int row = (c < NC) ? c : 0;
-    double r[8];
-    {
-        const double2* src = reinterpret_cast<const double2*>(ws + (long)first * 56 + row * 8);
+    double2* bw = reinterpret_cast<double2*>(g.ring);          // [RING][4][8]: lane c's row of the workspace
+    double* bu = g.ring + RING * 64;                           // [RING][8]:    lane c's component of u
+    double* sx = g.sm + SM_X;
+    // every lane stages what it will read itself, so no cross-lane visibility is needed for the ring
+    auto issue = [&](int q) {
+        if (q < rows && c < NC) {
+            const int s = q & (RING - 1);
+            const long node = first + dir * q;
+            const double* src = ws + node * 56 + c * 8;
 #pragma unroll
-        for (int v = 0; v < 4; ++v) { double2 t = src[v]; r[2 * v] = t.x; r[2 * v + 1] = t.y; }
-    }
-    double ucur = (c < NC) ? up[(long)first * NC + c] : 0.0;
+            for (int v = 0; v < 4; ++v) cp_async16(bw + (s * 4 + v) * 8 + c, src + 2 * v);
+            cp_async8(bu + s * 8 + c, up + node * NC + c);
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int q = 0; q < RING; ++q) issue(q);
     for (int q = 0; q < rows; ++q) {
         const int k = first + dir * q;
-        double rn[8];
-        double unext = 0.0;
-        if (q + 1 < rows) {       // prefetch next row (workspace and u) while this one is reduced
-            const double2* src = reinterpret_cast<const double2*>(ws + (long)(k + dir) * 56 + row * 8);
-#pragma unroll
-            for (int v = 0; v < 4; ++v) { double2 t = src[v]; rn[2 * v] = t.x; rn[2 * v + 1] = t.y; }
-            if (c < NC) unext = up[(long)(k + dir) * NC + c];
-        }
-        double xi = r[7];
-#pragma unroll
-        for (int j = 0; j < NC; ++j) xi -= r[j] * xn[j];
+        const int s = q & (RING - 1);
+        cp_async_wait<RING - 1>();
+        double xi = 0.0;
         if (c < NC) {
+            const double2 r0 = bw[(s * 4 + 0) * 8 + c], r1 = bw[(s * 4 + 1) * 8 + c];
+            const double2 r2 = bw[(s * 4 + 2) * 8 + c], r3 = bw[(s * 4 + 3) * 8 + c];
+            const double ucur = bu[s * 8 + c];
+            xi = r3.y;
+            xi -= r0.x * xn[0]; xi -= r0.y * xn[1]; xi -= r1.x * xn[2]; xi -= r1.y * xn[3];
+            xi -= r2.x * xn[4]; xi -= r2.y * xn[5]; xi -= r3.x * xn[6];
             const double un = ucur - relax * xi;
             up[(long)k * NC + c] = un;
             mdx = fmax(mdx, fabs(xi));
             mu = fmax(mu, fabs(un));
         }
-#pragma unroll
-        for (int j = 0; j < NC; ++j) xn[j] = __shfl_sync(g.mask, xi, g.base + j);
-        if (q + 1 < rows) {
-#pragma unroll
-            for (int v = 0; v < 8; ++v) r[v] = rn[v];
-            ucur = unext;
-        }
+        issue(q + RING);
+        // x_k of all components to every lane (double-buffered: one group barrier per row)
+        double* sxq = sx + (q & 1) * 8;
+        sxq[c] = xi;
+        __syncwarp(g.mask);
+        const double2* xs = reinterpret_cast<const double2*>(sxq);
+        const double2 a0 = xs[0], a1 = xs[1], a2 = xs[2];
+        xn[0] = a0.x; xn[1] = a0.y; xn[2] = a1.x; xn[3] = a1.y; xn[4] = a2.x; xn[5] = a2.y; xn[6] = sxq[6];
     }
+    cp_async_wait<0>();
+    __syncwarp(g.mask);
 }
 
 struct NewtonOut { int iters; double r0, r; int status; };
@@ -616,6 +684,7 @@ __device__ __forceinline__ bool group_setup(Group& g, int batch, int& prob, doub
     const int gid = threadIdx.x >> 3;
     g.sm = smem + gid * SM_GROUP;
     g.psm = smem + GROUPS_PER_BLOCK * SM_GROUP + (threadIdx.x >> 4) * SM_PAIR;
+    g.ring = smem + GROUPS_PER_BLOCK * SM_GROUP + PROBLEMS_PER_BLOCK * SM_PAIR + gid * SM_RING;
     prob = blockIdx.x * PROBLEMS_PER_BLOCK + (threadIdx.x >> 4);
     return prob < batch;
 }
@@ -768,7 +837,7 @@ assemble1d_kernel(int batch, int n, const double* __restrict__ x, const double* 
         CellCols cc;
 #pragma unroll
         for (int i = 0; i < NC; ++i) { cc.c00[i] = 0; cc.c01[i] = 0; cc.c10[i] = 0; cc.c11[i] = 0; }
-        cell_columns<3>(P, g.sm + SM_U, L, c, x[k] - x[k - 1], Um, U0, mym, my0, mynm, myn0, cc);
+        cell_columns<3>(P, g.sm + SM_U, g.sm + SM_U + 8, L, c, x[k] - x[k - 1], Um, U0, mym, my0, mynm, myn0, cc);
 #pragma unroll
         for (int i = 0; i < NC; ++i) { A[i] = cc.c10[i]; B[i] += cc.c11[i]; }
         frow += cc.f1;
@@ -782,7 +851,7 @@ assemble1d_kernel(int batch, int n, const double* __restrict__ x, const double* 
         CellCols cc;
 #pragma unroll
         for (int i = 0; i < NC; ++i) { cc.c00[i] = 0; cc.c01[i] = 0; cc.c10[i] = 0; cc.c11[i] = 0; }
-        cell_columns<3>(P, g.sm + SM_U, L, c, x[k + 1] - x[k], U0, U1, my0, my1, myn0, myn1, cc);
+        cell_columns<3>(P, g.sm + SM_U, g.sm + SM_U + 8, L, c, x[k + 1] - x[k], U0, U1, my0, my1, myn0, myn1, cc);
 #pragma unroll
         for (int i = 0; i < NC; ++i) { B[i] += cc.c00[i]; C[i] = cc.c01[i]; }
         frow += cc.f0;
@@ -855,22 +924,34 @@ __global__ void field1d_kernel(int batch, int n, const double* __restrict__ x, c
 // ---------------------------------------------------------------------------------------
 // host launchers (called from capi.cu)
 // ---------------------------------------------------------------------------------------
+template <bool PIV, int NQ>
+static cudaError_t launch_newton_variant(gmpnp_handle* h, int blocks, size_t smem, int mode, double* d_u, double* d_un_rw,
+                                         const double* d_un_ro, const gmpnp_newton_opts* opts, int n_stage,
+                                         const double* d_Vpath, double* d_hist, int* d_iters, double* d_r0, double* d_r,
+                                         double* d_hfrac, int* d_stage, int* d_status, cudaStream_t st) {
+    using namespace edl1d;
+    cudaError_t e = cudaFuncSetAttribute(newton1d_kernel<PIV, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    newton1d_kernel<PIV, NQ><<<blocks, THREADS, smem, st>>>(mode, h->batch, h->n_nodes, h->d_x, h->d_params, d_u, d_un_rw,
+        d_un_ro, h->d_ws, *opts, n_stage, d_Vpath, d_hist, d_iters, d_r0, d_r, d_hfrac, d_stage, d_status);
+    return cudaGetLastError();
+}
+
 int edl1d_launch_newton(gmpnp_handle* h, int mode, double* d_u, double* d_un_rw, const double* d_un_ro,
                         const gmpnp_newton_opts* opts, int n_stage, const double* d_Vpath, double* d_hist,
                         int* d_iters, double* d_r0, double* d_r, double* d_hfrac, int* d_stage,
                         int* d_status, cudaStream_t st) {
     using namespace edl1d;
     const int blocks = (h->batch + PROBLEMS_PER_BLOCK - 1) / PROBLEMS_PER_BLOCK;
-    const size_t smem = (size_t)(GROUPS_PER_BLOCK * SM_GROUP + PROBLEMS_PER_BLOCK * SM_PAIR) * sizeof(double);
-#define GMPNP_LAUNCH_NEWTON(PIV, NQ)                                                                         \
-    newton1d_kernel<PIV, NQ><<<blocks, THREADS, smem, st>>>(mode, h->batch, h->n_nodes, h->d_x, h->d_params, d_u, \
-        d_un_rw, d_un_ro, h->d_ws, *opts, n_stage, d_Vpath, d_hist, d_iters, d_r0, d_r, d_hfrac, d_stage, d_status)
+    const size_t smem = (size_t)(GROUPS_PER_BLOCK * (SM_GROUP + SM_RING) + PROBLEMS_PER_BLOCK * SM_PAIR) * sizeof(double);
     const bool consistent = (opts->jac_rule == 1);
-    if (opts->pivot) { if (consistent) GMPNP_LAUNCH_NEWTON(true, 2); else GMPNP_LAUNCH_NEWTON(true, 3); }
-    else             { if (consistent) GMPNP_LAUNCH_NEWTON(false, 2); else GMPNP_LAUNCH_NEWTON(false, 3); }
-#undef GMPNP_LAUNCH_NEWTON
+    cudaError_t e;
+#define GMPNP_ARGS h, blocks, smem, mode, d_u, d_un_rw, d_un_ro, opts, n_stage, d_Vpath, d_hist, d_iters, d_r0, d_r, d_hfrac, d_stage, d_status, st
+    if (opts->pivot) e = consistent ? launch_newton_variant<true, 2>(GMPNP_ARGS) : launch_newton_variant<true, 3>(GMPNP_ARGS);
+    else             e = consistent ? launch_newton_variant<false, 2>(GMPNP_ARGS) : launch_newton_variant<false, 3>(GMPNP_ARGS);
+#undef GMPNP_ARGS
     h->launches++;
-    GMPNP_CUDA_TRY(h, cudaGetLastError());
+    GMPNP_CUDA_TRY(h, e);
     return GMPNP_OK;
 }
 
