@@ -25,7 +25,7 @@ constexpr int SM_A = 80;      // sub-diagonal block, column-major [7][8]
 constexpr int SM_M = 136;     // residual rows of the current node [8]
 constexpr int SM_X = 144;     // back-substitution: solution of the neighbour row, double-buffered [2][8]
 constexpr int SM_PC = 160;    // Gauss-Jordan: pivot column broadcast, double-buffered [2][8]
-constexpr int SM_GROUP = 176; // doubles per group
+constexpr int SM_GROUP = 184; // doubles per group (== 8 mod 16: the two groups of a half-warp use disjoint banks)
 // Multi-row staging ring (cp.async, RING rows ahead of the row being processed), per group:
 //   forward sweep : fu[RING][8] = (u_0..u_6 of a node, 1.0), fn[RING][8] = (u_n,0..6 of the node, x of the node)
 //   backward sweep: bw[RING][4][8] double2 = the lane's own 64-B workspace row, bu[RING][8] = the lane's u component
@@ -33,7 +33,7 @@ constexpr int SM_GROUP = 176; // doubles per group
 // and a register prefetch gets spilled by the 255-register forward body, so the rows are staged through
 // shared memory instead of registers.
 constexpr int RING = 8;
-constexpr int SM_RING = RING * 72;  // doubles per group
+constexpr int SM_RING = RING * 72 + 8;  // doubles per group (== 8 mod 16, see SM_GROUP)
 constexpr int GROUPS_PER_BLOCK = 16;
 constexpr int THREADS = GROUPS_PER_BLOCK * 8;
 
@@ -108,8 +108,11 @@ struct CellCols { double c00[NC], c01[NC], c10[NC], c11[NC]; double f0, f1; };
 template <int NQJ>
 __device__ __forceinline__ void cell_columns(const double* __restrict__ P, const double* __restrict__ sU0,
                                              const double* __restrict__ sU1, const LaneConst& L, int c, double h,
-                                             const double (&U0)[NC], const double (&U1)[NC],
+                                             double prow, const double (&U0)[NC], const double (&U1)[NC],
                                              double myU0, double myU1, double myN0, double myN1, CellCols& o) {
+    // prow scales the Poisson row (row NS of every block and the Poisson residual): the solver passes 1/q so
+    // that the row is O(1) like the species rows and the in-block pivot is almost always the diagonal
+    // (q ~ 1e9 in 1D, 1D:193); the materialising kernel passes 1.
     const double ih = fast_rcp(h);
     double g[NC];
 #pragma unroll
@@ -122,8 +125,7 @@ __device__ __forceinline__ void cell_columns(const double* __restrict__ P, const
     // grad phi_0 = -ih, grad phi_1 = +ih
     const double Ga0 = -G * ih, Ga1 = G * ih;
     const double gpa0 = -gp * ih, gpa1 = gp * ih;
-    o.f0 = 0.0; o.f1 = 0.0;
-    if (c == 7) return;
+    // lane 7 (right-hand-side lane) has no column: it shadows the potential lane, its blocks are never read
     const double myg = (myU1 - myU0) * ih;
     // quadrature accumulators: a0 = int u_i D, a1 = int u_i phi_0 D^2, a2 = int u_i phi_1 D^2, mD = int phi_b D
     // (Jacobian rule); own-row residual sums a0F = int u_c D, R0/R1 = int (-R_c) phi_a (residual rule)
@@ -227,21 +229,22 @@ __device__ __forceinline__ void cell_columns(const double* __restrict__ P, const
             double v10 = nuj * (Ga1 * a1[i] - k);
             double v11 = nuj * (Ga1 * a2[i] + k);
             if (i < 5) { v00 += R00[i]; v01 += R01[i]; v10 += R01[i]; v11 += R11[i]; }
-            const bool dg = (i == c);
-            o.c00[i] = v00 + (dg ? d00 : 0.0);
-            o.c01[i] = v01 + (dg ? d01 : 0.0);
-            o.c10[i] = v10 + (dg ? d10 : 0.0);
-            o.c11[i] = v11 + (dg ? d11 : 0.0);
+            const double dg = (i == c) ? 1.0 : 0.0;
+            o.c00[i] = fma(dg, d00, v00);
+            o.c01[i] = fma(dg, d01, v01);
+            o.c10[i] = fma(dg, d10, v10);
+            o.c11[i] = fma(dg, d11, v11);
         }
         // Poisson row:  -eps'_j (gp.grad a) m_b + q z_j c0_j M_ab
         double depsj = 0.0;
         if (c == 0) depsj = (6.0 - P[GMPNP_P_EPSW]) * (1.0 / 55.0) * P[GMPNP_P_EPSH];
         if (c == NS - 1) depsj = (6.0 - P[GMPNP_P_EPSW]) * (1.0 / 55.0) * P[GMPNP_P_EPSC];
-        const double qz = P[GMPNP_P_Q] * P[GMPNP_P_ZC0 + c];
-        o.c00[NS] = -depsj * gpa0 * mb + qz * Md;
-        o.c01[NS] = -depsj * gpa0 * mb + qz * Mo;
-        o.c10[NS] = -depsj * gpa1 * mb + qz * Mo;
-        o.c11[NS] = -depsj * gpa1 * mb + qz * Md;
+        const double qz = P[GMPNP_P_Q] * P[GMPNP_P_ZC0 + c] * prow;
+        const double dm = depsj * mb * prow;
+        o.c00[NS] = -dm * gpa0 + qz * Md;
+        o.c01[NS] = -dm * gpa0 + qz * Mo;
+        o.c10[NS] = -dm * gpa1 + qz * Mo;
+        o.c11[NS] = -dm * gpa1 + qz * Md;
     } else {
         // ---- potential column and the Poisson residual row ------------------------------------
         const double ih2 = ih * ih;
@@ -256,11 +259,11 @@ __device__ __forceinline__ void cell_columns(const double* __restrict__ P, const
         }
         const double wm = P[GMPNP_P_EPSC] * 0.5 * (U0[NS - 1] + U1[NS - 1]) + P[GMPNP_P_EPSH] * 0.5 * (U0[0] + U1[0]);
         const double epsm = P[GMPNP_P_EPSW] * ((55.0 - wm) * (1.0 / 55.0)) + 6.0 * (wm * (1.0 / 55.0));
-        const double v = -ih2 * h * epsm;
+        const double v = -ih2 * h * epsm * prow;
         o.c00[NS] = v; o.c11[NS] = v; o.c01[NS] = -v; o.c10[NS] = -v;
         const double qh = P[GMPNP_P_Q] * h;
-        o.f0 = -gpa0 * h * epsm + qh * ((1.0 / 3.0) * rho0 + (1.0 / 6.0) * rho1);
-        o.f1 = -gpa1 * h * epsm + qh * ((1.0 / 6.0) * rho0 + (1.0 / 3.0) * rho1);
+        o.f0 = (-gpa0 * h * epsm + qh * ((1.0 / 3.0) * rho0 + (1.0 / 6.0) * rho1)) * prow;
+        o.f1 = (-gpa1 * h * epsm + qh * ((1.0 / 6.0) * rho0 + (1.0 / 3.0) * rho1)) * prow;
     }
 }
 
@@ -307,20 +310,16 @@ __device__ __forceinline__ void eliminate_row(const Group& g, bool with_prev, co
     double* sA = g.sm + SM_A;
     const int c = g.c;
     if (with_prev) {
-        if (c < NC) {
+        // A row-major in shared memory (lane c writes column c: conflict-free), rows read back as 4 x 128 bit
 #pragma unroll
-            for (int i = 0; i < NC; ++i) sA[c * 8 + i] = A[i];
-        }
+        for (int i = 0; i < NC; ++i) sA[i * 8 + c] = A[i];
         __syncwarp(g.mask);
         double t[NC];
 #pragma unroll
-        for (int i = 0; i < NC; ++i) t[i] = 0.0;
-#pragma unroll
-        for (int s = 0; s < NC; ++s) {
-            const double* col = sA + s * 8;
-            const double xs = X[s];
-#pragma unroll
-            for (int i = 0; i < NC; ++i) t[i] += col[i] * xs;
+        for (int i = 0; i < NC; ++i) {
+            const double2* row = reinterpret_cast<const double2*>(sA + i * 8);
+            const double2 a0 = row[0], a1 = row[1], a2 = row[2], a3 = row[3];
+            t[i] = a0.x * X[0] + a0.y * X[1] + a1.x * X[2] + a1.y * X[3] + a2.x * X[4] + a2.y * X[5] + a3.x * X[6];
         }
         __syncwarp(g.mask);
         if (c < NC) {
@@ -397,6 +396,7 @@ __device__ double forward_sweep(const Group& g, const LaneConst& L, const double
     const int c = g.c;
     double* sF = g.sm + SM_M;                        // residual rows of the current node, gathered for lane 7
     const bool use_un = (P[GMPNP_P_KAPPA] != 0.0);   // steady equations never read u_n
+    const double qscale = P[GMPNP_P_Q], prow = 1.0 / qscale;
     double* fu = g.ring;                             // [RING][8]: u of a node, slot 7 = 1.0
     double* fn = g.ring + RING * 8;                  // [RING][8]: u_n of a node, slot 7 = x of the node
     // stage node first + dir*j into ring slot j % RING (always commits, so group counting stays uniform)
@@ -451,10 +451,8 @@ __device__ double forward_sweep(const Group& g, const LaneConst& L, const double
             cp_async_wait<RING - 2>();               // node r+1 has landed (groups 0 .. r+RING-1 are in flight)
             __syncwarp(g.mask);
             read_node(r + 1, U1, x1, mine1, myN1);
-#pragma unroll
-            for (int i = 0; i < NC; ++i) { cc.c00[i] = 0.0; cc.c01[i] = 0.0; cc.c10[i] = 0.0; cc.c11[i] = 0.0; }
-            cell_columns<NQJ>(P, fu + (r & (RING - 1)) * 8, fu + ((r + 1) & (RING - 1)) * 8, L, c, fabs(x1 - x0), U0, U1,
-                              myU0, mine1, myN0, myN1, cc);
+            cell_columns<NQJ>(P, fu + (r & (RING - 1)) * 8, fu + ((r + 1) & (RING - 1)) * 8, L, c, fabs(x1 - x0), prow,
+                              U0, U1, myU0, mine1, myN0, myN1, cc);
         }
         // ---- row k: A = P10, B = P11 + c00, coupling ahead = c01, d = F1behind + F0 ----------
         sF[c] = f1_behind + cc.f0;                   // this lane's residual row of node k
@@ -486,8 +484,11 @@ __device__ double forward_sweep(const Group& g, const LaneConst& L, const double
             else Y[NS] = U0[NS] - P[GMPNP_P_V];
         }
         if (c == 7) {
+            // ||b||_2 of the reference's (unscaled) system: undo the Poisson-row scaling except on Dirichlet rows
 #pragma unroll
-            for (int i = 0; i < NC; ++i) rsq += Y[i] * Y[i];
+            for (int i = 0; i < NS; ++i) rsq += Y[i] * Y[i];
+            const double yp = (k == 0 || k == n - 1) ? Y[NS] : Y[NS] * qscale;
+            rsq += yp * yp;
         }
         eliminate_row<PIVOT>(g, r > 0, P10, B, Y, X, singular);
         // ---- store (coupling'_k | d'_k) ------------------------------------------------------
@@ -837,7 +838,7 @@ assemble1d_kernel(int batch, int n, const double* __restrict__ x, const double* 
         CellCols cc;
 #pragma unroll
         for (int i = 0; i < NC; ++i) { cc.c00[i] = 0; cc.c01[i] = 0; cc.c10[i] = 0; cc.c11[i] = 0; }
-        cell_columns<3>(P, g.sm + SM_U, g.sm + SM_U + 8, L, c, x[k] - x[k - 1], Um, U0, mym, my0, mynm, myn0, cc);
+        cell_columns<3>(P, g.sm + SM_U, g.sm + SM_U + 8, L, c, x[k] - x[k - 1], 1.0, Um, U0, mym, my0, mynm, myn0, cc);
 #pragma unroll
         for (int i = 0; i < NC; ++i) { A[i] = cc.c10[i]; B[i] += cc.c11[i]; }
         frow += cc.f1;
@@ -851,7 +852,7 @@ assemble1d_kernel(int batch, int n, const double* __restrict__ x, const double* 
         CellCols cc;
 #pragma unroll
         for (int i = 0; i < NC; ++i) { cc.c00[i] = 0; cc.c01[i] = 0; cc.c10[i] = 0; cc.c11[i] = 0; }
-        cell_columns<3>(P, g.sm + SM_U, g.sm + SM_U + 8, L, c, x[k + 1] - x[k], U0, U1, my0, my1, myn0, myn1, cc);
+        cell_columns<3>(P, g.sm + SM_U, g.sm + SM_U + 8, L, c, x[k + 1] - x[k], 1.0, U0, U1, my0, my1, myn0, myn1, cc);
 #pragma unroll
         for (int i = 0; i < NC; ++i) { B[i] += cc.c00[i]; C[i] = cc.c01[i]; }
         frow += cc.f0;
