@@ -19,20 +19,27 @@ namespace edl1d {
 
 constexpr int NS = 6;
 constexpr int NC = 7;
-constexpr int SM_P = 0;       // params            [64]
-constexpr int SM_U = 64;      // staged nodal vals [2][8]  (slot 7 holds the constant 1.0)
-constexpr int SM_A = 80;      // sub-diagonal block, column-major [7][8]
-constexpr int SM_M = 136;     // residual rows of the current node [8]
-constexpr int SM_X = 144;     // back-substitution: solution of the neighbour row, double-buffered [2][8]
-constexpr int SM_PC = 160;    // Gauss-Jordan: pivot column broadcast, double-buffered [2][8]
-constexpr int SM_GROUP = 184; // doubles per group (== 8 mod 16: the two groups of a half-warp use disjoint banks)
+// Shared memory of newton1d_kernel, per 8-lane group (doubles):
+constexpr int SM_A = 0;       // sub-diagonal block A_k = block (1,0) of the cell behind, row-major, double-buffered [2][7][8]
+constexpr int SM_B = 112;     // block (1,1) of the cell behind, [i*8+c], double-buffered [2][7][8]
+constexpr int SM_M = 224;     // residual rows of the current node [8]
+constexpr int SM_X = 232;     // back-substitution: solution of the neighbour row, double-buffered [2][8]
+constexpr int SM_PC = 248;    // Gauss-Jordan: pivot column broadcast, double-buffered [2][8]
+constexpr int SM_GROUP = 264; // doubles per group (== 8 mod 16: the two groups of a half-warp use disjoint banks)
+// plus, per pair of groups (= problem): the parameter record [64]; the merge area of a pair aliases the
+// staging ring of its bottom-half group (idle between the two sweeps).
+// Shared memory of assemble1d_kernel, per group: params [64], staged nodal values [2][8], residual rows [8]
+constexpr int AS_P = 0, AS_U = 64, AS_M = 80, AS_GROUP = 88;
 // Multi-row staging ring (cp.async, RING rows ahead of the row being processed), per group:
 //   forward sweep : fu[RING][8] = (u_0..u_6 of a node, 1.0), fn[RING][8] = (u_n,0..6 of the node, x of the node)
 //   backward sweep: bw[RING][4][8] double2 = the lane's own 64-B workspace row, bu[RING][8] = the lane's u component
 // The two sweeps alias the same memory.  One row of global-load latency (~1 us) is several backward rows long,
 // and a register prefetch gets spilled by the 255-register forward body, so the rows are staged through
 // shared memory instead of registers.
-constexpr int RING = 8;
+#ifndef GMPNP_RING
+#define GMPNP_RING 4
+#endif
+constexpr int RING = GMPNP_RING;
 constexpr int SM_RING = RING * 72 + 8;  // doubles per group (== 8 mod 16, see SM_GROUP)
 constexpr int GROUPS_PER_BLOCK = 16;
 constexpr int THREADS = GROUPS_PER_BLOCK * 8;
@@ -105,11 +112,16 @@ __device__ __forceinline__ void lane_consts(const double* P, int c, LaneConst& L
 //              residual pass (lane 7 only collects the rows, see forward_sweep)
 struct CellCols { double c00[NC], c01[NC], c10[NC], c11[NC]; double f0, f1; };
 
-template <int NQJ>
+// STASH: the blocks of local node 1 (c10, c11: needed by the NEXT row) go straight to shared memory
+// (s10[i*8+c], s11[i*8+c]) instead of staying in registers across the elimination of the current row.
+template <int NQJ, bool STASH>
 __device__ __forceinline__ void cell_columns(const double* __restrict__ P, const double* __restrict__ sU0,
                                              const double* __restrict__ sU1, const LaneConst& L, int c, double h,
                                              double prow, const double (&U0)[NC], const double (&U1)[NC],
-                                             double myU0, double myU1, double myN0, double myN1, CellCols& o) {
+                                             double myU0, double myU1, double myN0, double myN1, CellCols& o,
+                                             double* __restrict__ s10 = nullptr, double* __restrict__ s11 = nullptr) {
+    auto put10 = [&](int i, double v) { if (STASH) s10[i * 8 + c] = v; else o.c10[i] = v; };
+    auto put11 = [&](int i, double v) { if (STASH) s11[i * 8 + c] = v; else o.c11[i] = v; };
     // prow scales the Poisson row (row NS of every block and the Poisson residual): the solver passes 1/q so
     // that the row is O(1) like the species rows and the in-block pivot is almost always the diagonal
     // (q ~ 1e9 in 1D, 1D:193); the materialising kernel passes 1.
@@ -232,8 +244,8 @@ __device__ __forceinline__ void cell_columns(const double* __restrict__ P, const
             const double dg = (i == c) ? 1.0 : 0.0;
             o.c00[i] = fma(dg, d00, v00);
             o.c01[i] = fma(dg, d01, v01);
-            o.c10[i] = fma(dg, d10, v10);
-            o.c11[i] = fma(dg, d11, v11);
+            put10(i, fma(dg, d10, v10));
+            put11(i, fma(dg, d11, v11));
         }
         // Poisson row:  -eps'_j (gp.grad a) m_b + q z_j c0_j M_ab
         double depsj = 0.0;
@@ -243,8 +255,8 @@ __device__ __forceinline__ void cell_columns(const double* __restrict__ P, const
         const double dm = depsj * mb * prow;
         o.c00[NS] = -dm * gpa0 + qz * Md;
         o.c01[NS] = -dm * gpa0 + qz * Mo;
-        o.c10[NS] = -dm * gpa1 + qz * Mo;
-        o.c11[NS] = -dm * gpa1 + qz * Md;
+        put10(NS, -dm * gpa1 + qz * Mo);
+        put11(NS, -dm * gpa1 + qz * Md);
     } else {
         // ---- potential column and the Poisson residual row ------------------------------------
         const double ih2 = ih * ih;
@@ -253,14 +265,14 @@ __device__ __forceinline__ void cell_columns(const double* __restrict__ P, const
         for (int i = 0; i < NS; ++i) {
             const double iU = 0.5 * h * (U0[i] + U1[i]);
             const double v = P[GMPNP_P_Z + i] * ih2 * iU;
-            o.c00[i] = v; o.c11[i] = v; o.c01[i] = -v; o.c10[i] = -v;
+            o.c00[i] = v; put11(i, v); o.c01[i] = -v; put10(i, -v);
             rho0 += P[GMPNP_P_ZC0 + i] * U0[i];
             rho1 += P[GMPNP_P_ZC0 + i] * U1[i];
         }
         const double wm = P[GMPNP_P_EPSC] * 0.5 * (U0[NS - 1] + U1[NS - 1]) + P[GMPNP_P_EPSH] * 0.5 * (U0[0] + U1[0]);
         const double epsm = P[GMPNP_P_EPSW] * ((55.0 - wm) * (1.0 / 55.0)) + 6.0 * (wm * (1.0 / 55.0));
         const double v = -ih2 * h * epsm * prow;
-        o.c00[NS] = v; o.c11[NS] = v; o.c01[NS] = -v; o.c10[NS] = -v;
+        o.c00[NS] = v; put11(NS, v); o.c01[NS] = -v; put10(NS, -v);
         const double qh = P[GMPNP_P_Q] * h;
         o.f0 = (-gpa0 * h * epsm + qh * ((1.0 / 3.0) * rho0 + (1.0 / 6.0) * rho1)) * prow;
         o.f1 = (-gpa1 * h * epsm + qh * ((1.0 / 6.0) * rho0 + (1.0 / 3.0) * rho1)) * prow;
@@ -274,7 +286,9 @@ struct Group {
     int c;            // lane in group (column id)
     unsigned mask;    // participation mask of the 8 lanes
     int base;         // first lane of the group inside the warp
-    double* sm;       // per-group shared memory
+    const double* P;  // parameter record of the problem (shared memory)
+    double* sm;       // per-group shared memory (work area)
+    double* su;       // assemble1d_kernel only: staged nodal values [2][8]
     double* ring;     // per-group staging ring (SM_RING doubles, 16-B aligned)
     // two-sided elimination: two groups (a "pair", 16 lanes) share one problem
     int half;         // 0: sweeps down from node 0; 1: sweeps up from node n-1
@@ -286,7 +300,7 @@ struct Group {
 // publish this lane's component of a node (already in a register) in sU[slot] and give every lane
 // a register copy of all 7 components
 __device__ __forceinline__ void stage_node(const Group& g, double mine, int slot, double (&U)[NC]) {
-    double* sU = g.sm + SM_U + slot * 8;
+    double* sU = g.su + slot * 8;
     sU[g.c] = (g.c < NC) ? mine : 1.0;
     __syncwarp(g.mask);
 #pragma unroll
@@ -305,15 +319,12 @@ __device__ __forceinline__ void load_node(const Group& g, const double* __restri
 // search so all agree on the pivot row without a shared-memory round trip; rows are swapped physically so
 // all register indexing is static.  On exit Y = eliminated coupling column (lanes<7) / rhs (lane 7).
 template <bool PIVOT>
-__device__ __forceinline__ void eliminate_row(const Group& g, bool with_prev, const double (&A)[NC], double (&B)[NC],
+__device__ __forceinline__ void eliminate_row(const Group& g, const double* __restrict__ sA, double (&B)[NC],
                                               double (&Y)[NC], const double (&X)[NC], int& singular) {
-    double* sA = g.sm + SM_A;
     const int c = g.c;
-    if (with_prev) {
-        // A row-major in shared memory (lane c writes column c: conflict-free), rows read back as 4 x 128 bit
-#pragma unroll
-        for (int i = 0; i < NC; ++i) sA[i * 8 + c] = A[i];
-        __syncwarp(g.mask);
+    if (sA != nullptr) {
+        // A row-major in shared memory (lane c wrote column c: conflict-free), rows read back as 4 x 128 bit;
+        // the writes are ordered before these reads by the group barrier after the residual gather
         double t[NC];
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
@@ -321,7 +332,6 @@ __device__ __forceinline__ void eliminate_row(const Group& g, bool with_prev, co
             const double2 a0 = row[0], a1 = row[1], a2 = row[2], a3 = row[3];
             t[i] = a0.x * X[0] + a0.y * X[1] + a1.x * X[2] + a1.y * X[3] + a2.x * X[4] + a2.y * X[5] + a3.x * X[6];
         }
-        __syncwarp(g.mask);
         if (c < NC) {
 #pragma unroll
             for (int i = 0; i < NC; ++i) B[i] -= t[i];
@@ -392,7 +402,7 @@ __device__ double forward_sweep(const Group& g, const LaneConst& L, const double
                                 int first, int dir, int rows, const double* __restrict__ up,
                                 const double* __restrict__ unp, double* __restrict__ ws, double (&X)[NC],
                                 int& singular) {
-    const double* P = g.sm + SM_P;
+    const double* P = g.P;
     const int c = g.c;
     double* sF = g.sm + SM_M;                        // residual rows of the current node, gathered for lane 7
     const bool use_un = (P[GMPNP_P_KAPPA] != 0.0);   // steady equations never read u_n
@@ -419,49 +429,48 @@ __device__ double forward_sweep(const Group& g, const LaneConst& L, const double
     }
 #pragma unroll
     for (int j = 0; j < RING; ++j) issue(j);
-    double U0[NC], U1[NC];
-    double P10[NC], P11[NC];      // cell behind: block (1,0) and (1,1) columns
     double f1_behind = 0.0;       // cell behind: this lane's residual row at the shared node
 #pragma unroll
-    for (int i = 0; i < NC; ++i) { X[i] = 0.0; P10[i] = 0.0; P11[i] = 0.0; }
-    // read one staged node: all components (broadcast), its coordinate, this lane's own component and u_n
-    auto read_node = [&](int j, double (&U)[NC], double& xk, double& mine, double& myN) {
-        const int s8 = (j & (RING - 1)) * 8;
-        const double2* q = reinterpret_cast<const double2*>(fu + s8);
-        const double2 q0 = q[0], q1 = q[1], q2 = q[2];
-        U[0] = q0.x; U[1] = q0.y; U[2] = q1.x; U[3] = q1.y; U[4] = q2.x; U[5] = q2.y; U[6] = fu[s8 + 6];
-        xk = fn[s8 + 7];
-        mine = fu[s8 + c];                           // lane 7 reads the constant 1.0
-        myN = (c < NC && use_un) ? fn[s8 + c] : 0.0;
-    };
-    cp_async_wait<RING - 1>();
-    __syncwarp(g.mask);
-    double mine1, myN1, x1, myN0 = 0.0;
-    read_node(0, U1, x1, mine1, myN1);
+    for (int i = 0; i < NC; ++i) X[i] = 0.0;
     double rsq = 0.0;
     for (int r = 0; r < rows; ++r) {
         const int k = first + dir * r;               // current node
-#pragma unroll
-        for (int i = 0; i < NC; ++i) U0[i] = U1[i];
-        myN0 = myN1;
-        const double x0 = x1;
-        const double myU0 = mine1;
-        CellCols cc;
-        {
-            cp_async_wait<RING - 2>();               // node r+1 has landed (groups 0 .. r+RING-1 are in flight)
-            __syncwarp(g.mask);
-            read_node(r + 1, U1, x1, mine1, myN1);
-            cell_columns<NQJ>(P, fu + (r & (RING - 1)) * 8, fu + ((r + 1) & (RING - 1)) * 8, L, c, fabs(x1 - x0), prow,
-                              U0, U1, myU0, mine1, myN0, myN1, cc);
-        }
-        // ---- row k: A = P10, B = P11 + c00, coupling ahead = c01, d = F1behind + F0 ----------
-        sF[c] = f1_behind + cc.f0;                   // this lane's residual row of node k
-        f1_behind = cc.f1;
+        const int s0 = (r & (RING - 1)) * 8, s1 = ((r + 1) & (RING - 1)) * 8;
+        // blocks (1,0) / (1,1) of a cell are produced one row before they are used: double-buffered in shared memory
+        double* sA_cur = g.sm + SM_A + (r & 1) * 56;
+        double* sA_nxt = g.sm + SM_A + ((r + 1) & 1) * 56;
+        double* sB_cur = g.sm + SM_B + (r & 1) * 56;
+        double* sB_nxt = g.sm + SM_B + ((r + 1) & 1) * 56;
+        cp_async_wait<RING - 2>();                   // node r+1 has landed (groups 0 .. r+RING-1 are in flight)
         __syncwarp(g.mask);
-        issue(r + RING);                             // slot of node r is free: every lane is past its reads
         double B[NC], Y[NC];
+        {
+            // nodal values of the cell ahead (local node 0 = current node) straight from the staging ring
+            double U0[NC], U1[NC];
+            {
+                const double2* q = reinterpret_cast<const double2*>(fu + s0);
+                const double2 q0 = q[0], q1 = q[1], q2 = q[2];
+                U0[0] = q0.x; U0[1] = q0.y; U0[2] = q1.x; U0[3] = q1.y; U0[4] = q2.x; U0[5] = q2.y; U0[6] = fu[s0 + 6];
+                const double2* w = reinterpret_cast<const double2*>(fu + s1);
+                const double2 w0 = w[0], w1 = w[1], w2 = w[2];
+                U1[0] = w0.x; U1[1] = w0.y; U1[2] = w1.x; U1[3] = w1.y; U1[4] = w2.x; U1[5] = w2.y; U1[6] = fu[s1 + 6];
+            }
+            const double h = fabs(fn[s1 + 7] - fn[s0 + 7]);
+            const double myU0 = fu[s0 + c], myU1 = fu[s1 + c];          // lane 7 reads the constant 1.0
+            const double myN0 = (c < NC && use_un) ? fn[s0 + c] : 0.0, myN1 = (c < NC && use_un) ? fn[s1 + c] : 0.0;
+            CellCols cc;
+            cell_columns<NQJ, true>(P, fu + s0, fu + s1, L, c, h, prow, U0, U1, myU0, myU1, myN0, myN1, cc, sA_nxt, sB_nxt);
+            // ---- row k: A = (1,0) behind, B = (1,1) behind + c00, coupling ahead = c01, d = F1behind + F0 ----
 #pragma unroll
-        for (int i = 0; i < NC; ++i) { B[i] = P11[i] + cc.c00[i]; Y[i] = cc.c01[i]; }
+            for (int i = 0; i < NC; ++i) { B[i] = cc.c00[i]; Y[i] = cc.c01[i]; }
+            sF[c] = f1_behind + cc.f0;               // this lane's residual row of node k
+            f1_behind = cc.f1;
+        }
+        if (r > 0) {
+#pragma unroll
+            for (int i = 0; i < NC; ++i) B[i] += sB_cur[i * 8 + c];
+        }
+        __syncwarp(g.mask);
         if (c == 7) {
 #pragma unroll
             for (int i = 0; i < NC; ++i) Y[i] = sF[i];      // lane 7: rhs lives in Y
@@ -476,12 +485,12 @@ __device__ double forward_sweep(const Group& g, const LaneConst& L, const double
 #pragma unroll
             for (int i = 0; i < NC; ++i) {
                 if (c < NC) { B[i] = (i == c) ? 1.0 : 0.0; Y[i] = 0.0; }
-                else Y[i] = U0[i] - ((i < NS) ? 1.0 : 0.0);
+                else Y[i] = fu[s0 + i] - ((i < NS) ? 1.0 : 0.0);
             }
         }
         if (k == 0) {
             if (c < NC) { B[NS] = (c == NS) ? 1.0 : 0.0; Y[NS] = 0.0; }
-            else Y[NS] = U0[NS] - P[GMPNP_P_V];
+            else Y[NS] = fu[s0 + NS] - P[GMPNP_P_V];
         }
         if (c == 7) {
             // ||b||_2 of the reference's (unscaled) system: undo the Poisson-row scaling except on Dirichlet rows
@@ -490,13 +499,12 @@ __device__ double forward_sweep(const Group& g, const LaneConst& L, const double
             const double yp = (k == 0 || k == n - 1) ? Y[NS] : Y[NS] * qscale;
             rsq += yp * yp;
         }
-        eliminate_row<PIVOT>(g, r > 0, P10, B, Y, X, singular);
+        issue(r + RING);                             // slot of node r is free: every lane is past its last read of it
+        eliminate_row<PIVOT>(g, r > 0 ? sA_cur : nullptr, B, Y, X, singular);
         // ---- store (coupling'_k | d'_k) ------------------------------------------------------
         double* w = ws + (long)k * 56;
 #pragma unroll
-        for (int i = 0; i < NC; ++i) w[i * 8 + c] = Y[i];
-#pragma unroll
-        for (int i = 0; i < NC; ++i) { X[i] = Y[i]; P10[i] = cc.c10[i]; P11[i] = cc.c11[i]; }
+        for (int i = 0; i < NC; ++i) { w[i * 8 + c] = Y[i]; X[i] = Y[i]; }
     }
     cp_async_wait<0>();
     __syncwarp(g.mask);
@@ -572,27 +580,24 @@ __device__ double factor_problem(const Group& g, const LaneConst& L, const doubl
     double X[NC];
     const int first = g.half ? n - 1 : 0, dir = g.half ? -1 : 1, rows = g.half ? n - m : m;
     double rsq = forward_sweep<PIVOT, NQJ>(g, L, x, n, first, dir, rows, up, unp, ws, X, singular);
-    // merge: bottom publishes (A'_m | d'_m)
+    // merge: bottom publishes (A'_m | d'_m) row-major: psm[i*8 + c], column 7 = d'_m
     if (g.half) {
 #pragma unroll
-        for (int i = 0; i < NC; ++i) g.psm[g.c * 8 + i] = X[i];
+        for (int i = 0; i < NC; ++i) g.psm[i * 8 + g.c] = X[i];
     }
     __syncwarp(g.pmask);
     double Y[NC];
 #pragma unroll
     for (int i = 0; i < NC; ++i) Y[i] = 0.0;
     if (!g.half) {
-        double A[NC], B[NC];
+        double B[NC];
 #pragma unroll
-        for (int i = 0; i < NC; ++i) {
-            A[i] = g.psm[g.c * 8 + i];
-            B[i] = (i == g.c) ? 1.0 : 0.0;
-        }
+        for (int i = 0; i < NC; ++i) B[i] = (i == g.c) ? 1.0 : 0.0;
         if (g.c == 7) {
 #pragma unroll
-            for (int i = 0; i < NC; ++i) Y[i] = A[i];          // rhs d'_m
+            for (int i = 0; i < NC; ++i) Y[i] = g.psm[i * 8 + 7];          // rhs d'_m
         }
-        eliminate_row<PIVOT>(g, true, A, B, Y, X, singular);
+        eliminate_row<PIVOT>(g, g.psm, B, Y, X, singular);
     }
     __syncwarp(g.pmask);
 #pragma unroll
@@ -671,7 +676,6 @@ __device__ NewtonOut newton_solve(const Group& g, const LaneConst& L, const doub
     return out;
 }
 
-constexpr int SM_PAIR = 64;                              // doubles of merge area per pair
 constexpr int PROBLEMS_PER_BLOCK = GROUPS_PER_BLOCK / 2;
 
 __device__ __forceinline__ bool group_setup(Group& g, int batch, int& prob, double* smem) {
@@ -684,15 +688,19 @@ __device__ __forceinline__ bool group_setup(Group& g, int batch, int& prob, doub
     g.pmask = 0xFFFFu << g.pbase;
     const int gid = threadIdx.x >> 3;
     g.sm = smem + gid * SM_GROUP;
-    g.psm = smem + GROUPS_PER_BLOCK * SM_GROUP + (threadIdx.x >> 4) * SM_PAIR;
-    g.ring = smem + GROUPS_PER_BLOCK * SM_GROUP + PROBLEMS_PER_BLOCK * SM_PAIR + gid * SM_RING;
+    g.ring = smem + GROUPS_PER_BLOCK * SM_GROUP + gid * SM_RING;
+    g.psm = smem + GROUPS_PER_BLOCK * SM_GROUP + (gid | 1) * SM_RING;      // ring of the pair's bottom-half group
+    g.P = smem + GROUPS_PER_BLOCK * (SM_GROUP + SM_RING) + (gid >> 1) * GMPNP_NPAR;
+    g.su = nullptr;
     prob = blockIdx.x * PROBLEMS_PER_BLOCK + (threadIdx.x >> 4);
     return prob < batch;
 }
 
+// parameter record of the pair's problem -> shared memory (both groups of the pair cooperate)
 __device__ __forceinline__ void load_params(const Group& g, const double* __restrict__ params, int prob) {
-    for (int i = g.c; i < GMPNP_NPAR; i += 8) g.sm[SM_P + i] = params[(long)prob * GMPNP_NPAR + i];
-    __syncwarp(g.mask);
+    double* P = const_cast<double*>(g.P);
+    for (int i = (threadIdx.x & 15); i < GMPNP_NPAR; i += 16) P[i] = params[(long)prob * GMPNP_NPAR + i];
+    __syncwarp(g.pmask);
 }
 
 // mode 0: single Newton solve (gmpnp_newton_1d)
@@ -713,7 +721,7 @@ newton1d_kernel(int mode, int batch, int n, const double* __restrict__ x, const 
     Group g; int prob;
     if (!group_setup(g, batch, prob, smem)) return;
     load_params(g, params, prob);
-    double* P = g.sm + SM_P;
+    double* P = const_cast<double*>(g.P);
     double* up = u + (long)prob * n * NC;
     double* ws = wsall + (long)prob * n * 56;
     LaneConst L;
@@ -758,7 +766,7 @@ newton1d_kernel(int mode, int batch, int n, const double* __restrict__ x, const 
                 else if (f > hohp && f <= (hohp + 0.4) && frac <= 1.0) frac = frac * 1.04;
                 else if (f > (hohp + 0.4) && frac <= 1.0) frac = frac * 1.15;
                 __syncwarp(g.pmask);
-                if (g.c == 0) {
+                if (writer) {
                     P[GMPNP_P_JFLUX + 1] = -1.0 * P[GMPNP_P_JOHPRE] * (1 - frac);
                     P[GMPNP_P_JFLUX + 0] = P[GMPNP_P_JHPRE] * frac;
                 }
@@ -774,7 +782,7 @@ newton1d_kernel(int mode, int batch, int n, const double* __restrict__ x, const 
     }
     // mode 2: steady continuation
     {
-        if (g.c == 0) P[GMPNP_P_KAPPA] = 0.0;
+        if (writer) P[GMPNP_P_KAPPA] = 0.0;
         __syncwarp(g.pmask);
         int st = GMPNP_CONVERGED, done = 0;
         const double xtol_final = opts.xtol;
@@ -784,7 +792,7 @@ newton1d_kernel(int mode, int batch, int n, const double* __restrict__ x, const 
             const bool final_stage = (s + 1 == n_stage) || isnan(Vpath[(long)prob * n_stage + s + 1]);
             opts.xtol = (final_stage || !(opts.xtol_path > 0.0)) ? xtol_final : opts.xtol_path;
             __syncwarp(g.pmask);
-            if (g.c == 0) P[GMPNP_P_V] = Vs;
+            if (writer) P[GMPNP_P_V] = Vs;
             __syncwarp(g.pmask);
             // kappa = 0: u_n is never read for its value; pass u itself
             NewtonOut o = newton_solve<PIVOT, NQJ>(g, L, x, n, up, up, ws, opts);
@@ -811,18 +819,20 @@ assemble1d_kernel(int batch, int n, const double* __restrict__ x, const double* 
     Group g;
     g.c = lane & 7; g.base = lane & ~7; g.mask = 0xFFu << g.base;
     const int gid = threadIdx.x >> 3;
-    g.sm = smem + gid * SM_GROUP;
+    double* base = smem + gid * AS_GROUP;
+    g.sm = base; g.su = base + AS_U; g.P = base + AS_P;
     const long item = (long)blockIdx.x * GROUPS_PER_BLOCK + gid;
     if (item >= (long)batch * n) return;
     const int prob = (int)(item / n), k = (int)(item % n);
-    load_params(g, params, prob);
-    const double* P = g.sm + SM_P;
+    for (int i = g.c; i < GMPNP_NPAR; i += 8) base[AS_P + i] = params[(long)prob * GMPNP_NPAR + i];
+    __syncwarp(g.mask);
+    const double* P = g.P;
     LaneConst L;
     lane_consts(P, g.c, L);
     const double* up = u + (long)prob * n * NC;
     const double* unp = un + (long)prob * n * NC;
     const int c = g.c;
-    double* sF = g.sm + SM_M;
+    double* sF = base + AS_M;
     double A[NC], B[NC], C[NC];
 #pragma unroll
     for (int i = 0; i < NC; ++i) { A[i] = 0.0; B[i] = 0.0; C[i] = 0.0; }
@@ -838,21 +848,21 @@ assemble1d_kernel(int batch, int n, const double* __restrict__ x, const double* 
         CellCols cc;
 #pragma unroll
         for (int i = 0; i < NC; ++i) { cc.c00[i] = 0; cc.c01[i] = 0; cc.c10[i] = 0; cc.c11[i] = 0; }
-        cell_columns<3>(P, g.sm + SM_U, g.sm + SM_U + 8, L, c, x[k] - x[k - 1], 1.0, Um, U0, mym, my0, mynm, myn0, cc);
+        cell_columns<3, false>(P, g.su, g.su + 8, L, c, x[k] - x[k - 1], 1.0, Um, U0, mym, my0, mynm, myn0, cc);
 #pragma unroll
         for (int i = 0; i < NC; ++i) { A[i] = cc.c10[i]; B[i] += cc.c11[i]; }
         frow += cc.f1;
     }
     __syncwarp(g.mask);
     if (k + 1 < n) {
-        g.sm[SM_U + c] = my0;
+        g.su[c] = my0;
         const double my1 = (c < NC) ? up[(long)(k + 1) * NC + c] : 1.0;
         const double myn1 = (c < NC) ? unp[(long)(k + 1) * NC + c] : 0.0;
         stage_node(g, my1, 1, U1);
         CellCols cc;
 #pragma unroll
         for (int i = 0; i < NC; ++i) { cc.c00[i] = 0; cc.c01[i] = 0; cc.c10[i] = 0; cc.c11[i] = 0; }
-        cell_columns<3>(P, g.sm + SM_U, g.sm + SM_U + 8, L, c, x[k + 1] - x[k], 1.0, U0, U1, my0, my1, myn0, myn1, cc);
+        cell_columns<3, false>(P, g.su, g.su + 8, L, c, x[k + 1] - x[k], 1.0, U0, U1, my0, my1, myn0, myn1, cc);
 #pragma unroll
         for (int i = 0; i < NC; ++i) { B[i] += cc.c00[i]; C[i] = cc.c01[i]; }
         frow += cc.f0;
@@ -944,7 +954,7 @@ int edl1d_launch_newton(gmpnp_handle* h, int mode, double* d_u, double* d_un_rw,
                         int* d_status, cudaStream_t st) {
     using namespace edl1d;
     const int blocks = (h->batch + PROBLEMS_PER_BLOCK - 1) / PROBLEMS_PER_BLOCK;
-    const size_t smem = (size_t)(GROUPS_PER_BLOCK * (SM_GROUP + SM_RING) + PROBLEMS_PER_BLOCK * SM_PAIR) * sizeof(double);
+    const size_t smem = (size_t)(GROUPS_PER_BLOCK * (SM_GROUP + SM_RING) + PROBLEMS_PER_BLOCK * GMPNP_NPAR) * sizeof(double);
     const bool consistent = (opts->jac_rule == 1);
     cudaError_t e;
 #define GMPNP_ARGS h, blocks, smem, mode, d_u, d_un_rw, d_un_ro, opts, n_stage, d_Vpath, d_hist, d_iters, d_r0, d_r, d_hfrac, d_stage, d_status, st
@@ -961,7 +971,7 @@ int edl1d_launch_assemble(gmpnp_handle* h, const double* d_u, const double* d_un
     using namespace edl1d;
     const long items = (long)h->batch * h->n_nodes;
     const int blocks = (int)((items + GROUPS_PER_BLOCK - 1) / GROUPS_PER_BLOCK);
-    const size_t smem = (size_t)GROUPS_PER_BLOCK * SM_GROUP * sizeof(double);
+    const size_t smem = (size_t)GROUPS_PER_BLOCK * AS_GROUP * sizeof(double);
     assemble1d_kernel<<<blocks, THREADS, smem, st>>>(h->batch, h->n_nodes, h->d_x, h->d_params, d_u, d_un, d_F, d_J);
     h->launches++;
     GMPNP_CUDA_TRY(h, cudaGetLastError());
