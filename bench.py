@@ -36,6 +36,10 @@ def parse():
     ap.add_argument("--voltages", type=int, default=256, help="voltage points per chain (256 = config 2)")
     ap.add_argument("--cpu-sample", type=int, default=16, help="sweep points timed on the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dv", type=float, default=0.75, help="largest voltage increment of the continuation [V_T]")
+    ap.add_argument("--xtol-path", type=float, default=1.0,
+                    help="increment tolerance of the intermediate continuation stages (1.0 = one Newton corrector "
+                         "per voltage increment); the final stage always converges to xtol = 1e-12")
     return ap.parse_args()
 
 
@@ -43,7 +47,7 @@ def parse():
 # CPU arm: the oracle (port of the reference's algorithm class: P1 assembly + sparse LU + Newton)
 # --------------------------------------------------------------------------------------------
 def _cpu_solve_point(args):
-    cation, conc, L_n, V = args
+    cation, conc, L_n, V, dv, xtol_path = args
     import numpy as np
     from gmpnp_b200 import meshio, params
     from gmpnp_b200.sweep import voltage_paths
@@ -51,31 +55,31 @@ def _cpu_solve_point(args):
     os.environ["OMP_NUM_THREADS"] = "1"
     mesh = meshio.load_mesh(params.mesh_name_1d(L_n))
     prm = params.params_1d(concentration_elec=conc, cation=cation, L_n=L_n, voltage_multiplier=V)
-    path = voltage_paths(np.array([V]), 0.5)[0]
+    path = voltage_paths(np.array([V]), dv)[0]
     path = path[~np.isnan(path)]
     t = time.perf_counter()
     try:
-        u, its = osolver.steady_1d(mesh.x[:, 0], prm, path, xtol=1e-12, xtol_path=1e-1)
+        u, its = osolver.steady_1d(mesh.x[:, 0], prm, path, xtol=1e-12, xtol_path=xtol_path, jac_rule=1)
         ok = True
     except RuntimeError:
         its, ok = [], False
     return time.perf_counter() - t, sum(its), ok
 
 
-def cpu_sample_points(n_sample, n_voltages):
+def cpu_sample_points(n_sample, n_voltages, dv=0.75, xtol_path=1.0):
     import numpy as np
     from gmpnp_b200.sweep import config2_points
     pts = config2_points(n_voltages)
     rng = np.random.default_rng(0)
     sel = rng.choice(len(pts), size=min(n_sample, len(pts)), replace=False)
-    return [(pts[i].cation, pts[i].conc, pts[i].L_n, pts[i].V) for i in sorted(sel)]
+    return [(pts[i].cation, pts[i].conc, pts[i].L_n, pts[i].V, dv, xtol_path) for i in sorted(sel)]
 
 
-def run_cpu(n_sample, n_voltages, cores=None):
+def run_cpu(n_sample, n_voltages, cores=None, dv=0.75, xtol_path=1.0):
     import multiprocessing as mp
     cores = cores or (os.cpu_count() or 1)
     cores = max(1, min(cores, n_sample))
-    work = cpu_sample_points(n_sample, n_voltages)
+    work = cpu_sample_points(n_sample, n_voltages, dv, xtol_path)
     t = time.perf_counter()
     with mp.get_context("spawn").Pool(cores) as pool:
         res = pool.map(_cpu_solve_point, work, chunksize=1)
@@ -83,7 +87,8 @@ def run_cpu(n_sample, n_voltages, cores=None):
     n_ok = sum(1 for r in res if r[2])
     return dict(value=len(work) / wall, unit=UNIT, cores=cores, kind="port",
                 sample=f"{len(work)} of the {7680 if n_voltages == 256 else 30 * n_voltages} sweep points (seed 0), "
-                       f"oracle steady_1d (NumPy assembly + SuperLU), {n_ok} converged, wall {wall:.1f} s",
+                       f"oracle steady_1d (NumPy assembly + SuperLU, same continuation and Jacobian rule as the GPU arm), "
+                       f"{n_ok} converged, wall {wall:.1f} s",
                 newton_iterations=int(sum(r[1] for r in res)))
 
 
@@ -93,11 +98,11 @@ def reference_arm(args):
         return
     vals = []
     for _ in range(args.warmup if args.warmup < 1 else 1):
-        run_cpu(min(args.cpu_sample, os.cpu_count() or 1), args.voltages)
+        run_cpu(min(args.cpu_sample, os.cpu_count() or 1), args.voltages, dv=args.dv, xtol_path=args.xtol_path)
     info = None
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        info = run_cpu(args.cpu_sample, args.voltages)
+        info = run_cpu(args.cpu_sample, args.voltages, dv=args.dv, xtol_path=args.xtol_path)
         vals.append(info["value"])
     T = (time.perf_counter() - t0) / max(1, args.steps)
     v = sum(vals) / len(vals)
@@ -170,7 +175,7 @@ def main():
     # weak scaling: every rank owns one full config-2 sweep (independent sweep points, no collective
     # on the data path; one gather of the per-point summaries at the end)
     pts = sweep.config2_points(args.voltages)
-    sw = sweep.Sweep1D(pts, device=local)
+    sw = sweep.Sweep1D(pts, device=local, dv_max=args.dv, xtol_path=args.xtol_path)
     n_local = sw.n_points
 
     # pinned host staging for the e2e arm
@@ -241,7 +246,10 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = (bytes_total / world) / (ms * 1e-3) / 1e9       # per-GPU GB/s of the kernel
         prof = os.path.join(ROOT, "profiles", "traffic.json")
-        traffic = json.load(open(prof)).get("newton1d_dram_bytes_per_launch") if os.path.exists(prof) else None
+        # DRAM traffic of the kernel: ncu's dram__bytes_read+write over the algorithmic bytes of the captured launch,
+        # applied to this step's algorithmic bytes (the capture is one of the five launches of a step)
+        ratio = json.load(open(prof)).get("newton1d_dram_bytes_over_algorithmic_bytes") if os.path.exists(prof) else None
+        traffic = None if ratio is None else ratio * bytes_total / world
         line = {
             "metric": METRIC, "value": n_total / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -249,7 +257,7 @@ def main():
             "config": {"workload": WORKLOAD if args.voltages == 256 else f"reduced sweep ({args.voltages} V/chain)",
                        "points_per_gpu": n_local, "converged": int(n_conv_total),
                        "newton_iterations_per_step": int(n_its_total),
-                       "continuation": "dV<=0.5 V_T, xtol 1e-12 (final) / 1e-1 (path), consistent Jacobian",
+                       "continuation": f"dV<={args.dv:g} V_T, xtol 1e-12 (final) / {args.xtol_path:g} (path), consistent Jacobian",
                        "cache": "working set (elimination workspace 10.7 GB/GPU) >> 126 MB L2, no flush needed",
                        "parallelism": f"sweep points sharded, {world} GPU(s), no data-path collective"},
             "e2e": {"value": n_total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
@@ -263,7 +271,7 @@ def main():
             "clocks": sampler.summary(),
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = run_cpu(args.cpu_sample, args.voltages)
+            line["cpu_baseline"] = run_cpu(args.cpu_sample, args.voltages, dv=args.dv, xtol_path=args.xtol_path)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

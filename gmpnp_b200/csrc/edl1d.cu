@@ -707,7 +707,7 @@ __device__ __forceinline__ void load_params(const Group& g, const double* __rest
 // mode 1: pseudo-time march  (gmpnp_march_1d): n_stage steps, H_OHP controller, u_n <- u
 // mode 2: steady continuation (gmpnp_steady_continuation_1d): kappa = 0, V from Vpath
 #ifndef GMPNP_NEWTON_MIN_BLOCKS
-#define GMPNP_NEWTON_MIN_BLOCKS 2
+#define GMPNP_NEWTON_MIN_BLOCKS 3
 #endif
 template <bool PIVOT, int NQJ>
 __global__ void __launch_bounds__(THREADS, GMPNP_NEWTON_MIN_BLOCKS)

@@ -22,7 +22,10 @@ from . import forms, quadrature
 class Discretisation:
     """Mesh + fixed sparsity data for one (mesh, ncomp) pair."""
 
-    def __init__(self, x, cells, ncomp):
+    def __init__(self, x, cells, ncomp, jac_rule: int = 0):
+        """``jac_rule`` 0: FFC's rule pair (Jacobian integrated with the degree-4 rule, SURVEY App. B -- the
+        reference's iteration path); 1: the Jacobian uses the residual's rule (exact derivative of the discrete
+        residual: quadratic convergence, same converged solution)."""
         self.x = np.asarray(x, dtype=np.float64)
         if self.x.ndim == 1:
             self.x = self.x[:, None]
@@ -33,6 +36,8 @@ class Discretisation:
         self.ndof = ncomp * self.nv
         self.g, self.vol = forms.geometry(self.x, self.cells)
         self.ruleF, self.ruleJ = quadrature.rules_for_dim(self.dim)
+        if jac_rule == 1:
+            self.ruleJ = self.ruleF
         dofs = (self.cells[:, :, None] * ncomp + np.arange(ncomp)[None, None, :])   # [c, a, i]
         self.cell_dofs = dofs
         nloc = dofs.shape[1] * ncomp
@@ -158,7 +163,7 @@ def march_1d(x, prm, n_steps, H_OHP=None, rtol=1e-4, atol=1e-4, maxit=50):
     return np.array(hist), its, frac
 
 
-def steady_1d(x, prm, V_path, u0=None, xtol=1e-12, maxit=50, xtol_path=0.0):
+def steady_1d(x, prm, V_path, u0=None, xtol=1e-12, maxit=50, xtol_path=0.0, jac_rule=0):
     """Steady equations (kappa = 0) with voltage continuation along ``V_path``.
     Starts from the bulk state unless ``u0`` is given.  Returns (u[nv, ncomp] at the last V,
     list of Newton counts)."""
@@ -166,7 +171,7 @@ def steady_1d(x, prm, V_path, u0=None, xtol=1e-12, maxit=50, xtol_path=0.0):
     nv = len(x)
     cells = np.stack([np.arange(nv - 1), np.arange(1, nv)], axis=1)
     ncomp = prm.ns + 1
-    disc = Discretisation(x, cells, ncomp)
+    disc = Discretisation(x, cells, ncomp, jac_rule=jac_rule)
     ps = prm.with_(kappa=0.0)
     u = np.tile(np.array([1.0] * prm.ns + [0.0]), nv) if u0 is None else np.asarray(u0, float).reshape(-1).copy()
     its = []
