@@ -21,8 +21,8 @@ namespace pore3d {
 
 constexpr int NS = 8;
 constexpr int NC = 9;
-constexpr int NMOM = 60;     // mD[4] | mUD2[8][4] | iUD[8] | Ga[4] | gpa[4] | SU[8]
-constexpr int M_MD = 0, M_UD2 = 4, M_IUD = 36, M_GA = 44, M_GPA = 48, M_SU = 52;
+constexpr int NMOM = 64;     // mD[4] | mUD2[8][4] | iUD[8] | Ga[4] | gpa[4] | SU[8] | eps_r(mean) | pad[3]  (512-B records)
+constexpr int M_MD = 0, M_UD2 = 4, M_IUD = 36, M_GA = 44, M_GPA = 48, M_SU = 52, M_EPS = 60;
 constexpr int NZ = 16;       // z-slabs of the coarse space
 constexpr int NCO = NZ * NC; // coarse dimension (144)
 
@@ -151,6 +151,10 @@ tet_moments_kernel(int n_tet, int n_vert, const int* __restrict__ tets, const do
         for (int a = 0; a < 4; ++a) { mo[M_GA + a] = Ga[a]; mo[M_GPA + a] = gpa[a]; }
 #pragma unroll
         for (int i = 0; i < NS; ++i) mo[M_SU + i] = SU[i];
+        {
+            const double wm = (P[GMPNP_P_EPSC] * SU[NS - 1] + P[GMPNP_P_EPSH] * SU[0]) * 0.25;
+            mo[M_EPS] = P[GMPNP_P_EPSW] * ((55.0 - wm) / 55.0) + 6.0 * (wm / 55.0);
+        }
     }
     if (want_res) {
         // ---- element residual, 5-point rule (one negative weight) ---------------------------
@@ -255,23 +259,38 @@ __global__ void residual_gather_kernel(int n_vert, int n_tet, int n_dir, const i
 // ---------------------------------------------------------------------------------------
 // Kernel C: BSR gather assembly, one warp per (problem, block)
 // ---------------------------------------------------------------------------------------
+// Every entry of a block is linear in a few sums over the tets that share the vertex pair, so a warp first
+// ACCUMULATES those sums over the block's contributions (tet, a, b) -- lane-parallel, one sum per lane -- and
+// only then EXPANDS the 81 entries:
+//   lanes  0..7  Q_i   = sum Ga_a int(u_i phi_b D^2) + (g_a.g_b) int(u_i D)        (steric, row i)
+//   lanes  8..15 Pc_i  = sum (g_a.g_b) (vol/4) SU_i                                 (dF_i/dp before z_i)
+//   lanes 16..23 T_s   = sum cT SU_s,  cT = vol/60 (a == b) or vol/120              (reaction moments; the nodal
+//                        parts (u_a,s + u_b,s) sum cT are added after the loop, va/vb are fixed per block)
+//   all lanes:   dsum = sum kappa M_ab + K_ab + Ga_a mD_b,  zsum = sum gpa_a vol/4,  ppsum = -sum K_ab eps_r,
+//                sMab = sum M_ab,  scT = sum cT
+//   entry(i,j) = cQ Q_i + cD dsum + cDz zsum + sum_r rc_r T_{rs_r} + cP Pc_i + cE zsum + cM sMab + c8 ppsum
 struct EntryConst {          // per-lane constants of entry (i, j) of a 9x9 block
-    int i, j, valid;
-    double nuj, zi, qzc0j, depsj;
-    double rc[3];            // reaction derivative: sum_t rc[t] * int phi_a phi_b u_{rs[t]}
-    int rs[3];               // 0..7 species selector, 8 = constant
+    int i, i7, valid;
+    int rs[3];               // 0..7 species selector, 8 = constant (-> sMab)
+    double cQ, cD, cDz, cP, cE, cM, c8;
+    double rc[3];            // reaction derivative coefficients
 };
 
 __device__ void entry_consts(const double* P, int e, EntryConst& E) {
     E.valid = e < 81;
     const int i = E.valid ? e / 9 : 0, j = E.valid ? e % 9 : 0;
-    E.i = i; E.j = j;
-    E.nuj = (j < NS) ? P[GMPNP_P_NU + j] : 0.0;
-    E.zi = (i < NS) ? P[GMPNP_P_Z + i] : 0.0;
-    E.qzc0j = (j < NS) ? P[GMPNP_P_Q] * P[GMPNP_P_ZC0 + j] : 0.0;
-    E.depsj = 0.0;
-    if (j == 0) E.depsj = (6.0 - P[GMPNP_P_EPSW]) / 55.0 * P[GMPNP_P_EPSH];
-    if (j == NS - 1) E.depsj = (6.0 - P[GMPNP_P_EPSW]) / 55.0 * P[GMPNP_P_EPSC];
+    E.i = i; E.i7 = i & 7;
+    const bool ss = (i < NS && j < NS);
+    E.cQ = ss ? P[GMPNP_P_NU + j] : 0.0;
+    E.cD = (ss && i == j) ? 1.0 : 0.0;
+    E.cDz = (ss && i == j) ? P[GMPNP_P_Z + i] : 0.0;
+    E.cP = (i < NS && j == NS) ? P[GMPNP_P_Z + i] : 0.0;
+    double depsj = 0.0;
+    if (j == 0) depsj = (6.0 - P[GMPNP_P_EPSW]) / 55.0 * P[GMPNP_P_EPSH];
+    if (j == NS - 1) depsj = (6.0 - P[GMPNP_P_EPSW]) / 55.0 * P[GMPNP_P_EPSC];
+    E.cE = (i == NS && j < NS) ? -depsj : 0.0;
+    E.cM = (i == NS && j < NS) ? P[GMPNP_P_Q] * P[GMPNP_P_ZC0 + j] : 0.0;
+    E.c8 = (i == NS && j == NS) ? 1.0 : 0.0;
     for (int t = 0; t < 3; ++t) { E.rc[t] = 0.0; E.rs[t] = 8; }
     if (i >= 5 || j >= 5) return;
     const double kW = P[GMPNP_P_KW], kA = P[GMPNP_P_KA], kB = P[GMPNP_P_KB];
@@ -301,18 +320,20 @@ __device__ void entry_consts(const double* P, int e, EntryConst& E) {
     }
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int ASM_WARPS = 8;
+
+__global__ void __launch_bounds__(ASM_WARPS * 32)
 assemble_bsr_kernel(int n_blocks, int n_vert, int n_tet, const int* __restrict__ blk_ptr,
-                    const int* __restrict__ blk_src, const int* __restrict__ blk_row, const int* __restrict__ col_idx,
-                    const double* __restrict__ geom, const int* __restrict__ dir_flag,
-                    const double* __restrict__ params, const double* __restrict__ u, const double* __restrict__ mom,
-                    double* __restrict__ J) {
+                    const int* __restrict__ blk_src, const double2* __restrict__ blk_geo,
+                    const int* __restrict__ blk_row, const int* __restrict__ col_idx,
+                    const int* __restrict__ dir_flag, const double* __restrict__ params, const double* __restrict__ u,
+                    const double* __restrict__ mom, double* __restrict__ J) {
     __shared__ double P[GMPNP_NPAR];
+    __shared__ double sums[ASM_WARPS][32];   // per warp: Q[0..7] | Pc[8..15] | Tt[16..23] | sMab [24]
     const int prob = blockIdx.y;
     for (int i = threadIdx.x; i < GMPNP_NPAR; i += blockDim.x) P[i] = params[(long)prob * GMPNP_NPAR + i];
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int warps_per_block = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     EntryConst E[3];
 #pragma unroll
     for (int t = 0; t < 3; ++t) entry_consts(P, lane + 32 * t, E[t]);
@@ -320,61 +341,48 @@ assemble_bsr_kernel(int n_blocks, int n_vert, int n_tet, const int* __restrict__
     const double* up = u + (long)prob * n_vert * NC;
     const double* mo = mom + (long)prob * n_tet * NMOM;
     double* Jp = J + (long)prob * n_blocks * 81;
-    for (int blk = blockIdx.x * warps_per_block + (threadIdx.x >> 5); blk < n_blocks; blk += gridDim.x * warps_per_block) {
+    // role of this lane in the accumulation phase: which two moments of a tet record it reads
+    const int role = lane >> 3, li = lane & 7;           // 0: Q_i, 1: Pc_i, 2: T_s, 3: idle
+    const int idx1_base = (role == 0) ? M_UD2 + 4 * li : M_SU + li;
+    const int idx1_bmul = (role == 0) ? 1 : 0;
+    const int idx2 = M_IUD + li;
+    double* sw = sums[w];
+    for (int blk = blockIdx.x * ASM_WARPS + w; blk < n_blocks; blk += gridDim.x * ASM_WARPS) {
         const int va = blk_row[blk], vb = col_idx[blk];
-        double acc[3] = {0.0, 0.0, 0.0};
-        for (int s = blk_ptr[blk]; s < blk_ptr[blk + 1]; ++s) {
+        double acc = 0.0, dsum = 0.0, zsum = 0.0, ppsum = 0.0, sMab = 0.0, scT = 0.0;
+        const int s0 = blk_ptr[blk], s1 = blk_ptr[blk + 1];
+        for (int s = s0; s < s1; ++s) {
             const int src = blk_src[s];
+            const double2 kv = blk_geo[s];               // (g_a.g_b, vol): geometry only, shared by the batch
             const int t = src >> 4, a = (src >> 2) & 3, b = src & 3;
-            const double* ge = geom + (long)t * 13;
-            const double vol = ge[12];
-            const double kab = ge[a * 3] * ge[b * 3] + ge[a * 3 + 1] * ge[b * 3 + 1] + ge[a * 3 + 2] * ge[b * 3 + 2];
-            const double Kab = kab * vol;
-            const double Mab = vol * ((a == b) ? 0.1 : 0.05);
-            const double mb = 0.25 * vol;
+            const double kab = kv.x, vol = kv.y;
             const double* m = mo + (long)t * NMOM;
-            const double Ga = m[M_GA + a], gpa = m[M_GPA + a], mDb = m[M_MD + b];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                if (!E[k].valid) continue;
-                const int i = E[k].i, j = E[k].j;
-                double val;
-                if (i < NS && j < NS) {
-                    val = E[k].nuj * (Ga * m[M_UD2 + i * 4 + b] + kab * m[M_IUD + i]);
-                    if (i == j) val += kappa * Mab + Kab + E[k].zi * gpa * mb + Ga * mDb;
-                    // reaction: int phi_a phi_b u_m = vol/120 (SU_m + U_a + U_b) (a != b), vol/60 (SU_m + 2 U_a) (a == b)
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) {
-                        if (E[k].rc[r] != 0.0) {
-                            const int sel = E[k].rs[r];
-                            double T;
-                            if (sel == 8) T = Mab;
-                            else {
-                                const double ua = up[(long)va * NC + sel], ub = up[(long)vb * NC + sel];
-                                T = (a == b) ? vol * (1.0 / 60.0) * (m[M_SU + sel] + 2.0 * ua)
-                                             : vol * (1.0 / 120.0) * (m[M_SU + sel] + ua + ub);
-                            }
-                            val += E[k].rc[r] * T;
-                        }
-                    }
-                } else if (i < NS) {            // dF_i/dp
-                    val = E[k].zi * kab * (mb * m[M_SU + i]);
-                } else if (j < NS) {            // dF_p/du_j
-                    val = -E[k].depsj * gpa * mb + E[k].qzc0j * Mab;
-                } else {                        // dF_p/dp
-                    const double wm = (P[GMPNP_P_EPSC] * m[M_SU + NS - 1] + P[GMPNP_P_EPSH] * m[M_SU]) * 0.25;
-                    const double epsm = P[GMPNP_P_EPSW] * ((55.0 - wm) / 55.0) + 6.0 * (wm / 55.0);
-                    val = -kab * vol * epsm;
-                }
-                acc[k] += val;
-            }
+            const double Ga = m[M_GA + a], gpa = m[M_GPA + a], mDb = m[M_MD + b], eps = m[M_EPS];
+            const double Kab = kab * vol, mb = 0.25 * vol;
+            const double Mab = vol * ((a == b) ? 0.1 : 0.05);
+            const double cT = vol * ((a == b) ? (1.0 / 60.0) : (1.0 / 120.0));
+            dsum += kappa * Mab + Kab + Ga * mDb;
+            zsum += gpa * mb;
+            ppsum -= Kab * eps;
+            sMab += Mab;
+            scT += cT;
+            const double w1 = (role == 0) ? Ga : ((role == 1) ? kab * mb : cT);
+            const double w2 = (role == 0) ? kab : 0.0;
+            acc += w1 * m[idx1_base + idx1_bmul * b] + w2 * m[idx2];
         }
-        // Dirichlet rows: identity
+        if (role == 2) acc += (up[(long)va * NC + li] + up[(long)vb * NC + li]) * scT;    // nodal part of T_s
+        __syncwarp();                                    // previous block's expansion reads are done
+        sw[lane] = (lane == 24) ? sMab : acc;
+        __syncwarp();
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             if (!E[k].valid) continue;
-            if (dir_flag[(long)va * NC + E[k].i] >= 0) acc[k] = (va == vb && E[k].i == E[k].j) ? 1.0 : 0.0;
-            Jp[(long)blk * 81 + lane + 32 * k] = acc[k];
+            double val = E[k].cQ * sw[E[k].i7] + E[k].cP * sw[8 + E[k].i7];
+            val += E[k].cD * dsum + (E[k].cDz + E[k].cE) * zsum + E[k].cM * sMab + E[k].c8 * ppsum;
+            val += E[k].rc[0] * sw[16 + E[k].rs[0]] + E[k].rc[1] * sw[16 + E[k].rs[1]] + E[k].rc[2] * sw[16 + E[k].rs[2]];
+            // Dirichlet rows: identity
+            if (dir_flag[(long)va * NC + E[k].i] >= 0) val = (va == vb && lane + 32 * k == E[k].i * 10) ? 1.0 : 0.0;
+            Jp[(long)blk * 81 + lane + 32 * k] = val;
         }
     }
 }
@@ -736,6 +744,7 @@ static int dev_upload(gmpnp_handle* h, T** dptr, const std::vector<T>& v) {
 
 struct Host3D {   // device arrays that only the 3D path needs and common.cuh does not name
     int* d_blk_row = nullptr;
+    double2* d_blk_geo = nullptr;   // per gather-list entry (tet, a, b): (grad lambda_a . grad lambda_b, volume)
     int* d_agg = nullptr;
     int* d_agg_ptr = nullptr;
     int* d_agg_nodes = nullptr;
@@ -755,7 +764,7 @@ void pore3d_free_ext(gmpnp_handle* h) {
     auto it = g_ext.find(h);
     if (it == g_ext.end()) return;
     Host3D* e = it->second;
-    void* bufs[] = {e->d_blk_row, e->d_agg, e->d_agg_ptr, e->d_agg_nodes, e->d_Aci, e->d_yc, e->d_V, e->d_w, e->d_z,
+    void* bufs[] = {e->d_blk_row, e->d_blk_geo, e->d_agg, e->d_agg_ptr, e->d_agg_nodes, e->d_Aci, e->d_yc, e->d_V, e->d_w, e->d_z,
                     e->d_dx, e->d_d1, e->d_d2, e->d_nrm, e->d_H, e->d_cs, e->d_sn, e->d_g, e->d_tol, e->d_coef,
                     e->d_beta, e->d_dxmax, e->d_umax, e->d_jdone, e->d_active};
     for (void* b : bufs) if (b) cudaFree(b);
@@ -852,13 +861,19 @@ int gmpnp_create_3d(gmpnp_handle** out, int device, const double* h_xyz, int n_v
     std::partial_sum(blk_cnt.begin(), blk_cnt.end(), blk_cnt.begin());
     std::partial_sum(node_cnt.begin(), node_cnt.end(), node_cnt.begin());
     std::vector<int> blk_src((size_t)16 * n_tet), node_src((size_t)4 * n_tet);
+    std::vector<double2> blk_geo((size_t)16 * n_tet);
     {
         std::vector<int> bpos(blk_cnt.begin(), blk_cnt.end() - 1), npos(node_cnt.begin(), node_cnt.end() - 1);
         for (int t = 0; t < n_tet; ++t)            // ascending tet order => deterministic summation order
             for (int a = 0; a < 4; ++a) {
                 node_src[npos[h_tets[4 * t + a]]++] = t * 4 + a;
-                for (int b = 0; b < 4; ++b)
-                    blk_src[bpos[find_blk(h_tets[4 * t + a], h_tets[4 * t + b])]++] = t * 16 + a * 4 + b;
+                for (int b = 0; b < 4; ++b) {
+                    const int pos = bpos[find_blk(h_tets[4 * t + a], h_tets[4 * t + b])]++;
+                    blk_src[pos] = t * 16 + a * 4 + b;
+                    const double* ge = &geom[(size_t)t * 13];
+                    blk_geo[pos] = make_double2(ge[a * 3] * ge[b * 3] + ge[a * 3 + 1] * ge[b * 3 + 1] +
+                                                ge[a * 3 + 2] * ge[b * 3 + 2], ge[12]);
+                }
             }
     }
     // ---- Dirichlet flags, z-slab aggregates -------------------------------------------------
@@ -894,6 +909,7 @@ int gmpnp_create_3d(gmpnp_handle** out, int device, const double* h_xyz, int n_v
     if ((rc = dev_upload(h, &h->d_dir_dof, dir_dof))) return rc;
     if ((rc = dev_upload(h, &h->d_dir_flag, dir_flag))) return rc;
     if ((rc = dev_upload(h, &e->d_blk_row, blk_row))) return rc;
+    if ((rc = dev_upload(h, &e->d_blk_geo, blk_geo))) return rc;
     if ((rc = dev_upload(h, &e->d_agg, agg))) return rc;
     if ((rc = dev_upload(h, &e->d_agg_ptr, agg_ptr))) return rc;
     if ((rc = dev_upload(h, &e->d_agg_nodes, agg_nodes))) return rc;
@@ -950,12 +966,11 @@ static int launch_assemble(gmpnp_handle* h, const double* d_u, const double* d_u
         h->launches++;
     }
     if (d_J) {
-        const int warps = 8;
-        int gx = std::min((h->n_blocks + warps - 1) / warps, 148 * 8);
+        int gx = std::min((h->n_blocks + ASM_WARPS - 1) / ASM_WARPS, 148 * 8);
         dim3 gC(gx, B);
-        assemble_bsr_kernel<<<gC, warps * 32, 0, st>>>(h->n_blocks, V, T, h->d_blk_ptr, h->d_blk_src, ext(h)->d_blk_row,
-                                                       h->d_col_idx, h->d_geom, h->d_dir_flag, h->d_params, d_u,
-                                                       h->d_mom, d_J);
+        assemble_bsr_kernel<<<gC, ASM_WARPS * 32, 0, st>>>(h->n_blocks, V, T, h->d_blk_ptr, h->d_blk_src,
+                                                           ext(h)->d_blk_geo, ext(h)->d_blk_row, h->d_col_idx,
+                                                           h->d_dir_flag, h->d_params, d_u, h->d_mom, d_J);
         h->launches++;
     }
     GMPNP_CUDA_TRY(h, cudaGetLastError());
