@@ -351,24 +351,33 @@ assemble_bsr_kernel(int n_blocks, int n_vert, int n_tet, const int* __restrict__
         const int va = blk_row[blk], vb = col_idx[blk];
         double acc = 0.0, dsum = 0.0, zsum = 0.0, ppsum = 0.0, sMab = 0.0, scT = 0.0;
         const int s0 = blk_ptr[blk], s1 = blk_ptr[blk + 1];
-        for (int s = s0; s < s1; ++s) {
-            const int src = blk_src[s];
-            const double2 kv = blk_geo[s];               // (g_a.g_b, vol): geometry only, shared by the batch
-            const int t = src >> 4, a = (src >> 2) & 3, b = src & 3;
-            const double kab = kv.x, vol = kv.y;
-            const double* m = mo + (long)t * NMOM;
-            const double Ga = m[M_GA + a], gpa = m[M_GPA + a], mDb = m[M_MD + b], eps = m[M_EPS];
-            const double Kab = kab * vol, mb = 0.25 * vol;
-            const double Mab = vol * ((a == b) ? 0.1 : 0.05);
-            const double cT = vol * ((a == b) ? (1.0 / 60.0) : (1.0 / 120.0));
-            dsum += kappa * Mab + Kab + Ga * mDb;
-            zsum += gpa * mb;
-            ppsum -= Kab * eps;
-            sMab += Mab;
-            scT += cT;
-            const double w1 = (role == 0) ? Ga : ((role == 1) ? kab * mb : cT);
-            const double w2 = (role == 0) ? kab : 0.0;
-            acc += w1 * m[idx1_base + idx1_bmul * b] + w2 * m[idx2];
+        // gather list of the block: coalesced 32 entries at a time, then broadcast entry by entry, so that the
+        // moment loads of several contributions are in flight together
+        for (int sb = s0; sb < s1; sb += 32) {
+            const int cnt = min(32, s1 - sb);
+            int my_src = 0;
+            double2 my_kv = make_double2(0.0, 0.0);
+            if (lane < cnt) { my_src = blk_src[sb + lane]; my_kv = blk_geo[sb + lane]; }
+#pragma unroll 4
+            for (int q = 0; q < cnt; ++q) {
+                const int src = __shfl_sync(0xffffffffu, my_src, q);
+                const double kab = __shfl_sync(0xffffffffu, my_kv.x, q), vol = __shfl_sync(0xffffffffu, my_kv.y, q);
+                const int t = src >> 4, a = (src >> 2) & 3, b = src & 3;
+                const double* m = mo + (long)t * NMOM;
+                const double Ga = m[M_GA + a], gpa = m[M_GPA + a], mDb = m[M_MD + b], eps = m[M_EPS];
+                const double m1 = m[idx1_base + idx1_bmul * b], m2 = m[idx2];
+                const double Kab = kab * vol, mb = 0.25 * vol;
+                const double Mab = vol * ((a == b) ? 0.1 : 0.05);
+                const double cT = vol * ((a == b) ? (1.0 / 60.0) : (1.0 / 120.0));
+                dsum += kappa * Mab + Kab + Ga * mDb;
+                zsum += gpa * mb;
+                ppsum -= Kab * eps;
+                sMab += Mab;
+                scT += cT;
+                const double w1 = (role == 0) ? Ga : ((role == 1) ? kab * mb : cT);
+                const double w2 = (role == 0) ? kab : 0.0;
+                acc += w1 * m1 + w2 * m2;
+            }
         }
         if (role == 2) acc += (up[(long)va * NC + li] + up[(long)vb * NC + li]) * scT;    // nodal part of T_s
         __syncwarp();                                    // previous block's expansion reads are done
@@ -728,6 +737,63 @@ median_kernel(int n_vert, int npow2, int comp, const double* __restrict__ u, dou
         med[prob] = (n_vert & 1) ? sv[n_vert / 2] : 0.5 * (sv[n_vert / 2 - 1] + sv[n_vert / 2]);
 }
 
+// ---------------------------------------------------------------------------------------
+// Vector kernels of the mesh-partitioned mode (one problem spans several GPUs: SURVEY 8e (2)).
+// Reductions are two-stage (grid-wide partial sums in a fixed chunk order, then one small CTA per
+// output), so a single large vector uses the whole GPU and the result is deterministic.
+// ---------------------------------------------------------------------------------------
+constexpr int VEC_CHUNK = 8192;        // entries per CTA of the first reduction stage
+
+// partial[k][chunk] = sum over the chunk of V_k[i] * w[i]      grid = (nchunks, nvec)
+__global__ void __launch_bounds__(256)
+vec_dot_partial_kernel(long n, long vstride, const double* __restrict__ V, const double* __restrict__ w,
+                       double* __restrict__ partial, int nchunks) {
+    __shared__ double sh[8];
+    const int chunk = blockIdx.x, k = blockIdx.y;
+    const double* vk = V + (long)k * vstride;
+    const long i0 = (long)chunk * VEC_CHUNK, i1 = min(n, i0 + VEC_CHUNK);
+    double s = 0.0;
+    for (long i = i0 + threadIdx.x; i < i1; i += blockDim.x) s += vk[i] * w[i];
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) partial[(long)k * nchunks + chunk] = s;
+}
+
+// out[k] = sum_chunk partial[k][chunk]                            grid = nvec
+__global__ void __launch_bounds__(256)
+vec_dot_final_kernel(const double* __restrict__ partial, int nchunks, double* __restrict__ out) {
+    __shared__ double sh[8];
+    const int k = blockIdx.x;
+    double s = 0.0;
+    for (int c = threadIdx.x; c < nchunks; c += blockDim.x) s += partial[(long)k * nchunks + c];
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) out[k] = s;
+}
+
+// out[i] = beta * y[i] + sum_k coef[k] V_k[i]   (y may be null; out may alias y)
+__global__ void __launch_bounds__(256)
+vec_lincomb_kernel(long n, long vstride, int nvec, const double* __restrict__ V, const double* __restrict__ coef,
+                   double beta, const double* y, double* out) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = (y != nullptr) ? beta * y[i] : 0.0;
+    for (int k = 0; k < nvec; ++k) s += coef[k] * V[(long)k * vstride + i];
+    out[i] = s;
+}
+
+// z = D^{-1} r on the first n_rows block rows (Dirichlet rows are identity rows of J, so their D^{-1} is I)
+__global__ void __launch_bounds__(256)
+bjacobi_apply_kernel(int n_rows, const double* __restrict__ Dinv, const double* __restrict__ r, double* __restrict__ z) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)n_rows * NC) return;
+    const int v = (int)(idx / NC), i = (int)(idx % NC);
+    const double* d = Dinv + (long)v * 81 + i * 9;
+    const double* rv = r + (long)v * NC;
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) s += d[j] * rv[j];
+    z[idx] = s;
+}
+
 }  // namespace pore3d
 
 // =======================================================================================
@@ -750,6 +816,8 @@ struct Host3D {   // device arrays that only the 3D path needs and common.cuh do
     int* d_agg_nodes = nullptr;
     double* d_Aci = nullptr;
     double* d_yc = nullptr;
+    double* d_partial = nullptr;    // first-stage partial sums of the partitioned-mode reductions
+    size_t partial_doubles = 0;
     int restart_alloc = 0;
     double *d_V = nullptr, *d_w = nullptr, *d_z = nullptr, *d_dx = nullptr, *d_d1 = nullptr, *d_d2 = nullptr;
     double *d_nrm = nullptr, *d_H = nullptr, *d_cs = nullptr, *d_sn = nullptr, *d_g = nullptr, *d_tol = nullptr;
@@ -764,7 +832,7 @@ void pore3d_free_ext(gmpnp_handle* h) {
     auto it = g_ext.find(h);
     if (it == g_ext.end()) return;
     Host3D* e = it->second;
-    void* bufs[] = {e->d_blk_row, e->d_blk_geo, e->d_agg, e->d_agg_ptr, e->d_agg_nodes, e->d_Aci, e->d_yc, e->d_V, e->d_w, e->d_z,
+    void* bufs[] = {e->d_partial, e->d_blk_row, e->d_blk_geo, e->d_agg, e->d_agg_ptr, e->d_agg_nodes, e->d_Aci, e->d_yc, e->d_V, e->d_w, e->d_z,
                     e->d_dx, e->d_d1, e->d_d2, e->d_nrm, e->d_H, e->d_cs, e->d_sn, e->d_g, e->d_tol, e->d_coef,
                     e->d_beta, e->d_dxmax, e->d_umax, e->d_jdone, e->d_active};
     for (void* b : bufs) if (b) cudaFree(b);
@@ -1204,6 +1272,60 @@ int gmpnp_newton_3d(gmpnp_handle* h, double* d_u, const double* d_un, const gmpn
     if (d_r0) GMPNP_CUDA_TRY(h, cudaMemcpyAsync(d_r0, r0.data(), sizeof(double) * B, cudaMemcpyHostToDevice, st));
     if (d_r) GMPNP_CUDA_TRY(h, cudaMemcpyAsync(d_r, r.data(), sizeof(double) * B, cudaMemcpyHostToDevice, st));
     GMPNP_CUDA_TRY(h, cudaStreamSynchronize(st));
+    return GMPNP_OK;
+}
+
+// ---- mesh-partitioned mode: building blocks of the distributed GMRES (see gmpnp_b200/dist3d.py) -------------
+int gmpnp_vec_multi_dot(gmpnp_handle* h, const double* d_V, long long vstride, int nvec, const double* d_w,
+                        long long n, double* d_out, void* stream) {
+    if (!h || h->dim != 3 || !d_V || !d_w || !d_out || nvec < 1 || n < 1) return GMPNP_ERR_ARG;
+    GMPNP_CUDA_TRY(h, cudaSetDevice(h->device));
+    Host3D* e = ext(h);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nchunks = (int)((n + VEC_CHUNK - 1) / VEC_CHUNK);
+    const size_t need = (size_t)nchunks * nvec;
+    if (e->partial_doubles < need) {
+        if (e->d_partial) GMPNP_CUDA_TRY(h, cudaFree(e->d_partial));
+        e->partial_doubles = std::max(need, (size_t)nchunks * 128);
+        GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_partial, sizeof(double) * e->partial_doubles));
+    }
+    dim3 g(nchunks, nvec);
+    vec_dot_partial_kernel<<<g, 256, 0, st>>>(n, vstride, d_V, d_w, e->d_partial, nchunks);
+    vec_dot_final_kernel<<<nvec, 256, 0, st>>>(e->d_partial, nchunks, d_out);
+    h->launches += 2;
+    GMPNP_CUDA_TRY(h, cudaGetLastError());
+    return GMPNP_OK;
+}
+
+int gmpnp_vec_lincomb(gmpnp_handle* h, const double* d_V, long long vstride, int nvec, const double* d_coef,
+                      double beta, const double* d_y, double* d_out, long long n, void* stream) {
+    if (!h || h->dim != 3 || !d_V || !d_coef || !d_out || nvec < 1 || n < 1) return GMPNP_ERR_ARG;
+    GMPNP_CUDA_TRY(h, cudaSetDevice(h->device));
+    vec_lincomb_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, vstride, nvec, d_V, d_coef, beta,
+                                                                                   d_y, d_out);
+    h->launches++;
+    GMPNP_CUDA_TRY(h, cudaGetLastError());
+    return GMPNP_OK;
+}
+
+int gmpnp_bjacobi_setup_3d(gmpnp_handle* h, const double* d_J, void* stream) {
+    if (!h || h->dim != 3) return GMPNP_ERR_ARG;
+    GMPNP_CUDA_TRY(h, cudaSetDevice(h->device));
+    dim3 gj((h->n_nodes + 63) / 64, h->batch);
+    bjacobi_invert_kernel<<<gj, 64, 0, (cudaStream_t)stream>>>(h->n_nodes, h->n_blocks, h->d_diag_idx, d_J ? d_J : h->d_J,
+                                                               h->d_Dinv);
+    h->launches++;
+    GMPNP_CUDA_TRY(h, cudaGetLastError());
+    return GMPNP_OK;
+}
+
+int gmpnp_bjacobi_apply_3d(gmpnp_handle* h, const double* d_r, double* d_z, int n_rows, void* stream) {
+    if (!h || h->dim != 3 || !d_r || !d_z || h->batch != 1 || n_rows < 1 || n_rows > h->n_nodes) return GMPNP_ERR_ARG;
+    GMPNP_CUDA_TRY(h, cudaSetDevice(h->device));
+    const long total = (long)n_rows * NC;
+    bjacobi_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n_rows, h->d_Dinv, d_r, d_z);
+    h->launches++;
+    GMPNP_CUDA_TRY(h, cudaGetLastError());
     return GMPNP_OK;
 }
 

@@ -174,6 +174,23 @@ int gmpnp_newton_3d(gmpnp_handle* h, double* d_u, const double* d_un,
                     const gmpnp_newton_opts* opts, int* d_iters, double* d_r0, double* d_r,
                     int* d_lin_iters, int* d_status, void* stream);
 
+/* ---- mesh-partitioned mode (one problem spans the GPUs of a box; SURVEY 8e (2), BASELINE config 5) -----------
+ * The reference has no distributed path; these are the per-rank building blocks of the
+ * distributed GMRES that replaces the MUMPS solve of 3D/MPNP_CO2ER_pore.py:792 on a partitioned mesh.  A rank's
+ * handle is created on its LOCAL mesh (owned vertices first, ghost vertices after); the halo exchange and the
+ * all-reduces of the dot products are done by the host with torch.distributed between these calls.
+ *   gmpnp_vec_multi_dot:  d_out[k] = sum_{i<n} V_k[i] w[i], V_k = d_V + k*vstride  (two-stage, deterministic)
+ *   gmpnp_vec_lincomb:    d_out[i] = beta*d_y[i] + sum_k d_coef[k] V_k[i]  (d_y may be NULL, d_out may alias d_y;
+ *                         d_coef is a device array)
+ *   gmpnp_bjacobi_setup_3d: invert the diagonal 9x9 blocks of d_J (NULL: the handle's last Jacobian)
+ *   gmpnp_bjacobi_apply_3d: d_z = D^-1 d_r on the first n_rows block rows (batch 1)                         */
+int gmpnp_vec_multi_dot(gmpnp_handle* h, const double* d_V, long long vstride, int nvec, const double* d_w,
+                        long long n, double* d_out, void* stream);
+int gmpnp_vec_lincomb(gmpnp_handle* h, const double* d_V, long long vstride, int nvec, const double* d_coef,
+                      double beta, const double* d_y, double* d_out, long long n, void* stream);
+int gmpnp_bjacobi_setup_3d(gmpnp_handle* h, const double* d_J, void* stream);
+int gmpnp_bjacobi_apply_3d(gmpnp_handle* h, const double* d_r, double* d_z, int n_rows, void* stream);
+
 /* Median over the vertices of component `comp` for every problem (np.median, 3D:817-820):
  * d_med[batch].                                                                            */
 int gmpnp_median_3d(gmpnp_handle* h, const double* d_u, int comp, double* d_med, void* stream);
