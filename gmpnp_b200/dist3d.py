@@ -238,9 +238,11 @@ class PartitionedPore:
                 d2n = self.dot_owned(Vb, j + 1, ws, extra_self=True)
                 d2 = d2n[: j + 1]
                 self.lincomb(Vb, j + 1, -d2, ws, beta=1.0, ys=ws)
-                hv = (d1 + d2).cpu().numpy()
-                nrm2 = float(d2n[j + 1]) - float((d2 * d2).sum())
-                if not nrm2 > 1e-28 * max(float(d2n[j + 1]), 1e-300):       # cancellation: recompute directly
+                # one device->host read per iteration: h = d1 + d2, ||w'||^2 and sum d2^2 (Pythagoras for ||w''||)
+                host = torch.cat([d1 + d2, d2n[j + 1:j + 2], (d2 * d2).sum().view(1)]).cpu().numpy()
+                hv, ww, s2 = host[: j + 1], float(host[j + 1]), float(host[j + 2])
+                nrm2 = ww - s2
+                if not nrm2 > 1e-28 * max(ww, 1e-300):                       # cancellation: recompute directly
                     nrm2 = float(self.dot_owned([t.view(1, -1) for t in ws], 1, ws)[0])
                 hn = math.sqrt(max(nrm2, 0.0))
                 H[: j + 1, j] = hv
