@@ -61,6 +61,7 @@ SIGNATURES = {
     "gmpnp_spmv_3d": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "gmpnp_newton_3d": (_i, [_vp, _vp, _vp, _po, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gmpnp_median_3d": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "gmpnp_spmv_rows_3d": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "gmpnp_vec_multi_dot": (_i, [_vp, _vp, C.c_longlong, _i, _vp, C.c_longlong, _vp, _vp]),
     "gmpnp_vec_lincomb": (_i, [_vp, _vp, C.c_longlong, _i, _vp, _d, _vp, _vp, C.c_longlong, _vp]),
     "gmpnp_bjacobi_setup_3d": (_i, [_vp, _vp, _vp]),

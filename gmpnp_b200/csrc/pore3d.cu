@@ -401,12 +401,12 @@ assemble_bsr_kernel(int n_blocks, int n_vert, int n_tet, const int* __restrict__
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 bsr_spmv_kernel(int n_vert, int n_blocks, const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
-                const double* __restrict__ J, const double* __restrict__ x, double* __restrict__ y) {
+                const double* __restrict__ J, const double* __restrict__ x, double* __restrict__ y, int row0, int row1) {
     __shared__ double part[8][96];
     const int prob = blockIdx.y;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int row = blockIdx.x * 8 + w;
-    if (row >= n_vert) return;
+    const int row = row0 + blockIdx.x * 8 + w;
+    if (row >= row1) return;
     const double* Jp = J + (long)prob * n_blocks * 81;
     const double* xp = x + (long)prob * n_vert * NC;
     const int j0 = lane % 9, j1 = (lane + 32) % 9, j2 = (lane + 64) % 9;
@@ -1045,9 +1045,12 @@ static int launch_assemble(gmpnp_handle* h, const double* d_u, const double* d_u
     return GMPNP_OK;
 }
 
-static int launch_spmv(gmpnp_handle* h, const double* d_J, const double* d_x, double* d_y, cudaStream_t st) {
-    dim3 g((h->n_nodes + 7) / 8, h->batch);
-    bsr_spmv_kernel<<<g, 256, 0, st>>>(h->n_nodes, h->n_blocks, h->d_row_ptr, h->d_col_idx, d_J, d_x, d_y);
+static int launch_spmv(gmpnp_handle* h, const double* d_J, const double* d_x, double* d_y, cudaStream_t st,
+                       int row0 = 0, int row1 = -1) {
+    if (row1 < 0) row1 = h->n_nodes;
+    if (row1 <= row0) return GMPNP_OK;
+    dim3 g((row1 - row0 + 7) / 8, h->batch);
+    bsr_spmv_kernel<<<g, 256, 0, st>>>(h->n_nodes, h->n_blocks, h->d_row_ptr, h->d_col_idx, d_J, d_x, d_y, row0, row1);
     h->launches++;
     return GMPNP_OK;
 }
@@ -1193,6 +1196,15 @@ int gmpnp_spmv_3d(gmpnp_handle* h, const double* d_J, const double* d_x, double*
     if (!h || h->dim != 3 || !d_x || !d_y) return GMPNP_ERR_ARG;
     GMPNP_CUDA_TRY(h, cudaSetDevice(h->device));
     launch_spmv(h, d_J ? d_J : h->d_J, d_x, d_y, (cudaStream_t)stream);
+    GMPNP_CUDA_TRY(h, cudaGetLastError());
+    return GMPNP_OK;
+}
+
+int gmpnp_spmv_rows_3d(gmpnp_handle* h, const double* d_J, const double* d_x, double* d_y, int row0, int row1,
+                       void* stream) {
+    if (!h || h->dim != 3 || !d_x || !d_y || row0 < 0 || row1 > h->n_nodes || row0 > row1) return GMPNP_ERR_ARG;
+    GMPNP_CUDA_TRY(h, cudaSetDevice(h->device));
+    launch_spmv(h, d_J ? d_J : h->d_J, d_x, d_y, (cudaStream_t)stream, row0, row1);
     GMPNP_CUDA_TRY(h, cudaGetLastError());
     return GMPNP_OK;
 }

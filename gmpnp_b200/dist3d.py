@@ -128,6 +128,7 @@ class PartitionedPore:
         self.n_own = [p.n_own for p in self.parts]
         self.J = [None] * len(self.parts)
         self.stats = dict(spmv=0, halo=0, allreduce=0, gmres_iters=0)
+        self.overlap, self.overlap_min_rows = None, 150_000
         self.set_dirichlet(float(prm.extras["eq_scaled"][0]))
 
     # -- helpers ----------------------------------------------------------------------------
@@ -185,14 +186,33 @@ class PartitionedPore:
         nrm2 = self.dot_owned([F.view(1, -1) for F in Fs], 1, [F.view(-1) for F in Fs])
         return Fs, math.sqrt(float(nrm2[0]))
 
-    def spmv(self, xs, ys=None):
-        """y = J x on the owned rows (ghost rows of y are meaningless); x's ghosts are refreshed first."""
-        self.comm.halo([x[0] for x in xs])
+    def spmv(self, xs, overlap=None):
+        """y = J x on the owned rows (ghost rows of y are not computed).  With ``overlap`` the interior rows (no ghost
+        column) are multiplied on a side stream while the halo exchange of x is in flight and the boundary rows
+        follow it; for small parts the exchange is launch-latency bound and the extra stream hand-offs cost more
+        than they hide, so the default only overlaps from ``overlap_min_rows`` owned rows per part upwards."""
+        if overlap is None:
+            overlap = self.overlap if self.overlap is not None else min(self.n_own) >= self.overlap_min_rows
         self.stats["halo"] += 1
         self.stats["spmv"] += 1
-        out = []
-        for k, (s, x) in enumerate(zip(self.solvers, xs)):
-            out.append(s.spmv(self.J[k], x))
+        main = torch.cuda.current_stream(self.device)
+        out = [torch.empty_like(x) for x in xs]
+        if overlap:
+            if not hasattr(self, "_side"):
+                self._side = torch.cuda.Stream(self.device)
+            side = self._side
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                for s, p, J, x, y in zip(self.solvers, self.parts, self.J, xs, out):
+                    y.record_stream(side)
+                    check(self.lib.gmpnp_spmv_rows_3d(s._h, ptr(J), ptr(x), ptr(y), 0, p.n_int,
+                                                      C.c_void_p(side.cuda_stream)), s._h)
+        self.comm.halo([x[0] for x in xs])
+        for s, p, J, x, y in zip(self.solvers, self.parts, self.J, xs, out):
+            check(self.lib.gmpnp_spmv_rows_3d(s._h, ptr(J), ptr(x), ptr(y), p.n_int if overlap else 0, p.n_own,
+                                              self._stream()), s._h)
+        if overlap:
+            main.wait_stream(side)
         return out
 
     def precond(self, rs, zs):

@@ -8,8 +8,10 @@ smallest interfaces is used):
 * every vertex has exactly one OWNER rank (contiguous ranges of the z-sorted vertex list, so all
   ranks own the same number of block rows +- 1);
 * a rank's LOCAL mesh = all tets that touch an owned vertex; its local vertex numbering puts the
-  owned vertices first (ascending global id) and the GHOST vertices (vertices of local tets owned
-  by other ranks) after them, so "the first n_own rows" is the owned part of every local vector;
+  owned vertices first -- INTERIOR ones (no ghost neighbour) before BOUNDARY ones, ascending global
+  id inside each group -- and the GHOST vertices (vertices of local tets owned by other ranks) after
+  them, so "the first n_own rows" is the owned part of every local vector and "the first n_int rows"
+  can be multiplied while the halo exchange is still in flight;
 * the rows of owned vertices are therefore assembled completely from local tets (no exchange of
   matrix entries); ghost rows are incomplete and never used;
 * per neighbour, ``send`` lists the owned vertices that are ghosts over there and ``recv`` the local
@@ -33,6 +35,7 @@ class MeshPart:
     world: int
     glob: np.ndarray                 # [n_local] global vertex id of every local vertex (owned first)
     n_own: int
+    n_int: int                       # the first n_int owned vertices have no ghost neighbour (interior rows)
     x: np.ndarray                    # [n_local, 3]
     cells: np.ndarray                # [t_local, 4] in local numbering
     cell_glob: np.ndarray            # [t_local] global tet ids
@@ -85,12 +88,20 @@ def partition_z(mesh: meshio.Mesh, world: int, ranks=None) -> list:
         lv = local_verts[r]
         own = np.nonzero(owner == r)[0]                          # ascending global id (incl. isolated vertices)
         ghost = lv[owner[lv] != r]
+        # boundary-owned vertices: share a local tet with a ghost vertex
+        tc = cells[local_cells[r]]
+        has_ghost = (cell_owner[local_cells[r]] != r).any(axis=1)
+        bverts = np.unique(tc[has_ghost])
+        is_b = np.zeros(x.shape[0], dtype=bool)
+        is_b[bverts] = True
+        own = np.concatenate([own[~is_b[own]], own[is_b[own]]])
+        n_int = int((~is_b[own]).sum())
         glob = np.concatenate([own, ghost]).astype(np.int64)
         g2l = -np.ones(x.shape[0], dtype=np.int64)
         g2l[glob] = np.arange(len(glob))
         lc = g2l[cells[local_cells[r]]]
         assert (lc >= 0).all()
-        part = MeshPart(rank=r, world=world, glob=glob, n_own=int(len(own)), x=x[glob].copy(),
+        part = MeshPart(rank=r, world=world, glob=glob, n_own=int(len(own)), n_int=n_int, x=x[glob].copy(),
                         cells=lc.astype(np.int32), cell_glob=local_cells[r].astype(np.int64))
         # receive: my ghosts grouped by owner (ascending global id inside a group)
         for s in np.unique(owner[ghost]):

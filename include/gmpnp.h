@@ -184,6 +184,10 @@ int gmpnp_newton_3d(gmpnp_handle* h, double* d_u, const double* d_un,
  *                         d_coef is a device array)
  *   gmpnp_bjacobi_setup_3d: invert the diagonal 9x9 blocks of d_J (NULL: the handle's last Jacobian)
  *   gmpnp_bjacobi_apply_3d: d_z = D^-1 d_r on the first n_rows block rows (batch 1)                         */
+/* y = J x restricted to the block rows [row0, row1): the partitioned mode multiplies the interior rows (no ghost
+ * column) while the halo exchange is in flight and the boundary rows after it.                                */
+int gmpnp_spmv_rows_3d(gmpnp_handle* h, const double* d_J, const double* d_x, double* d_y, int row0, int row1,
+                       void* stream);
 int gmpnp_vec_multi_dot(gmpnp_handle* h, const double* d_V, long long vstride, int nvec, const double* d_w,
                         long long n, double* d_out, void* stream);
 int gmpnp_vec_lincomb(gmpnp_handle* h, const double* d_V, long long vstride, int nvec, const double* d_coef,

@@ -35,6 +35,11 @@ def test_partition_invariants(world):
             assert np.array_equal(p.glob[ridx], q.glob[q.send[p.rank]])
             assert (ridx >= p.n_own).all() and (q.send[p.rank] < q.n_own).all()
         assert sum(len(v) for v in p.recv.values()) == p.n_ghost
+        # interior rows (the first n_int) have no ghost column; every other owned row has one
+        with_ghost = np.unique(p.cells[(p.cells >= p.n_own).any(axis=1)])
+        bnd = with_ghost[with_ghost < p.n_own]
+        assert 0 <= p.n_int <= p.n_own
+        assert (bnd >= p.n_int).all() and len(bnd) == p.n_own - p.n_int
     # the slabs are ordered along z
     zc = [m.x[p.glob[: p.n_own], 2].mean() for p in parts]
     assert zc == sorted(zc)

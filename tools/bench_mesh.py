@@ -28,6 +28,7 @@ ap.add_argument("--R", type=float, default=50e-9)
 ap.add_argument("--refine", type=int, default=2)
 ap.add_argument("--gmres-iters", type=int, default=30)
 ap.add_argument("--reps", type=int, default=10)
+ap.add_argument("--overlap", type=int, default=-1, help="1/0: force the interior-rows/halo overlap on/off (-1: auto)")
 ap.add_argument("--emulate", type=int, default=0, help="emulate this many ranks inside one process (LocalComm)")
 a = ap.parse_args()
 
@@ -56,6 +57,8 @@ else:
     comm = TorchComm(parts[0])
     nparts = world
 pp = PartitionedPore(mesh, a.L, a.R, prm, parts, comm, device=local, dirichlet=dirichlet)
+if a.overlap >= 0:
+    pp.overlap = bool(a.overlap)
 setup_s = time.time() - t0
 
 
@@ -130,7 +133,7 @@ if rank == 0:
             "n_gpus": world, "parts": nparts, "emulated_in_one_process": bool(a.emulate > 1),
             "vertices": nv, "tets": nt, "dofs": 9 * nv, "bsr_blocks_local_total": int(nb_tot),
             "jacobian_GB": 8 * 81 * nb_tot / 1e9, "ghost_vertices_total": int(ghost_tot),
-            "halo_bytes_per_spmv_total": int(halo_tot), "setup_s": setup_s,
+            "halo_bytes_per_spmv_total": int(halo_tot), "overlap": a.overlap, "setup_s": setup_s,
             "assemble_ms": ms_asm, "assemble_GBs_aggregate": b_asm / ms_asm / 1e6,
             "spmv_ms": ms_spmv, "spmv_local_kernel_ms": ms_spmv_local, "spmv_GBs_aggregate": b_spmv / ms_spmv / 1e6,
             "spmv_frac_of_hbm_peak_per_gpu": b_spmv / ms_spmv / 1e6 / (peak * gpus),
