@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--voltages", type=int, default=256, help="voltage points per chain (256 = config 2)")
     ap.add_argument("--cpu-sample", type=int, default=16, help="sweep points timed on the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pore3d-batch", type=int, default=32, help="3D pore problems per GPU in the 3D part (0: skip)")
     ap.add_argument("--dv", type=float, default=0.75, help="largest voltage increment of the continuation [V_T]")
     ap.add_argument("--xtol-path", type=float, default=1.0,
                     help="increment tolerance of the intermediate continuation stages (1.0 = one Newton corrector "
@@ -114,6 +115,84 @@ def reference_arm(args):
             "cpu_baseline": dict(info, value=v),
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# 3D pore part of the metric ("steady solves/sec (1D & 3D pore); assembly + SpMV HBM GB/s")
+# --------------------------------------------------------------------------------------------
+def bench_pore3d(local, world, dev, batch, peak):
+    """BASELINE config 3 (L_50_R_5, parameters_pore.yaml, 1.0 M, K+, as-executed BCs) as a batch of `batch` wall
+    voltages in [-0.5, -1.25] V_T: (i) steady solves = the reference's pseudo-time march (damped Newton, relaxation
+    0.9, GMRES + block-Jacobi/coarse) run to increments <= 1e-8, (ii) the assembly and BSR SpMV kernels alone."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from gmpnp_b200 import meshio, params, solver3d
+    mesh = meshio.load_mesh("L_50_R_5")
+    Vs = np.linspace(-0.5, -1.25, batch)
+    plist = [params.params_3d(L=50e-9, R=5e-9, voltage_multiplier=float(V)) for V in Vs]
+    pp = solver3d.PoreProblem(mesh, 50e-9, 5e-9, plist, device=local)
+    s = pp.solver
+    Vn, T, nb = s.n, s.n_tet, s.n_blocks
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        sync()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    u = solver3d.bulk_state(batch, Vn, dev)
+    u += 0.01 * torch.rand_like(u)
+    un = solver3d.bulk_state(batch, Vn, dev)
+    s.set_dirichlet(pp.dirichlet_values([float(p.extras["eq_scaled"][0]) for p in plist]))
+    F, J = s.assemble(u, un)
+    x = torch.rand_like(u)
+    ms_asm = timed(lambda: s.assemble(u, un), 10)
+    ms_spmv = timed(lambda: s.spmv(J, x), 30)
+    b_asm = batch * (8 * 81 * nb + 8 * 9 * Vn + 2 * 8 * 9 * Vn + 8 * 3 * Vn + 4 * 4 * T + 4 * 16 * T)
+    b_spmv = batch * (8 * 81 * nb + 4 * nb + 4 * (Vn + 1) + 2 * 8 * 9 * Vn)
+    del F, J, x
+    l0 = s.launch_count()
+    pp.steady(tol=1e-8, max_steps=3)                      # warm-up (allocations of the Krylov basis)
+    sync()
+    l1 = s.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = pp.steady(tol=1e-8, max_steps=20)
+    e1.record()
+    sync()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_steady = float(t[0])
+    res = {
+        "workload": f"config3 batch: L_50_R_5 (V=3679, T=17297, 33111 DOFs), {batch} wall voltages in [-0.5,-1.25] V_T per GPU, "
+                    "pseudo-time march to steady state (increment <= 1e-8)",
+        "steady_solves_per_s": world * batch / (ms_steady * 1e-3), "ms_per_batch": ms_steady,
+        "pseudo_time_steps": int(out["steps"]), "newton_iterations_per_problem": int(out["iters"].sum(axis=0).max()),
+        "gpu_launches": int(s.launch_count() - l1),
+        "assemble": {"ms": ms_asm, "GBs": b_asm / ms_asm / 1e6, "frac_of_hbm_peak": b_asm / ms_asm / 1e6 / peak,
+                     "algorithmic_bytes": b_asm},
+        "spmv": {"ms": ms_spmv, "GBs": b_spmv / ms_spmv / 1e6, "frac_of_hbm_peak": b_spmv / ms_spmv / 1e6 / peak,
+                 "algorithmic_bytes": b_spmv,
+                 "note": "batch Jacobians (%.2f GB) exceed the 126 MB L2" % (batch * 8 * 81 * nb / 1e9)},
+    }
+    pp.solver.close()
+    return res
 
 
 # --------------------------------------------------------------------------------------------
@@ -238,12 +317,18 @@ def main():
         n_total, n_conv_total, n_its_total, bytes_total = n_local, n_conv, n_its, alg_bytes
     ms, ms_e2e = [float(v) for v in t.tolist()]
 
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    pore3d = None
+    if args.pore3d_batch > 0:
+        sw.close()
+        del h_out
+        torch.cuda.empty_cache()
+        pore3d = bench_pore3d(local, world, dev, args.pore3d_batch, peak)
     if rank == 0:
-        peaks = {}
-        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(pk):
-            peaks = json.load(open(pk))
-        peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = (bytes_total / world) / (ms * 1e-3) / 1e9       # per-GPU GB/s of the kernel
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         # DRAM traffic of the kernel: ncu's dram__bytes_read+write over the algorithmic bytes of the captured launch,
@@ -270,6 +355,8 @@ def main():
                          "algorithmic_bytes_per_step": bytes_total / world},
             "clocks": sampler.summary(),
         }
+        if pore3d is not None:
+            line["pore3d"] = pore3d
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = run_cpu(args.cpu_sample, args.voltages, dv=args.dv, xtol_path=args.xtol_path)
         print(json.dumps(line), flush=True)

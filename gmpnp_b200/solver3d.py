@@ -173,15 +173,20 @@ class PoreProblem:
                     co2_entry=np.array(co2s))
 
     def steady(self, opts: NewtonOpts | None = None, tol: float = 1e-10, max_steps: int = 200, dt_growth: float = 1.0,
-               u0=None):
-        """Steady state as the limit of the reference's pseudo-time march.
+               u0=None, dv_max: float | None = None):
+        """Steady state as the limit of the reference's pseudo-time march, optionally with a VOLTAGE RAMP.
 
         With the as-executed boundary conditions (3D:460-467, no facet integrals -- SURVEY finding 3) every ionic
         species is pure-Neumann, so the time-independent equations are singular: the total amount of, e.g., the
         cation is fixed only by the initial state, which backward Euler conserves exactly.  The steady state is
         therefore computed the way the reference reaches it (3D:782-858: backward Euler with dt_scaled = 73.84,
         Sechenov median update per step) and marched until max|u - u_n| <= tol * max(1, max|u|), optionally
-        growing the step.  Each step is one damped Newton solve (relaxation 0.9, 3D:796) from the previous state."""
+        growing the step.  Each step is one damped Newton solve (relaxation 0.9, 3D:796) from the previous state.
+
+        ``dv_max`` (in V_T): the reference applies the full wall voltage in the first step, from which its Newton
+        iteration diverges beyond |V| ~ 1.5 V_T on L_50_R_5; with ``dv_max`` the wall voltage of every problem is
+        ramped proportionally over ceil(max|V| / dv_max) pseudo-time steps (voltage continuation, BASELINE
+        north_star), and the convergence test only starts once the ramp is complete."""
         opts = opts or NewtonOpts.reference_3d()
         s = self.solver
         B = s.batch
@@ -189,10 +194,14 @@ class PoreProblem:
         u = un.clone()
         co2 = [float(p.extras["eq_scaled"][0]) for p in self.plist]
         packed = np.stack([p.pack() for p in self.plist])
+        Vt = np.array([p.V for p in self.plist], dtype=np.float64)
+        n_ramp = 1 if not dv_max else max(1, int(np.ceil(np.abs(Vt).max() / dv_max - 1e-12)))
         its, incs = [], []
         for step in range(max_steps):
+            Vk = Vt * min(1.0, (step + 1) / n_ramp)
+            packed[:, _params.P_V] = Vk
             s.set_params(packed)
-            s.set_dirichlet(self.dirichlet_values(co2))
+            s.set_dirichlet(self.dirichlet_values(co2, V=Vk))
             out = s.newton(u, un, opts)
             st = out["status"].cpu().numpy()
             if (st != 0).any():
@@ -205,6 +214,6 @@ class PoreProblem:
             incs.append(inc)
             un.copy_(u)
             packed[:, _params.P_KAPPA] /= dt_growth
-            if inc <= tol:
+            if inc <= tol and step + 1 >= n_ramp:
                 break
         return dict(u=u, iters=np.array(its), increments=np.array(incs), co2_entry=np.array(co2), steps=len(incs))
