@@ -37,6 +37,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=16, help="sweep points timed on the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pore3d-batch", type=int, default=32, help="3D pore problems per GPU in the 3D part (0: skip)")
+    ap.add_argument("--pivot", type=int, default=0, help="partial pivoting inside the 7x7 blocks (0: none; "
+                    "non-converged points are retried with pivoting, see Sweep1D)")
     ap.add_argument("--dv", type=float, default=0.75, help="largest voltage increment of the continuation [V_T]")
     ap.add_argument("--xtol-path", type=float, default=1.0,
                     help="increment tolerance of the intermediate continuation stages (1.0 = one Newton corrector "
@@ -254,7 +256,7 @@ def main():
     # weak scaling: every rank owns one full config-2 sweep (independent sweep points, no collective
     # on the data path; one gather of the per-point summaries at the end)
     pts = sweep.config2_points(args.voltages)
-    sw = sweep.Sweep1D(pts, device=local, dv_max=args.dv, xtol_path=args.xtol_path)
+    sw = sweep.Sweep1D(pts, device=local, dv_max=args.dv, xtol_path=args.xtol_path, pivot=args.pivot)
     n_local = sw.n_points
 
     # pinned host staging for the e2e arm
@@ -342,7 +344,8 @@ def main():
             "config": {"workload": WORKLOAD if args.voltages == 256 else f"reduced sweep ({args.voltages} V/chain)",
                        "points_per_gpu": n_local, "converged": int(n_conv_total),
                        "newton_iterations_per_step": int(n_its_total),
-                       "continuation": f"dV<={args.dv:g} V_T, xtol 1e-12 (final) / {args.xtol_path:g} (path), consistent Jacobian",
+                       "continuation": f"dV<={args.dv:g} V_T, xtol 1e-12 (final) / {args.xtol_path:g} (path), consistent Jacobian, "
+                                       f"in-block pivoting {'on' if args.pivot else 'off (equilibrated rows; failures retried with pivoting)'}",
                        "cache": "working set (elimination workspace 10.7 GB/GPU) >> 126 MB L2, no flush needed",
                        "parallelism": f"sweep points sharded, {world} GPU(s), no data-path collective"},
             "e2e": {"value": n_total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),

@@ -69,14 +69,13 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// 1/x to within ~1 ulp: hardware seed + two Newton steps (the IEEE division sequence costs ~4x as many
-// instructions; pivots and steric denominators do not need correct rounding)
+// 1/x to within ~1 ulp: hardware seed (>= 20 correct bits, PTX rcp.approx.ftz.f64) + two Newton steps
+// (20 -> 40 -> 80 bits); the IEEE division sequence costs ~4x as many instructions, and pivots and steric
+// denominators do not need correct rounding
 __device__ __forceinline__ double fast_rcp(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
     double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
     r = fma(r, e, r);
     e = fma(-x, r, 1.0);
     return fma(r, e, r);
@@ -475,20 +474,21 @@ __device__ double forward_sweep(const Group& g, const LaneConst& L, const double
 #pragma unroll
             for (int i = 0; i < NC; ++i) Y[i] = sF[i];      // lane 7: rhs lives in Y
             // point fluxes `J_i v_i ds` at both end points (1D:553, 738)
-            if (k == 0 || k == n - 1) {
+            if (r == 0) {
 #pragma unroll
                 for (int i = 0; i < NS; ++i) Y[i] += P[GMPNP_P_JFLUX + i];
             }
         }
-        // Dirichlet rows (1D:350-355): x=1 all components = (1,..,1,0); x=0 potential = V
-        if (k == n - 1) {
+        // Dirichlet rows (1D:350-355): x=1 all components = (1,..,1,0); x=0 potential = V.  Only the first row
+        // of a half is a boundary node (the halves start at nodes 0 and n-1).
+        if (r == 0 && k == n - 1) {
 #pragma unroll
             for (int i = 0; i < NC; ++i) {
                 if (c < NC) { B[i] = (i == c) ? 1.0 : 0.0; Y[i] = 0.0; }
                 else Y[i] = fu[s0 + i] - ((i < NS) ? 1.0 : 0.0);
             }
         }
-        if (k == 0) {
+        if (r == 0 && k == 0) {
             if (c < NC) { B[NS] = (c == NS) ? 1.0 : 0.0; Y[NS] = 0.0; }
             else Y[NS] = fu[s0 + NS] - P[GMPNP_P_V];
         }
@@ -496,7 +496,7 @@ __device__ double forward_sweep(const Group& g, const LaneConst& L, const double
             // ||b||_2 of the reference's (unscaled) system: undo the Poisson-row scaling except on Dirichlet rows
 #pragma unroll
             for (int i = 0; i < NS; ++i) rsq += Y[i] * Y[i];
-            const double yp = (k == 0 || k == n - 1) ? Y[NS] : Y[NS] * qscale;
+            const double yp = (r == 0) ? Y[NS] : Y[NS] * qscale;
             rsq += yp * yp;
         }
         issue(r + RING);                             // slot of node r is free: every lane is past its last read of it
@@ -521,48 +521,56 @@ __device__ void backward_sweep(const Group& g, int first, int dir, int rows, dou
                                double& mdx, double& mu) {
     if (rows <= 0) return;
     const int c = g.c;
-    double2* bw = reinterpret_cast<double2*>(g.ring);          // [RING][4][8]: lane c's row of the workspace
-    double* bu = g.ring + RING * 64;                           // [RING][8]:    lane c's component of u
+    double2* bwc = reinterpret_cast<double2*>(g.ring) + c;     // [RING][4][8]: lane c's row of the workspace
+    double* buc = g.ring + RING * 64 + c;                      // [RING][8]:    lane c's component of u
     double* sx = g.sm + SM_X;
-    // every lane stages what it will read itself, so no cross-lane visibility is needed for the ring
-    auto issue = [&](int q) {
-        if (q < rows && c < NC) {
-            const int s = q & (RING - 1);
-            const long node = first + dir * q;
-            const double* src = ws + node * 56 + c * 8;
+    // every lane stages what it will read itself, so no cross-lane visibility is needed for the ring;
+    // running global pointers, ring slots as compile-time constants (the row loop is unrolled RING times)
+    const double* wsrc = ws + (long)first * 56 + c * 8;        // workspace row of the next node to stage
+    const double* usrc = up + (long)first * NC + c;
+    double* udst = up + (long)first * NC + c;                  // u of the next node to update
+    const long wstep = (long)dir * 56, ustep = (long)dir * NC;
+    int staged = 0;
+    auto issue = [&](int s) {
+        if (staged < rows && c < NC) {
 #pragma unroll
-            for (int v = 0; v < 4; ++v) cp_async16(bw + (s * 4 + v) * 8 + c, src + 2 * v);
-            cp_async8(bu + s * 8 + c, up + node * NC + c);
+            for (int v = 0; v < 4; ++v) cp_async16(bwc + (s * 4 + v) * 8, wsrc + 2 * v);
+            cp_async8(buc + s * 8, usrc);
         }
         cp_async_commit();
+        wsrc += wstep; usrc += ustep; ++staged;
     };
 #pragma unroll
-    for (int q = 0; q < RING; ++q) issue(q);
-    for (int q = 0; q < rows; ++q) {
-        const int k = first + dir * q;
-        const int s = q & (RING - 1);
-        cp_async_wait<RING - 1>();
-        double xi = 0.0;
-        if (c < NC) {
-            const double2 r0 = bw[(s * 4 + 0) * 8 + c], r1 = bw[(s * 4 + 1) * 8 + c];
-            const double2 r2 = bw[(s * 4 + 2) * 8 + c], r3 = bw[(s * 4 + 3) * 8 + c];
-            const double ucur = bu[s * 8 + c];
-            xi = r3.y;
-            xi -= r0.x * xn[0]; xi -= r0.y * xn[1]; xi -= r1.x * xn[2]; xi -= r1.y * xn[3];
-            xi -= r2.x * xn[4]; xi -= r2.y * xn[5]; xi -= r3.x * xn[6];
-            const double un = ucur - relax * xi;
-            up[(long)k * NC + c] = un;
-            mdx = fmax(mdx, fabs(xi));
-            mu = fmax(mu, fabs(un));
+    for (int s = 0; s < RING; ++s) issue(s);
+    for (int q0 = 0; q0 < rows; q0 += RING) {
+#pragma unroll
+        for (int s = 0; s < RING; ++s) {
+            if (q0 + s < rows) {                               // group-uniform
+                cp_async_wait<RING - 1>();
+                double xi = 0.0;
+                if (c < NC) {
+                    const double2 r0 = bwc[(s * 4 + 0) * 8], r1 = bwc[(s * 4 + 1) * 8];
+                    const double2 r2 = bwc[(s * 4 + 2) * 8], r3 = bwc[(s * 4 + 3) * 8];
+                    const double ucur = buc[s * 8];
+                    xi = r3.y;
+                    xi -= r0.x * xn[0]; xi -= r0.y * xn[1]; xi -= r1.x * xn[2]; xi -= r1.y * xn[3];
+                    xi -= r2.x * xn[4]; xi -= r2.y * xn[5]; xi -= r3.x * xn[6];
+                    const double un = ucur - relax * xi;
+                    *udst = un;
+                    mdx = fmax(mdx, fabs(xi));
+                    mu = fmax(mu, fabs(un));
+                }
+                udst += ustep;
+                issue(s);
+                // x_k of all components to every lane (double-buffered: one group barrier per row)
+                double* sxq = sx + (s & 1) * 8;
+                sxq[c] = xi;
+                __syncwarp(g.mask);
+                const double2* xs = reinterpret_cast<const double2*>(sxq);
+                const double2 a0 = xs[0], a1 = xs[1], a2 = xs[2];
+                xn[0] = a0.x; xn[1] = a0.y; xn[2] = a1.x; xn[3] = a1.y; xn[4] = a2.x; xn[5] = a2.y; xn[6] = sxq[6];
+            }
         }
-        issue(q + RING);
-        // x_k of all components to every lane (double-buffered: one group barrier per row)
-        double* sxq = sx + (q & 1) * 8;
-        sxq[c] = xi;
-        __syncwarp(g.mask);
-        const double2* xs = reinterpret_cast<const double2*>(sxq);
-        const double2 a0 = xs[0], a1 = xs[1], a2 = xs[2];
-        xn[0] = a0.x; xn[1] = a0.y; xn[2] = a1.x; xn[3] = a1.y; xn[4] = a2.x; xn[5] = a2.y; xn[6] = sxq[6];
     }
     cp_async_wait<0>();
     __syncwarp(g.mask);

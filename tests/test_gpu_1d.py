@@ -315,3 +315,25 @@ def test_solve_EDL_drop_in_writes_reference_outputs(lib, tmp_path):
     gs = np.load(os.path.join(GOLDEN, "steady_50um.npz"))
     assert abs(m2["field_OHP"] - gs["ohp_-2.5"][0]) <= 1e-7 * abs(gs["ohp_-2.5"][0])
     assert abs(m2["eps_rel_OHP"] - gs["ohp_-2.5"][1]) <= 1e-9 * gs["ohp_-2.5"][1]
+
+
+def test_sweep_without_in_block_pivoting_matches_pivoted_solutions(lib):
+    """The sweep default skips the in-block pivot search (Poisson row equilibrated): same converged solutions as the
+    pivoted elimination, same Newton counts, and `retry_failed` re-runs non-converged points with pivoting."""
+    from gmpnp_b200 import sweep
+    pts = [p for p in sweep.config2_points(8, meshes=(1e-6,)) if p.V in (-12.5, -12.5 * 3 / 8)]
+    res = {}
+    for piv in (0, 1):
+        sw = sweep.Sweep1D(pts, device=0, dv_max=0.75, xtol_path=1.0, pivot=piv)
+        sw.upload()
+        outs = sw.solve_resident()
+        torch.cuda.synchronize()
+        assert int(sum((o["status"] != 0).sum() for o in outs)) == 0
+        assert sw.retry_failed(outs) == 0
+        res[piv] = (sw.groups[0]["u"].cpu().numpy().copy(), outs[0]["iters"].cpu().numpy().copy())
+        sw.close()
+    u0, it0 = res[0]
+    u1, it1 = res[1]
+    for c in range(7):
+        assert rel_l2(u0[:, :, c], u1[:, :, c]) < 1e-9, c
+    assert np.abs(it0.sum(axis=1) - it1.sum(axis=1)).max() <= 1
