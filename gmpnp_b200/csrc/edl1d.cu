@@ -54,7 +54,8 @@ __device__ __constant__ double GW2[2] = {0.5, 0.5};
 struct LaneConst {
     double coef[5];   // elementary-rate derivative coefficients of this lane's column (w,a,b,a2,b2)
     int sel[5];       // which staged nodal value multiplies it (7 = constant 1)
-    double rsig[6];   // -R_c = rsig . (w, a, b, a2, b2, kw1): this lane's own reaction row (residual)
+    double rsig[6];   // -R_c = rsig . (uH uOH, uOH uHCO3, uCO2 uOH, uCO32, uHCO3, 1): this lane's own reaction row
+                      // of the residual, rate constants folded in
 };
 
 __device__ __forceinline__ void cp_async8(double* dst_smem, const double* src) {
@@ -92,6 +93,7 @@ __device__ __forceinline__ void lane_consts(const double* P, int c, LaneConst& L
     else if (c == 3) { L.coef[3] = kA2; L.sel[3] = 7; }
     else if (c == 4) { L.coef[2] = kB; L.sel[2] = 1; }
     // own reaction row of the residual (1D:383-410): signs of (w, a, b, a2, b2, kw1), scaled by scale_R
+    const double kk[6] = {kW, kA, kB, kA2, kB2, P[GMPNP_P_KW1]};
     const double sg[5][6] = {{1, 0, 0, 0, 0, -1}, {1, 1, 1, -1, -1, -1}, {0, 1, -1, -1, 1, 0},
                              {0, -1, 0, 1, 0, 0}, {0, 0, 1, 0, -1, 0}};
 #pragma unroll
@@ -100,7 +102,7 @@ __device__ __forceinline__ void lane_consts(const double* P, int c, LaneConst& L
     for (int i = 0; i < 5; ++i) {
         if (c == i) {
 #pragma unroll
-            for (int t = 0; t < 6; ++t) L.rsig[t] = P[GMPNP_P_S + i] * sg[i][t];
+            for (int t = 0; t < 6; ++t) L.rsig[t] = P[GMPNP_P_S + i] * sg[i][t] * kk[t];
         }
     }
 }
@@ -155,11 +157,8 @@ __device__ __forceinline__ void cell_columns(const double* __restrict__ P, const
     };
     auto resid_acc = [&](double l0, double l1, double W, const double (&uq)[NS], double D) {
         a0F += W * D * (l0 * myU0 + l1 * myU1);
-        const double w = P[GMPNP_P_KW] * uq[0] * uq[1], a = P[GMPNP_P_KA] * uq[1] * uq[2];
-        const double b = P[GMPNP_P_KB] * uq[4] * uq[1];
-        const double a2_ = P[GMPNP_P_KA2] * uq[3], b2 = P[GMPNP_P_KB2] * uq[2];
-        const double mr = L.rsig[0] * w + L.rsig[1] * a + L.rsig[2] * b + L.rsig[3] * a2_ + L.rsig[4] * b2 +
-                          L.rsig[5] * P[GMPNP_P_KW1];
+        const double mr = L.rsig[0] * (uq[0] * uq[1]) + L.rsig[1] * (uq[1] * uq[2]) + L.rsig[2] * (uq[4] * uq[1]) +
+                          L.rsig[3] * uq[3] + L.rsig[4] * uq[2] + L.rsig[5];
         R0 += W * l0 * mr; R1 += W * l1 * mr;
     };
     if (c < NS) {
@@ -206,15 +205,16 @@ __device__ __forceinline__ void cell_columns(const double* __restrict__ P, const
         const double zj = P[GMPNP_P_Z + c];
         const double ih2 = ih * ih;
         const double Md = h * (1.0 / 3.0), Mo = h * (1.0 / 6.0), mb = 0.5 * h;
-        // reaction moments  E_r[ab] = coef_r * int phi_a phi_b u_sel  (polynomial: closed form)
-        double E00[5], E01[5], E11[5];
+        // reaction block column: int phi_a phi_b u_sel = (h/12) (alpha u_sel(node 0) + beta u_sel(node 1)) with
+        // (alpha, beta) = (3,1), (1,1), (1,3) for ab = 00, 01, 11 (closed form), so the five rate derivatives are
+        // combined per NODE first (Pn0, Pn1) and the three blocks are formed from those
+        double E0[5], E1[5];
+        const double h12 = h * (1.0 / 12.0);
 #pragma unroll
         for (int r = 0; r < 5; ++r) {
-            const double v0 = sU0[L.sel[r]], v1 = sU1[L.sel[r]];
-            const double ch = L.coef[r] * h;
-            E00[r] = ch * (0.25 * v0 + (1.0 / 12.0) * v1);
-            E01[r] = ch * ((1.0 / 12.0) * (v0 + v1));
-            E11[r] = ch * ((1.0 / 12.0) * v0 + 0.25 * v1);
+            const double ch = L.coef[r] * h12;
+            E0[r] = ch * sU0[L.sel[r]];
+            E1[r] = ch * sU1[L.sel[r]];
         }
         const double s0 = P[GMPNP_P_S], s1 = P[GMPNP_P_S + 1], s2 = P[GMPNP_P_S + 2];
         const double s3 = P[GMPNP_P_S + 3], s4 = P[GMPNP_P_S + 4];
@@ -225,20 +225,28 @@ __device__ __forceinline__ void cell_columns(const double* __restrict__ P, const
             R[3] = s3 * (E[3] - E[1]);
             R[4] = s4 * (E[2] - E[4]);
         };
+        double Pn0[5], Pn1[5];
+        rx(E0, Pn0); rx(E1, Pn1);
         double R00[5], R01[5], R11[5];
-        rx(E00, R00); rx(E01, R01); rx(E11, R11);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            R01[i] = Pn0[i] + Pn1[i];
+            R00[i] = fma(2.0, Pn0[i], R01[i]);
+            R11[i] = fma(2.0, Pn1[i], R01[i]);
+        }
         // diagonal (i == j) extras per block
         const double d00 = kappa * Md + ih + zj * gpa0 * mb + Ga0 * mD0;
         const double d01 = kappa * Mo - ih + zj * gpa0 * mb + Ga0 * mD1;
         const double d10 = kappa * Mo - ih + zj * gpa1 * mb + Ga1 * mD0;
         const double d11 = kappa * Md + ih + zj * gpa1 * mb + Ga1 * mD1;
+        const double nG0 = nuj * Ga0, nG1 = nuj * Ga1, nk = nuj * ih2;
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
-            const double k = ih2 * a0[i];
-            double v00 = nuj * (Ga0 * a1[i] + k);
-            double v01 = nuj * (Ga0 * a2[i] - k);
-            double v10 = nuj * (Ga1 * a1[i] - k);
-            double v11 = nuj * (Ga1 * a2[i] + k);
+            const double k = nk * a0[i];
+            double v00 = fma(nG0, a1[i], k);
+            double v01 = fma(nG0, a2[i], -k);
+            double v10 = fma(nG1, a1[i], -k);
+            double v11 = fma(nG1, a2[i], k);
             if (i < 5) { v00 += R00[i]; v01 += R01[i]; v10 += R01[i]; v11 += R11[i]; }
             const double dg = (i == c) ? 1.0 : 0.0;
             o.c00[i] = fma(dg, d00, v00);
