@@ -27,7 +27,7 @@ ap.add_argument("--L", type=float, default=100e-9)
 ap.add_argument("--R", type=float, default=50e-9)
 ap.add_argument("--refine", type=int, default=2)
 ap.add_argument("--gmres-iters", type=int, default=30)
-ap.add_argument("--reps", type=int, default=10)
+ap.add_argument("--reps", type=int, default=30)
 ap.add_argument("--overlap", type=int, default=-1, help="1/0: force the interior-rows/halo overlap on/off (-1: auto)")
 ap.add_argument("--emulate", type=int, default=0, help="emulate this many ranks inside one process (LocalComm)")
 a = ap.parse_args()
@@ -69,7 +69,8 @@ def barrier():
 
 
 def timed(fn, reps):
-    fn()
+    for _ in range(5):
+        fn()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
