@@ -780,6 +780,106 @@ vec_lincomb_kernel(long n, long vstride, int nvec, const double* __restrict__ V,
     out[i] = s;
 }
 
+// ---- distributed z-slab coarse space (same Galerkin correction as the single-mesh path, split at the points where
+// the ranks have to exchange: A_c and P^T r are summed over the ranks by the host with an all-reduce) -------------
+// Ac += sum over the block rows [0, n_rows) of P^T J P (shared-memory accumulation per CTA, one flush per CTA)
+__global__ void __launch_bounds__(1024)
+coarse_accumulate_kernel(int n_rows, const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
+                         const int* __restrict__ agg, const int* __restrict__ dir_flag, const double* __restrict__ J,
+                         double* __restrict__ Ac_out) {
+    extern __shared__ double Ac[];          // [NCO][NCO]
+    for (int i = threadIdx.x; i < NCO * NCO; i += blockDim.x) Ac[i] = 0.0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int row = blockIdx.x * nw + w; row < n_rows; row += gridDim.x * nw) {
+        const int I = agg[row];
+        for (int s = row_ptr[row]; s < row_ptr[row + 1]; ++s) {
+            const int col = col_idx[s];
+            const int Jc = agg[col];
+            for (int e = lane; e < 81; e += 32) {
+                const int i = e / 9, j = e % 9;
+                if (dir_flag[(long)row * NC + i] >= 0 || dir_flag[(long)col * NC + j] >= 0) continue;
+                atomicAdd(&Ac[(I * NC + i) * NCO + Jc * NC + j], J[(long)s * 81 + e]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NCO * NCO; i += blockDim.x)
+        if (Ac[i] != 0.0) atomicAdd(&Ac_out[i], Ac[i]);
+}
+
+// Aci = inverse of the (all-reduced) Galerkin matrix; empty coarse columns (all members Dirichlet) -> identity
+__global__ void __launch_bounds__(1024)
+coarse_invert_kernel(const double* __restrict__ Ac_in, double* __restrict__ Aci) {
+    extern __shared__ double Ac[];          // [NCO][NCO]
+    for (int i = threadIdx.x; i < NCO * NCO; i += blockDim.x) Ac[i] = Ac_in[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < NCO; i += blockDim.x)
+        if (Ac[i * NCO + i] == 0.0) Ac[i * NCO + i] = 1.0;
+    __syncthreads();
+    __shared__ double pivinv;
+    for (int c = 0; c < NCO; ++c) {
+        if (threadIdx.x == 0) {
+            double p = Ac[c * NCO + c];
+            if (!(fabs(p) > 1e-300)) p = 1.0;
+            pivinv = 1.0 / p;
+        }
+        __syncthreads();
+        const double pi = pivinv;
+        for (int j = threadIdx.x; j < NCO; j += blockDim.x)
+            if (j != c) Ac[c * NCO + j] *= pi;
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < NCO * NCO; idx += blockDim.x) {
+            const int r = idx / NCO, j = idx % NCO;
+            if (r == c || j == c) continue;
+            Ac[idx] -= Ac[r * NCO + c] * Ac[c * NCO + j];
+        }
+        __syncthreads();
+        for (int r = threadIdx.x; r < NCO; r += blockDim.x)
+            Ac[r * NCO + c] = (r == c) ? pi : -Ac[r * NCO + c] * pi;
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < NCO * NCO; i += blockDim.x) Aci[i] = Ac[i];
+}
+
+// rc += P^T r over the block rows [0, n_rows) (Dirichlet DOFs excluded)
+__global__ void __launch_bounds__(256)
+coarse_restrict_kernel(int n_rows, const int* __restrict__ agg, const int* __restrict__ dir_flag,
+                       const double* __restrict__ r, double* __restrict__ rc) {
+    __shared__ double sh[NCO];
+    for (int i = threadIdx.x; i < NCO; i += blockDim.x) sh[i] = 0.0;
+    __syncthreads();
+    const long total = (long)n_rows * NC;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int v = (int)(idx / NC), i = (int)(idx % NC);
+        if (dir_flag[idx] < 0) atomicAdd(&sh[agg[v] * NC + i], r[idx]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NCO; i += blockDim.x)
+        if (sh[i] != 0.0) atomicAdd(&rc[i], sh[i]);
+}
+
+// z += P (Aci rc) on the block rows [0, n_rows) (Dirichlet DOFs excluded); every CTA recomputes the 144-vector
+__global__ void __launch_bounds__(256)
+coarse_prolong_kernel(int n_rows, const int* __restrict__ agg, const int* __restrict__ dir_flag,
+                      const double* __restrict__ Aci, const double* __restrict__ rc, double* __restrict__ z) {
+    __shared__ double src[NCO], yc[NCO];
+    for (int i = threadIdx.x; i < NCO; i += blockDim.x) src[i] = rc[i];
+    __syncthreads();
+    for (int t = threadIdx.x; t < NCO; t += blockDim.x) {
+        const double* A = Aci + (long)t * NCO;
+        double y = 0.0;
+        for (int j = 0; j < NCO; ++j) y += A[j] * src[j];
+        yc[t] = y;
+    }
+    __syncthreads();
+    const long total = (long)n_rows * NC;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int v = (int)(idx / NC), i = (int)(idx % NC);
+        if (dir_flag[idx] < 0) z[idx] += yc[agg[v] * NC + i];
+    }
+}
+
 // z = D^{-1} r on the first n_rows block rows (Dirichlet rows are identity rows of J, so their D^{-1} is I)
 __global__ void __launch_bounds__(256)
 bjacobi_apply_kernel(int n_rows, const double* __restrict__ Dinv, const double* __restrict__ r, double* __restrict__ z) {
@@ -1336,6 +1436,65 @@ int gmpnp_bjacobi_apply_3d(gmpnp_handle* h, const double* d_r, double* d_z, int 
     GMPNP_CUDA_TRY(h, cudaSetDevice(h->device));
     const long total = (long)n_rows * NC;
     bjacobi_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n_rows, h->d_Dinv, d_r, d_z);
+    h->launches++;
+    GMPNP_CUDA_TRY(h, cudaGetLastError());
+    return GMPNP_OK;
+}
+
+int gmpnp_set_aggregates_3d(gmpnp_handle* h, const int* h_agg) {
+    if (!h || h->dim != 3 || !h_agg) return GMPNP_ERR_ARG;
+    for (int v = 0; v < h->n_nodes; ++v)
+        if (h_agg[v] < 0 || h_agg[v] >= NZ) return GMPNP_ERR_ARG;
+    GMPNP_CUDA_TRY(h, cudaSetDevice(h->device));
+    GMPNP_CUDA_TRY(h, cudaMemcpy(ext(h)->d_agg, h_agg, sizeof(int) * h->n_nodes, cudaMemcpyHostToDevice));
+    return GMPNP_OK;
+}
+
+int gmpnp_coarse_accumulate_3d(gmpnp_handle* h, const double* d_J, int n_rows, double* d_Ac, void* stream) {
+    if (!h || h->dim != 3 || !d_Ac || h->batch != 1 || n_rows < 1 || n_rows > h->n_nodes) return GMPNP_ERR_ARG;
+    GMPNP_CUDA_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int smem = (int)(sizeof(double) * NCO * NCO);
+    GMPNP_CUDA_TRY(h, cudaFuncSetAttribute(coarse_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    GMPNP_CUDA_TRY(h, cudaMemsetAsync(d_Ac, 0, sizeof(double) * NCO * NCO, st));
+    const int grid = std::max(1, std::min(148, (n_rows + 31) / 32));
+    coarse_accumulate_kernel<<<grid, 1024, smem, st>>>(n_rows, h->d_row_ptr, h->d_col_idx, ext(h)->d_agg, h->d_dir_flag,
+                                                        d_J ? d_J : h->d_J, d_Ac);
+    h->launches++;
+    GMPNP_CUDA_TRY(h, cudaGetLastError());
+    return GMPNP_OK;
+}
+
+int gmpnp_coarse_invert_3d(gmpnp_handle* h, const double* d_Ac, void* stream) {
+    if (!h || h->dim != 3 || !d_Ac || h->batch != 1) return GMPNP_ERR_ARG;
+    GMPNP_CUDA_TRY(h, cudaSetDevice(h->device));
+    const int smem = (int)(sizeof(double) * NCO * NCO);
+    GMPNP_CUDA_TRY(h, cudaFuncSetAttribute(coarse_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    coarse_invert_kernel<<<1, 1024, smem, (cudaStream_t)stream>>>(d_Ac, ext(h)->d_Aci);
+    h->launches++;
+    GMPNP_CUDA_TRY(h, cudaGetLastError());
+    return GMPNP_OK;
+}
+
+int gmpnp_coarse_restrict_3d(gmpnp_handle* h, const double* d_r, int n_rows, double* d_rc, void* stream) {
+    if (!h || h->dim != 3 || !d_r || !d_rc || h->batch != 1 || n_rows < 1 || n_rows > h->n_nodes) return GMPNP_ERR_ARG;
+    GMPNP_CUDA_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    GMPNP_CUDA_TRY(h, cudaMemsetAsync(d_rc, 0, sizeof(double) * NCO, st));
+    const long total = (long)n_rows * NC;
+    const int grid = (int)std::max<long>(1, std::min<long>(148 * 4, (total + 2047) / 2048));
+    coarse_restrict_kernel<<<grid, 256, 0, st>>>(n_rows, ext(h)->d_agg, h->d_dir_flag, d_r, d_rc);
+    h->launches++;
+    GMPNP_CUDA_TRY(h, cudaGetLastError());
+    return GMPNP_OK;
+}
+
+int gmpnp_coarse_prolong_3d(gmpnp_handle* h, const double* d_rc, double* d_z, int n_rows, void* stream) {
+    if (!h || h->dim != 3 || !d_rc || !d_z || h->batch != 1 || n_rows < 1 || n_rows > h->n_nodes) return GMPNP_ERR_ARG;
+    GMPNP_CUDA_TRY(h, cudaSetDevice(h->device));
+    const long total = (long)n_rows * NC;
+    const int grid = (int)std::max<long>(1, std::min<long>(148 * 4, (total + 2047) / 2048));
+    coarse_prolong_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_rows, ext(h)->d_agg, h->d_dir_flag, ext(h)->d_Aci, d_rc, d_z);
     h->launches++;
     GMPNP_CUDA_TRY(h, cudaGetLastError());
     return GMPNP_OK;

@@ -7,7 +7,9 @@ LU (3D:792) and has no distributed path at all.  Here the refined p
 
 * BSR SpMV on the local rows after a HALO EXCHANGE of the ghost vertices' 9-vectors
   (``torch.distributed`` point-to-point over NCCL/NVLink; interface size ~ a pore cross-section),
-* a per-node 9x9 block-Jacobi preconditioner (communication-free),
+* a per-node 9x9 block-Jacobi preconditioner (communication-free) plus the additive z-slab coarse correction of
+  the single-mesh path (16 slabs x 9 components): its 144 x 144 Galerkin matrix is summed over the ranks once per
+  Newton iteration, its restricted residual (144 doubles) once per application,
 * CGS2 orthogonalisation with ONE all-reduce per Gram-Schmidt pass (the norm of the new direction is fused
   into the second pass), i.e. two small all-reduces per iteration; the Hessenberg/Givens recurrences run
   redundantly on every rank's host from the reduced dot products.
@@ -112,16 +114,26 @@ class PartitionedPore:
     """One pore problem (one parameter point) on a partitioned mesh.  ``parts`` are the parts handled by THIS
     process (all of them with :class:`LocalComm`, exactly one with :class:`TorchComm`)."""
 
-    def __init__(self, mesh, L: float, R: float, prm, parts, comm, device: int = 0, dirichlet=None):
+    NZ = 16          # z-slabs of the coarse space (NZ in csrc/pore3d.cu)
+
+    def __init__(self, mesh, L: float, R: float, prm, parts, comm, device: int = 0, dirichlet=None, coarse: bool = True):
         self.mesh, self.L, self.R, self.prm = mesh, L, R, prm
         self.parts, self.comm = list(parts), comm
         self.device = torch.device("cuda", int(device))
         self.dofs, self.kind, self.info = dirichlet if dirichlet is not None else marking.dirichlet_sets(mesh, L, R)
         self.solvers, self.dir_sel = [], []
+        self.coarse = bool(coarse)
+        z = np.asarray(mesh.x)[:, 2]
+        zmin, zmax = float(z.min()), float(z.max())
         for p in self.parts:
             ld, sel = _part.local_dirichlet(p, self.dofs)
             s = Solver3D(p.local_mesh(), ld, batch=1, device=device)
             s.set_params([prm])
+            # GLOBAL z-slab ids of the local vertices (the handle's own default is relative to the local slab)
+            agg = np.clip(((p.x[:, 2] - zmin) / (zmax - zmin if zmax > zmin else 1.0) * self.NZ).astype(np.int32),
+                          0, self.NZ - 1)
+            agg = np.ascontiguousarray(agg, dtype=np.int32)
+            check(s.lib.gmpnp_set_aggregates_3d(s._h, agg.ctypes.data_as(C.POINTER(C.c_int))), s._h)
             self.solvers.append(s)
             self.dir_sel.append(sel)
         self.lib = self.solvers[0].lib
@@ -183,6 +195,17 @@ class PartitionedPore:
                 self.J[k] = J
                 check(self.lib.gmpnp_bjacobi_setup_3d(s._h, ptr(J), self._stream()), s._h)
             Fs.append(F)
+        if want_J and self.coarse:
+            nco = self.NZ * NC
+            Acs = []
+            for s, p, J in zip(self.solvers, self.parts, self.J):
+                Ac = torch.empty(nco * nco, dtype=torch.float64, device=self.device)
+                check(self.lib.gmpnp_coarse_accumulate_3d(s._h, ptr(J), p.n_own, ptr(Ac), self._stream()), s._h)
+                Acs.append(Ac)
+            Ac = self.comm.allreduce_sum(Acs)
+            self.stats["allreduce"] += 1
+            for s in self.solvers:
+                check(self.lib.gmpnp_coarse_invert_3d(s._h, ptr(Ac), self._stream()), s._h)
         nrm2 = self.dot_owned([F.view(1, -1) for F in Fs], 1, [F.view(-1) for F in Fs])
         return Fs, math.sqrt(float(nrm2[0]))
 
@@ -218,8 +241,19 @@ class PartitionedPore:
         return out
 
     def precond(self, rs, zs):
+        """z = D^-1 r + P A_c^-1 P^T r on the owned rows (one 144-double all-reduce when the coarse space is on)."""
         for s, p, r, z in zip(self.solvers, self.parts, rs, zs):
             check(self.lib.gmpnp_bjacobi_apply_3d(s._h, ptr(r), ptr(z), p.n_own, self._stream()), s._h)
+        if self.coarse:
+            rcs = []
+            for s, p, r in zip(self.solvers, self.parts, rs):
+                rc = torch.empty(self.NZ * NC, dtype=torch.float64, device=self.device)
+                check(self.lib.gmpnp_coarse_restrict_3d(s._h, ptr(r), p.n_own, ptr(rc), self._stream()), s._h)
+                rcs.append(rc)
+            rc = self.comm.allreduce_sum(rcs)
+            self.stats["allreduce"] += 1
+            for s, p, z in zip(self.solvers, self.parts, zs):
+                check(self.lib.gmpnp_coarse_prolong_3d(s._h, ptr(rc), ptr(z), p.n_own, self._stream()), s._h)
 
     # -- GMRES(m), right-preconditioned, CGS2 ------------------------------------------------------
     def gmres(self, bs, m: int = 50, maxit: int = 500, rtol: float = 1e-10, callback=None):

@@ -195,6 +195,17 @@ int gmpnp_vec_lincomb(gmpnp_handle* h, const double* d_V, long long vstride, int
 int gmpnp_bjacobi_setup_3d(gmpnp_handle* h, const double* d_J, void* stream);
 int gmpnp_bjacobi_apply_3d(gmpnp_handle* h, const double* d_r, double* d_z, int n_rows, void* stream);
 
+/* Distributed z-slab coarse correction (the Galerkin space of the single-mesh preconditioner, 16 slabs x 9
+ * components = 144 unknowns, split where the ranks exchange): set the GLOBAL slab id of every local vertex;
+ * accumulate this rank's P^T J P over its owned rows into d_Ac[144*144] (host all-reduces it), invert the reduced
+ * matrix into the handle; per application restrict d_rc[144] += P^T r over the owned rows (host all-reduces it)
+ * and prolong d_z += P (A_c^-1 d_rc).  Batch 1.                                                                */
+int gmpnp_set_aggregates_3d(gmpnp_handle* h, const int* h_agg);
+int gmpnp_coarse_accumulate_3d(gmpnp_handle* h, const double* d_J, int n_rows, double* d_Ac, void* stream);
+int gmpnp_coarse_invert_3d(gmpnp_handle* h, const double* d_Ac, void* stream);
+int gmpnp_coarse_restrict_3d(gmpnp_handle* h, const double* d_r, int n_rows, double* d_rc, void* stream);
+int gmpnp_coarse_prolong_3d(gmpnp_handle* h, const double* d_rc, double* d_z, int n_rows, void* stream);
+
 /* Median over the vertices of component `comp` for every problem (np.median, 3D:817-820):
  * d_med[batch].                                                                            */
 int gmpnp_median_3d(gmpnp_handle* h, const double* d_u, int comp, double* d_med, void* stream);
