@@ -29,6 +29,10 @@ ap.add_argument("--refine", type=int, default=2)
 ap.add_argument("--gmres-iters", type=int, default=30)
 ap.add_argument("--reps", type=int, default=30)
 ap.add_argument("--overlap", type=int, default=-1, help="1/0: force the interior-rows/halo overlap on/off (-1: auto)")
+ap.add_argument("--newton", type=int, default=0, help="also time this many damped Newton iterations of the first "
+                "reference time step (assembly + preconditioner setup + GMRES to --lin-rtol)")
+ap.add_argument("--lin-rtol", type=float, default=1e-8)
+ap.add_argument("--coarse", type=int, default=1)
 ap.add_argument("--emulate", type=int, default=0, help="emulate this many ranks inside one process (LocalComm)")
 a = ap.parse_args()
 
@@ -56,7 +60,7 @@ else:
     parts = partition.partition_z(mesh, world, ranks=[rank])
     comm = TorchComm(parts[0])
     nparts = world
-pp = PartitionedPore(mesh, a.L, a.R, prm, parts, comm, device=local, dirichlet=dirichlet)
+pp = PartitionedPore(mesh, a.L, a.R, prm, parts, comm, device=local, dirichlet=dirichlet, coarse=bool(a.coarse))
 if a.overlap >= 0:
     pp.overlap = bool(a.overlap)
 setup_s = time.time() - t0
@@ -114,6 +118,15 @@ if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_gmres = float(t[0])
 
+newton = None
+if a.newton > 0:
+    u0 = pp.from_global(ung * 0.0)
+    barrier()
+    t0 = time.time()
+    out = pp.newton(u0, uns, maxit=a.newton, lin_rtol=a.lin_rtol, lin_restart=100, lin_maxit=3000)
+    barrier()
+    newton = dict(out, wall_s=time.time() - t0)
+
 nb_local = sum(s.n_blocks for s in pp.solvers)
 own_rows = sum(p.n_own for p in pp.parts)
 ghost = sum(p.n_ghost for p in pp.parts)
@@ -140,7 +153,7 @@ if rank == 0:
             "spmv_frac_of_hbm_peak_per_gpu": b_spmv / ms_spmv / 1e6 / (peak * gpus),
             "gmres_iters": its, "gmres_ms_per_iter": ms_gmres / max(its, 1),
             "allreduces_per_iter": (pp.stats["allreduce"] - st0["allreduce"]) / max(its, 1),
-            "peak_GBs": peak}
+            "coarse_space": bool(a.coarse), "newton": newton, "peak_GBs": peak}
     print(json.dumps(line), flush=True)
 if world > 1:
     dist.barrier()
