@@ -337,3 +337,42 @@ def test_sweep_without_in_block_pivoting_matches_pivoted_solutions(lib):
     for c in range(7):
         assert rel_l2(u0[:, :, c], u1[:, :, c]) < 1e-9, c
     assert np.abs(it0.sum(axis=1) - it1.sum(axis=1)).max() <= 1
+
+
+@pytest.mark.parametrize("fine,coarse", [(1, 0), (1, 1), (2, 1), (2, 2), (5, 3), (6, 3), (40, 23), (41, 23)])
+def test_tiny_even_and_odd_meshes_match_the_oracle(lib, fine, coarse):
+    """Edge cases of the two-sided elimination: 2 ... 65 nodes, even and odd node counts (all reference meshes have an
+    odd count), fewer rows than the staging ring is deep.  One reference solve() from u = 0 with a short time step,
+    both Jacobian rules, pivoted and pivot-free: same Newton count and iterate as the oracle."""
+    from gmpnp_b200 import meshio, params, solver1d
+    from gmpnp_b200._lib import NewtonOpts
+    from oracle import solver as osolver
+    if coarse == 0:
+        x = np.array([0.0, 1.0])
+    else:
+        x = meshio.graded_interval(fine, 0.01, coarse).x[:, 0]
+    n = len(x)
+    cells = np.stack([np.arange(n - 1), np.arange(1, n)], axis=1)
+    prm = params.params_1d(L_n=1.0e-6, voltage_multiplier=-0.3, time_step=1.0e-7)
+    bd, bv = osolver.bc_1d(n, 7, prm.V)
+    for jac_rule in (0, 1):
+        disc = osolver.Discretisation(x, cells, 7, jac_rule=jac_rule)
+        un = np.tile(np.array([1.0] * 6 + [0.0]), n)
+        uo, k, conv, r0, r = osolver.newton(disc, prm, np.zeros(disc.ndof), un, bd, bv, point_flux=prm.jflux)
+        assert conv
+        for pivot in (1, 0):
+            s = solver1d.Solver1D(x, batch=3)
+            s.set_params([prm] * 3)
+            u = torch.zeros(3, n, 7, dtype=torch.float64, device=_dev())
+            unt = solver1d.bulk_state(3, n, _dev())
+            o = NewtonOpts.reference_1d()
+            o.jac_rule, o.pivot = jac_rule, pivot
+            out = s.newton(u, unt, o)
+            torch.cuda.synchronize()
+            assert out["status"].tolist() == [0, 0, 0], (n, jac_rule, pivot)
+            assert out["iters"].tolist() == [k] * 3, (n, jac_rule, pivot, out["iters"].tolist(), k)
+            assert abs(float(out["r0"][0]) - r0) <= 1e-10 * r0
+            got = u.cpu().numpy()
+            for c in range(7):
+                assert rel_l2(got[1][:, c], uo.reshape(n, 7)[:, c]) < 1e-8, (n, jac_rule, pivot, c)
+            s.close()
