@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--voltages", type=int, default=256, help="voltage points per chain (256 = config 2)")
     ap.add_argument("--cpu-sample", type=int, default=16, help="sweep points timed on the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pore3d-batch", type=int, default=32, help="3D pore problems per GPU in the 3D part (0: skip)")
+    ap.add_argument("--pore3d-batch", type=int, default=128, help="3D pore problems per GPU in the 3D part (0: skip)")
     ap.add_argument("--pivot", type=int, default=0, help="partial pivoting inside the 7x7 blocks (0: none; "
                     "non-converged points are retried with pivoting, see Sweep1D)")
     ap.add_argument("--dv", type=float, default=0.75, help="largest voltage increment of the continuation [V_T]")

@@ -322,7 +322,7 @@ __device__ void entry_consts(const double* P, int e, EntryConst& E) {
 
 constexpr int ASM_WARPS = 8;
 
-__global__ void __launch_bounds__(ASM_WARPS * 32)
+__global__ void __launch_bounds__(ASM_WARPS * 32, 4)
 assemble_bsr_kernel(int n_blocks, int n_vert, int n_tet, const int* __restrict__ blk_ptr,
                     const int* __restrict__ blk_src, const double2* __restrict__ blk_geo,
                     const int* __restrict__ blk_row, const int* __restrict__ col_idx,
@@ -330,13 +330,23 @@ assemble_bsr_kernel(int n_blocks, int n_vert, int n_tet, const int* __restrict__
                     const double* __restrict__ mom, double* __restrict__ J) {
     __shared__ double P[GMPNP_NPAR];
     __shared__ double sums[ASM_WARPS][32];   // per warp: Q[0..7] | Pc[8..15] | Tt[16..23] | sMab [24]
+    // per-entry constants of the 81 block entries, shared by the CTA (kept out of registers: the kernel is bound by
+    // the latency of its dependent gather loads, so occupancy matters more than a few shared-memory reads)
+    __shared__ double Ed[9][96];             // cQ, cD, cZ (= cDz + cE), cP, cM, c8, rc0, rc1, rc2
+    __shared__ int Ei[5][96];                // i7, i, rs0, rs1, rs2
     const int prob = blockIdx.y;
     for (int i = threadIdx.x; i < GMPNP_NPAR; i += blockDim.x) P[i] = params[(long)prob * GMPNP_NPAR + i];
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    EntryConst E[3];
-#pragma unroll
-    for (int t = 0; t < 3; ++t) entry_consts(P, lane + 32 * t, E[t]);
+    if (threadIdx.x < 96) {
+        EntryConst E;
+        entry_consts(P, threadIdx.x, E);
+        const int e = threadIdx.x;
+        Ed[0][e] = E.cQ; Ed[1][e] = E.cD; Ed[2][e] = E.cDz + E.cE; Ed[3][e] = E.cP; Ed[4][e] = E.cM; Ed[5][e] = E.c8;
+        Ed[6][e] = E.rc[0]; Ed[7][e] = E.rc[1]; Ed[8][e] = E.rc[2];
+        Ei[0][e] = E.i7; Ei[1][e] = E.i; Ei[2][e] = E.rs[0]; Ei[3][e] = E.rs[1]; Ei[4][e] = E.rs[2];
+    }
+    __syncthreads();
     const double kappa = P[GMPNP_P_KAPPA];
     const double* up = u + (long)prob * n_vert * NC;
     const double* mo = mom + (long)prob * n_tet * NMOM;
@@ -385,13 +395,15 @@ assemble_bsr_kernel(int n_blocks, int n_vert, int n_tet, const int* __restrict__
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            if (!E[k].valid) continue;
-            double val = E[k].cQ * sw[E[k].i7] + E[k].cP * sw[8 + E[k].i7];
-            val += E[k].cD * dsum + (E[k].cDz + E[k].cE) * zsum + E[k].cM * sMab + E[k].c8 * ppsum;
-            val += E[k].rc[0] * sw[16 + E[k].rs[0]] + E[k].rc[1] * sw[16 + E[k].rs[1]] + E[k].rc[2] * sw[16 + E[k].rs[2]];
+            const int e = lane + 32 * k;
+            if (e >= 81) continue;
+            const int i7 = Ei[0][e], ei = Ei[1][e];
+            double val = Ed[0][e] * sw[i7] + Ed[3][e] * sw[8 + i7];
+            val += Ed[1][e] * dsum + Ed[2][e] * zsum + Ed[4][e] * sMab + Ed[5][e] * ppsum;
+            val += Ed[6][e] * sw[16 + Ei[2][e]] + Ed[7][e] * sw[16 + Ei[3][e]] + Ed[8][e] * sw[16 + Ei[4][e]];
             // Dirichlet rows: identity
-            if (dir_flag[(long)va * NC + E[k].i] >= 0) val = (va == vb && lane + 32 * k == E[k].i * 10) ? 1.0 : 0.0;
-            Jp[(long)blk * 81 + lane + 32 * k] = val;
+            if (dir_flag[(long)va * NC + ei] >= 0) val = (va == vb && e == ei * 10) ? 1.0 : 0.0;
+            Jp[(long)blk * 81 + e] = val;
         }
     }
 }
@@ -1134,7 +1146,7 @@ static int launch_assemble(gmpnp_handle* h, const double* d_u, const double* d_u
         h->launches++;
     }
     if (d_J) {
-        int gx = std::min((h->n_blocks + ASM_WARPS - 1) / ASM_WARPS, 148 * 8);
+        int gx = std::min((h->n_blocks + ASM_WARPS - 1) / ASM_WARPS, 148 * 16);
         dim3 gC(gx, B);
         assemble_bsr_kernel<<<gC, ASM_WARPS * 32, 0, st>>>(h->n_blocks, V, T, h->d_blk_ptr, h->d_blk_src,
                                                            ext(h)->d_blk_geo, ext(h)->d_blk_row, h->d_col_idx,
