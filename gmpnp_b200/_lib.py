@@ -30,6 +30,15 @@ class NewtonOpts(C.Structure):
         return cls(1e-4, 1e-4, 0.9, 1e-12, 50, 0, 1, 2000, 100, 1e-10, 0.0, 0, 0)
 
     @classmethod
+    def sweep_3d(cls):
+        """reference_3d with the linear-solver settings used for batched sweeps: GMRES(40) to 1e-8.  Measured on a
+        batch of 64 config-3 problems: same Newton counts, solutions within 3e-11 of GMRES(100)/1e-10, 2.3x faster
+        (the CGS2 orthogonalisation against a long basis dominates the iteration's HBM traffic)."""
+        o = cls.reference_3d()
+        o.lin_restart, o.lin_rtol = 40, 1e-8
+        return o
+
+    @classmethod
     def steady(cls, xtol=1e-12, maxit=50, relax=1.0, xtol_path=0.0, jac_rule=0):
         return cls(1e-4, 1e-4, relax, xtol, maxit, 1, 1, 2000, 100, 1e-12, xtol_path, jac_rule, 0)
 
