@@ -892,6 +892,98 @@ coarse_prolong_kernel(int n_rows, const int* __restrict__ agg, const int* __rest
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// L2 projection of grad(u_i) onto P1 vectors (dolfin project(grad(u), W), 3D:884-909): consistent P1 mass
+// matrix M (scalar, same pattern as the BSR blocks, geometry only), right-hand side b_v = sum_{t in v} vol_t/4
+// grad(u)_t, Jacobi-preconditioned CG for all 27 columns (9 components x 3 directions) of a problem at once with
+// per-column scalars, fixed iteration count, no host synchronisation.  Post-processing, off the hot path.
+// ---------------------------------------------------------------------------------------
+constexpr int NG = NC * 3;              // columns k = comp * 3 + d
+
+// b[prob][v][k]; also x = 0, r = b, z = r / M_vv, p = z
+__global__ void __launch_bounds__(256)
+gradproj_rhs_kernel(int n_vert, const int* __restrict__ node_ptr, const int* __restrict__ node_src,
+                    const int* __restrict__ tets, const double* __restrict__ geom, const double* __restrict__ mass,
+                    const int* __restrict__ diag_idx, const double* __restrict__ u, double* __restrict__ x,
+                    double* __restrict__ r, double* __restrict__ z, double* __restrict__ pvec) {
+    const int prob = blockIdx.y;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)n_vert * NG) return;
+    const int v = (int)(idx / NG), k = (int)(idx % NG), comp = k / 3, d = k % 3;
+    const double* up = u + (long)prob * n_vert * NC;
+    double b = 0.0;
+    for (int s = node_ptr[v]; s < node_ptr[v + 1]; ++s) {
+        const int t = node_src[s] >> 2;
+        const double* ge = geom + (long)t * 13;
+        double gsum = 0.0;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) gsum += ge[a * 3 + d] * up[(long)tets[t * 4 + a] * NC + comp];
+        b += 0.25 * ge[12] * gsum;
+    }
+    const long o = (long)prob * n_vert * NG + idx;
+    const double zi = b / mass[diag_idx[v]];
+    x[o] = 0.0; r[o] = b; z[o] = zi; pvec[o] = zi;
+}
+
+// q = M p for the 27 columns
+__global__ void __launch_bounds__(256)
+gradproj_spmv_kernel(int n_vert, const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
+                     const double* __restrict__ mass, const double* __restrict__ pvec, double* __restrict__ q) {
+    const int prob = blockIdx.y;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)n_vert * NG) return;
+    const int v = (int)(idx / NG), k = (int)(idx % NG);
+    const double* pp = pvec + (long)prob * n_vert * NG;
+    double s = 0.0;
+    for (int e = row_ptr[v]; e < row_ptr[v + 1]; ++e) s += mass[e] * pp[(long)col_idx[e] * NG + k];
+    q[(long)prob * n_vert * NG + idx] = s;
+}
+
+// dots[prob][k] = sum_v a[v][k] b[v][k]          grid = (NG, batch)
+__global__ void __launch_bounds__(256)
+gradproj_dot_kernel(int n_vert, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ dots) {
+    __shared__ double sh[8];
+    const int k = blockIdx.x, prob = blockIdx.y;
+    const double* ap = a + (long)prob * n_vert * NG;
+    const double* bp = b + (long)prob * n_vert * NG;
+    double s = 0.0;
+    for (int v = threadIdx.x; v < n_vert; v += blockDim.x) s += ap[(long)v * NG + k] * bp[(long)v * NG + k];
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) dots[(long)prob * NG + k] = s;
+}
+
+// x += alpha p, r -= alpha q, z = r / M_vv   with alpha = rz / pq per column
+__global__ void __launch_bounds__(256)
+gradproj_update_kernel(int n_vert, const double* __restrict__ mass, const int* __restrict__ diag_idx,
+                       const double* __restrict__ rz, const double* __restrict__ pq, const double* __restrict__ pvec,
+                       const double* __restrict__ q, double* __restrict__ x, double* __restrict__ r, double* __restrict__ z) {
+    const int prob = blockIdx.y;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)n_vert * NG) return;
+    const int v = (int)(idx / NG), k = (int)(idx % NG);
+    const double den = pq[(long)prob * NG + k];
+    const double alpha = (den > 0.0) ? rz[(long)prob * NG + k] / den : 0.0;
+    const long o = (long)prob * n_vert * NG + idx;
+    x[o] += alpha * pvec[o];
+    const double rn = r[o] - alpha * q[o];
+    r[o] = rn;
+    z[o] = rn / mass[diag_idx[v]];
+}
+
+// p = z + beta p with beta = rz_new / rz_old per column
+__global__ void __launch_bounds__(256)
+gradproj_dir_kernel(int n_vert, const double* __restrict__ rz_new, const double* __restrict__ rz_old,
+                    const double* __restrict__ z, double* __restrict__ pvec) {
+    const int prob = blockIdx.y;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)n_vert * NG) return;
+    const int k = (int)(idx % NG);
+    const double den = rz_old[(long)prob * NG + k];
+    const double beta = (den > 0.0) ? rz_new[(long)prob * NG + k] / den : 0.0;
+    const long o = (long)prob * n_vert * NG + idx;
+    pvec[o] = z[o] + beta * pvec[o];
+}
+
 // z = D^{-1} r on the first n_rows block rows (Dirichlet rows are identity rows of J, so their D^{-1} is I)
 __global__ void __launch_bounds__(256)
 bjacobi_apply_kernel(int n_rows, const double* __restrict__ Dinv, const double* __restrict__ r, double* __restrict__ z) {
@@ -928,6 +1020,8 @@ struct Host3D {   // device arrays that only the 3D path needs and common.cuh do
     int* d_agg_nodes = nullptr;
     double* d_Aci = nullptr;
     double* d_yc = nullptr;
+    double* d_mass = nullptr;       // scalar P1 mass matrix on the BSR pattern [nb] (gradient projection)
+    double* d_gp = nullptr;         // gradient-projection work vectors [4][batch][V][27] + scalars
     double* d_partial = nullptr;    // first-stage partial sums of the partitioned-mode reductions
     size_t partial_doubles = 0;
     int restart_alloc = 0;
@@ -944,7 +1038,7 @@ void pore3d_free_ext(gmpnp_handle* h) {
     auto it = g_ext.find(h);
     if (it == g_ext.end()) return;
     Host3D* e = it->second;
-    void* bufs[] = {e->d_partial, e->d_blk_row, e->d_blk_geo, e->d_agg, e->d_agg_ptr, e->d_agg_nodes, e->d_Aci, e->d_yc, e->d_V, e->d_w, e->d_z,
+    void* bufs[] = {e->d_mass, e->d_gp, e->d_partial, e->d_blk_row, e->d_blk_geo, e->d_agg, e->d_agg_ptr, e->d_agg_nodes, e->d_Aci, e->d_yc, e->d_V, e->d_w, e->d_z,
                     e->d_dx, e->d_d1, e->d_d2, e->d_nrm, e->d_H, e->d_cs, e->d_sn, e->d_g, e->d_tol, e->d_coef,
                     e->d_beta, e->d_dxmax, e->d_umax, e->d_jdone, e->d_active};
     for (void* b : bufs) if (b) cudaFree(b);
@@ -1090,6 +1184,15 @@ int gmpnp_create_3d(gmpnp_handle** out, int device, const double* h_xyz, int n_v
     if ((rc = dev_upload(h, &h->d_dir_flag, dir_flag))) return rc;
     if ((rc = dev_upload(h, &e->d_blk_row, blk_row))) return rc;
     if ((rc = dev_upload(h, &e->d_blk_geo, blk_geo))) return rc;
+    {   // scalar P1 mass matrix on the block pattern: M_vw = sum_t vol_t (1 + delta_vw) / 20
+        std::vector<double> mass(nb, 0.0);
+        for (int s = 0; s < nb; ++s)
+            for (int c = blk_cnt[s]; c < blk_cnt[s + 1]; ++c) {
+                const int src = blk_src[c], a = (src >> 2) & 3, b = src & 3;
+                mass[s] += blk_geo[c].y * ((a == b) ? 0.1 : 0.05);
+            }
+        if ((rc = dev_upload(h, &e->d_mass, mass))) return rc;
+    }
     if ((rc = dev_upload(h, &e->d_agg, agg))) return rc;
     if ((rc = dev_upload(h, &e->d_agg_ptr, agg_ptr))) return rc;
     if ((rc = dev_upload(h, &e->d_agg_nodes, agg_nodes))) return rc;
@@ -1449,6 +1552,34 @@ int gmpnp_bjacobi_apply_3d(gmpnp_handle* h, const double* d_r, double* d_z, int 
     const long total = (long)n_rows * NC;
     bjacobi_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n_rows, h->d_Dinv, d_r, d_z);
     h->launches++;
+    GMPNP_CUDA_TRY(h, cudaGetLastError());
+    return GMPNP_OK;
+}
+
+int gmpnp_grad_project_3d(gmpnp_handle* h, const double* d_u, double* d_g, int n_iter, void* stream) {
+    if (!h || h->dim != 3 || !d_u || !d_g || n_iter < 1) return GMPNP_ERR_ARG;
+    GMPNP_CUDA_TRY(h, cudaSetDevice(h->device));
+    Host3D* e = ext(h);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int V = h->n_nodes, B = h->batch;
+    const size_t nvec = (size_t)B * V * NG;
+    if (!e->d_gp) GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_gp, sizeof(double) * (4 * nvec + 3 * (size_t)B * NG)));
+    double *r = e->d_gp, *z = r + nvec, *pv = z + nvec, *q = pv + nvec;
+    double *rz = q + nvec, *pq = rz + (size_t)B * NG, *rz2 = pq + (size_t)B * NG;
+    dim3 g((unsigned)(((long)V * NG + 255) / 256), B), gd(NG, B);
+    gradproj_rhs_kernel<<<g, 256, 0, st>>>(V, h->d_node_ptr, h->d_node_src, h->d_tets, h->d_geom, e->d_mass,
+                                           h->d_diag_idx, d_u, d_g, r, z, pv);
+    gradproj_dot_kernel<<<gd, 256, 0, st>>>(V, r, z, rz);
+    h->launches += 2;
+    for (int it = 0; it < n_iter; ++it) {
+        gradproj_spmv_kernel<<<g, 256, 0, st>>>(V, h->d_row_ptr, h->d_col_idx, e->d_mass, pv, q);
+        gradproj_dot_kernel<<<gd, 256, 0, st>>>(V, pv, q, pq);
+        gradproj_update_kernel<<<g, 256, 0, st>>>(V, e->d_mass, h->d_diag_idx, rz, pq, pv, q, d_g, r, z);
+        gradproj_dot_kernel<<<gd, 256, 0, st>>>(V, r, z, rz2);
+        gradproj_dir_kernel<<<g, 256, 0, st>>>(V, rz2, rz, z, pv);
+        std::swap(rz, rz2);
+        h->launches += 5;
+    }
     GMPNP_CUDA_TRY(h, cudaGetLastError());
     return GMPNP_OK;
 }

@@ -9,7 +9,8 @@ Behaviour kept on purpose (SURVEY findings 3, 4, 6): the residual has no boundar
 built with int() truncation.  Additions: ``--utilities_dir`` / ``--out_dir`` instead of hard-coded paths,
 ``--n_steps`` (the reference always runs 1000 steps, of which all but the first few are no-ops once the residual is
 below its 1e-4 tolerance), ``--mesh_file`` override.  The P1 gradient projections (``field_values``, ``*_grad``,
-3D:884-909) and the PVD files (3D:863-880) are post-processing outside the hot path and are not written yet.
+3D:884-909) are computed on the device (``gmpnp_grad_project_3d``) and written with the reference's keys and
+component-major layout; the PVD files (3D:863-880) are not written.
 """
 from __future__ import annotations
 
@@ -21,11 +22,12 @@ from datetime import datetime
 import numpy as np
 
 
-def scale_conc_time(species="H", C=None, bulk_conc=None, tau=None, diff_coeff_eff=None, L=0.0):
-    """Dimensionless -> SI (3D:56-67, without the gradient part)."""
+def scale_conc_time(species="H", C=None, grad_c=None, bulk_conc=None, tau=None, diff_coeff_eff=None, L=0.0):
+    """Dimensionless -> SI (3D:56-67)."""
     c = C * bulk_conc[species]
     t = tau * (L ** 2) / diff_coeff_eff[species]
-    return c, t
+    grad_c_scaled = grad_c * bulk_conc[species] / L
+    return c, t, grad_c_scaled
 
 
 def solveEDL(concentration_elec=1.0, voltage_multiplier=-1.0, H2_FE=0.05, current_rough=3000.0, L=100.0e-9,
@@ -54,15 +56,21 @@ def solveEDL(concentration_elec=1.0, voltage_multiplier=-1.0, H2_FE=0.05, curren
     hist = out["history"][:, 0]                                   # [steps+1, nvert, 9]
     names = ["H", "OH", "HCO3", "CO32", "CO2", "CO", "H2", "cat", "p"]
     arrays = {n: hist[:, :, i] for i, n in enumerate(names)}
+    # project(grad(u_i), W).compute_vertex_values(): flat, component-major [all x | all y | all z] (3D:884-909)
+    G = pp.solver.grad_project(out["u"])[0].cpu().numpy()        # [nvert, 9, 3]
+    grads = {n + "_grad": np.ascontiguousarray(G[:, i, :].T).ravel() for i, n in enumerate(names[:8])}
+    field_values = -np.ascontiguousarray(G[:, 8, :].T).ravel()   # project(-grad(u_np), W), 3D:884-885
     tau_array = np.linspace(0, T, tot_num_steps)                  # 3D:912
     species = prm.species
     bulk_conc = dict(zip(species, prm.c0))
     diff_eff = dict(zip(species, prm.D))
     scaled = {}
     for n, sp in zip(names[:8], species):
-        c, t = scale_conc_time(species=sp, C=arrays[n], bulk_conc=bulk_conc, tau=tau_array, diff_coeff_eff=diff_eff, L=L)
-        scaled["c_" + n], scaled["t_" + n] = c, t
+        c, t, gs = scale_conc_time(species=sp, C=arrays[n], grad_c=grads[n + "_grad"], bulk_conc=bulk_conc,
+                                   tau=tau_array, diff_coeff_eff=diff_eff, L=L)
+        scaled["c_" + n], scaled["t_" + n], scaled[n + "_grad"] = c, t, gs
     psi = arrays["p"] * prm.thermal_voltage
+    scaled["field_values"] = field_values * prm.thermal_voltage / L                                  # 3D:1016
     metadata = {
         "concentration_elec": concentration_elec, "cation": cation, "voltage_multiplier": voltage_multiplier,
         "H2_FE": H2_FE, "current_rough": current_rough, "L": L, "R": R, "press_gas": press_gas,
@@ -79,7 +87,8 @@ def solveEDL(concentration_elec=1.0, voltage_multiplier=-1.0, H2_FE=0.05, curren
             str(electrolyte_flow_geom_multiplier) + "_rough_" + str(roughness_factor)               # 3D:389-395
         newpath = os.path.join(out_dir or os.path.join(os.getcwd(), "out"), stamp + "_experiment", identifier)
         os.makedirs(newpath, exist_ok=True)
-        np.savez(os.path.join(newpath, "arrays_unscaled.npz"), coor=mesh.x, tau=tau_array, **arrays)   # 3D:916-937
+        np.savez(os.path.join(newpath, "arrays_unscaled.npz"), coor=mesh.x, tau=tau_array, field_values=field_values,
+                 **arrays, **grads)                                                                    # 3D:916-937
         np.savez(os.path.join(newpath, "arrays_scaled.npz"), x=mesh.x * L, psi=psi, **scaled)          # 3D:1026-1056
         with open(os.path.join(newpath, "metadata.json"), "w") as f:
             f.write(json.dumps(metadata, indent=0))

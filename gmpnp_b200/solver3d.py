@@ -120,6 +120,13 @@ class Solver3D:
         check(self.lib.gmpnp_median_3d(self._h, ptr(u), int(comp), ptr(med), self._stream()), self._h)
         return med
 
+    def grad_project(self, u, n_iter: int = 40):
+        """P1 L2 projection of grad(u_i) for all 9 components: [batch, n, 9, 3] (3D:884-909)."""
+        self._chk(u)
+        g = torch.empty(self.batch, self.n, NC, 3, dtype=torch.float64, device=self.device)
+        check(self.lib.gmpnp_grad_project_3d(self._h, ptr(u), ptr(g), int(n_iter), self._stream()), self._h)
+        return g
+
     def launch_count(self) -> int:
         return int(self.lib.gmpnp_launch_count(self._h))
 

@@ -206,6 +206,11 @@ int gmpnp_coarse_invert_3d(gmpnp_handle* h, const double* d_Ac, void* stream);
 int gmpnp_coarse_restrict_3d(gmpnp_handle* h, const double* d_r, int n_rows, double* d_rc, void* stream);
 int gmpnp_coarse_prolong_3d(gmpnp_handle* h, const double* d_rc, double* d_z, int n_rows, void* stream);
 
+/* L2 projection of grad(u_i) onto P1 vectors for all 9 components (dolfin project(grad(u), W) and
+ * project(-grad(u_p), W), 3D:884-909): d_g[batch][n_vert][9][3] = M^-1 b with the consistent P1 mass matrix,
+ * Jacobi-preconditioned CG with n_iter iterations (40 reach round-off on the reference meshes).  Post-processing. */
+int gmpnp_grad_project_3d(gmpnp_handle* h, const double* d_u, double* d_g, int n_iter, void* stream);
+
 /* Median over the vertices of component `comp` for every problem (np.median, 3D:817-820):
  * d_med[batch].                                                                            */
 int gmpnp_median_3d(gmpnp_handle* h, const double* d_u, int comp, double* d_med, void* stream);

@@ -209,6 +209,26 @@ def p1_gradient_projection_1d(x, f):
 # 3D pore
 # ---------------------------------------------------------------------------------------------
 
+def p1_gradient_projection_3d(mesh_x, mesh_cells, f):
+    """dolfin ``project(grad(f), W)`` for P1 nodal fields f[nv, k] (3D/MPNP_CO2ER_pore.py:884-909): solve
+    M g = b with the consistent P1 mass matrix, b_v = sum_{t ni v} vol_t/4 grad(f)_t.  Returns g[nv, k, 3]."""
+    x = np.asarray(mesh_x, dtype=np.float64)
+    cells = np.asarray(mesh_cells, dtype=np.int64)
+    g, vol = forms.geometry(x, cells)                    # g[c, a, d] = grad lambda_a
+    nv = x.shape[0]
+    f = np.asarray(f, dtype=np.float64).reshape(nv, -1)
+    gradf = np.einsum("cad,cak->ckd", g, f[cells])      # constant per cell
+    b = np.zeros((nv, f.shape[1], 3))
+    for a in range(4):
+        np.add.at(b, cells[:, a], 0.25 * vol[:, None, None] * gradf)
+    rows = np.repeat(cells, 4, axis=1).ravel()
+    cols = np.tile(cells, (1, 4)).ravel()
+    w = np.where(np.repeat(np.arange(4), 4)[None, :] == np.tile(np.arange(4), 4)[None, :], 0.1, 0.05) * vol[:, None]
+    M = sp.coo_matrix((w.ravel(), (rows, cols)), shape=(nv, nv)).tocsc()
+    lu = spla.splu(M)
+    return lu.solve(b.reshape(nv, -1)).reshape(nv, f.shape[1], 3)
+
+
 def march_3d(mesh_x, mesh_cells, prm, bc_dofs, bc_kind, n_steps, rtol=1e-4, atol=1e-4, maxit=50, relax=0.9,
              sechenov=None):
     """The reference's 3D loop (3D:782-858): u starts at 0, u_n at (1,..,1,0); damped Newton

@@ -180,3 +180,40 @@ def test_config3_pseudo_time_steady_state(lib):
     s = pp.solver
     med = [float(s.median(out["u"], c)[0]) for c in (1, 2, 3, 7)]
     assert abs(params.sechenov_co2_scaled(prm, *med) - out["co2_entry"][0]) <= 1e-12
+
+
+def test_gradient_projection_matches_oracle(lib):
+    """project(grad(u_i), W) for all 9 components (3D:884-909): device CG on the consistent P1 mass matrix vs the
+    oracle's sparse LU, on the config-3 mesh at a random nodal state, batch of 2."""
+    from gmpnp_b200 import marking, meshio, solver3d
+    from oracle import solver as osolver
+    mesh = meshio.load_mesh("L_50_R_5")
+    dofs, kind, _ = marking.dirichlet_sets(mesh, 50e-9, 5e-9)
+    s = solver3d.Solver3D(mesh, dofs, batch=2)
+    rng = np.random.default_rng(11)
+    u = rng.normal(size=(2, mesh.x.shape[0], 9))
+    u[1] = mesh.x[:, :1] * 2.0 + mesh.x[:, 1:2] * (-3.0) + mesh.x[:, 2:3] * 0.5 + 1.0      # linear field: exact gradient
+    g = s.grad_project(torch.as_tensor(u, device=s.device).contiguous()).cpu().numpy()
+    ref = osolver.p1_gradient_projection_3d(mesh.x, mesh.cells, u[0])
+    assert np.abs(g[0] - ref).max() <= 1e-10 * np.abs(ref).max()
+    assert np.abs(g[1] - np.array([2.0, -3.0, 0.5])).max() <= 1e-10
+    s.close()
+
+
+def test_solveEDL_drop_in_writes_reference_outputs(lib, tmp_path):
+    """The 3D drop-in (3D:96-1085): files, keys and shapes of the reference, incl. the gradient projections."""
+    import json
+    from gmpnp_b200 import pore3d
+    meta = pore3d.solveEDL(L=50e-9, R=5e-9, n_steps=2, out_dir=str(tmp_path))
+    d = meta["output_dir"]
+    un = np.load(os.path.join(d, "arrays_unscaled.npz"))
+    nv = 3679
+    keys = {"H", "OH", "HCO3", "CO32", "CO2", "CO", "H2", "cat", "p", "coor", "tau", "field_values"} | \
+        {n + "_grad" for n in ("H", "OH", "HCO3", "CO32", "CO2", "CO", "H2", "cat")}
+    assert set(un.files) == keys
+    assert un["H"].shape == (3, nv) and un["coor"].shape == (nv, 3) and un["field_values"].shape == (3 * nv,)
+    assert un["cat_grad"].shape == (3 * nv,)
+    sc = np.load(os.path.join(d, "arrays_scaled.npz"))
+    assert {"x", "psi", "c_H", "t_H", "H_grad", "field_values"} <= set(sc.files)
+    md = json.load(open(os.path.join(d, "metadata.json")))
+    assert md["newton_iterations"][0] == 6                        # golden count of the first reference step
