@@ -95,6 +95,44 @@ def run_cpu(n_sample, n_voltages, cores=None, dv=0.75, xtol_path=1.0):
                 newton_iterations=int(sum(r[1] for r in res)))
 
 
+def _cpu_newton_iteration_3d(_):
+    """One damped-Newton iteration of config 3 on the CPU oracle: P1 assembly of F and J (NumPy) + sparse LU
+    (SuperLU; the reference uses MUMPS, 3D:792) + solve."""
+    os.environ["OMP_NUM_THREADS"] = "1"
+    import numpy as np
+    import scipy.sparse.linalg as spla
+    from gmpnp_b200 import marking, meshio, params
+    from oracle import solver as osolver
+    mesh = meshio.load_mesh("L_50_R_5")
+    p3 = params.params_3d(L=50e-9, R=5e-9)
+    dofs, kind, _info = marking.dirichlet_sets(mesh, 50e-9, 5e-9)
+    disc = osolver.Discretisation(mesh.x, mesh.cells, 9)
+    eq = p3.extras["eq_scaled"]
+    vals = np.array([0.0, p3.V, float(eq[0]), eq[1], eq[2]])[kind.astype(np.int64)]
+    u = np.zeros(disc.ndof)
+    un = np.tile(np.array([1.0] * 8 + [0.0]), disc.nv)
+    t = time.perf_counter()
+    b = osolver.apply_bc_residual(disc.residual(u, un, p3), u, dofs.astype(np.int64), vals)
+    A = osolver.apply_bc_matrix(disc.jacobian(u, p3), dofs.astype(np.int64))
+    dx = spla.splu(A).solve(b)
+    return time.perf_counter() - t, float(np.abs(dx).max())
+
+
+def run_cpu_3d(newton_per_solve, cores=None):
+    """Bounded CPU sample of the 3D workload: ONE Newton iteration per process on up to 8 host cores at once;
+    steady solves/s is extrapolated with the Newton count per steady solve measured on the GPU arm."""
+    import multiprocessing as mp
+    cores = max(1, min(cores or (os.cpu_count() or 1), 8))
+    t = time.perf_counter()
+    with mp.get_context("spawn").Pool(cores) as pool:
+        res = pool.map(_cpu_newton_iteration_3d, range(cores), chunksize=1)
+    wall = time.perf_counter() - t
+    per_it = sum(r[0] for r in res) / len(res)
+    return dict(value=cores / (per_it * newton_per_solve), unit="steady solves/s (extrapolated)", cores=cores, kind="port",
+                sample=f"one damped-Newton iteration of config 3 (NumPy assembly + SuperLU of 33111 DOFs) per core on {cores} "
+                       f"cores at once: {per_it:.1f} s per iteration, wall {wall:.1f} s; x {newton_per_solve} iterations per steady solve")
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -362,6 +400,8 @@ def main():
             "clocks": sampler.summary(),
         }
         if pore3d is not None:
+            if world == 1 and not args.no_cpu_baseline:
+                pore3d["cpu_baseline"] = run_cpu_3d(pore3d["newton_iterations_per_problem"])
             line["pore3d"] = pore3d
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = run_cpu(args.cpu_sample, args.voltages, dv=args.dv, xtol_path=args.xtol_path)
