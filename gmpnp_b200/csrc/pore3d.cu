@@ -351,31 +351,30 @@ assemble_bsr_kernel(int n_blocks, int n_vert, int n_tet, const int* __restrict__
     const double* up = u + (long)prob * n_vert * NC;
     const double* mo = mom + (long)prob * n_tet * NMOM;
     double* Jp = J + (long)prob * n_blocks * 81;
-    // role of this lane in the accumulation phase: which two moments of a tet record it reads
-    const int role = lane >> 3, li = lane & 7;           // 0: Q_i, 1: Pc_i, 2: T_s, 3: idle
-    const int idx1_base = (role == 0) ? M_UD2 + 4 * li : M_SU + li;
-    const int idx1_bmul = (role == 0) ? 1 : 0;
-    const int idx2 = M_IUD + li;
+    // accumulation phase: the warp takes FOUR contributions (tet, a, b) of the block per pass, one per 8-lane group;
+    // lane li of a group accumulates the three moment sums of species li (Q_li, Pc_li, T_li) and, redundantly within
+    // the group, the five scalar sums; the four groups are combined with two xor-shuffle steps per block.
+    const int cs = lane >> 3, li = lane & 7;
     double* sw = sums[w];
     for (int blk = blockIdx.x * ASM_WARPS + w; blk < n_blocks; blk += gridDim.x * ASM_WARPS) {
         const int va = blk_row[blk], vb = col_idx[blk];
-        double acc = 0.0, dsum = 0.0, zsum = 0.0, ppsum = 0.0, sMab = 0.0, scT = 0.0;
+        double accQ = 0.0, accP = 0.0, accT = 0.0, dsum = 0.0, zsum = 0.0, ppsum = 0.0, sMab = 0.0, scT = 0.0;
         const int s0 = blk_ptr[blk], s1 = blk_ptr[blk + 1];
-        // gather list of the block: coalesced 32 entries at a time, then broadcast entry by entry, so that the
-        // moment loads of several contributions are in flight together
         for (int sb = s0; sb < s1; sb += 32) {
             const int cnt = min(32, s1 - sb);
             int my_src = 0;
             double2 my_kv = make_double2(0.0, 0.0);
             if (lane < cnt) { my_src = blk_src[sb + lane]; my_kv = blk_geo[sb + lane]; }
-#pragma unroll 4
-            for (int q = 0; q < cnt; ++q) {
-                const int src = __shfl_sync(0xffffffffu, my_src, q);
-                const double kab = __shfl_sync(0xffffffffu, my_kv.x, q), vol = __shfl_sync(0xffffffffu, my_kv.y, q);
-                const int t = src >> 4, a = (src >> 2) & 3, b = src & 3;
+            for (int q0 = 0; q0 < cnt; q0 += 4) {
+                const int q = q0 + cs;                              // this group's contribution (may be past the end)
+                const int src = __shfl_sync(0xffffffffu, my_src, q & 31);
+                double kab = __shfl_sync(0xffffffffu, my_kv.x, q & 31), vol = __shfl_sync(0xffffffffu, my_kv.y, q & 31);
+                const bool live = q < cnt;
+                if (!live) { kab = 0.0; vol = 0.0; }                // a dead slot contributes exact zeros
+                const int t = live ? (src >> 4) : 0, a = (src >> 2) & 3, b = src & 3;
                 const double* m = mo + (long)t * NMOM;
-                const double Ga = m[M_GA + a], gpa = m[M_GPA + a], mDb = m[M_MD + b], eps = m[M_EPS];
-                const double m1 = m[idx1_base + idx1_bmul * b], m2 = m[idx2];
+                const double Ga = live ? m[M_GA + a] : 0.0, gpa = m[M_GPA + a], mDb = m[M_MD + b], eps = m[M_EPS];
+                const double mq = m[M_UD2 + 4 * li + b], mi = m[M_IUD + li], ms = m[M_SU + li];
                 const double Kab = kab * vol, mb = 0.25 * vol;
                 const double Mab = vol * ((a == b) ? 0.1 : 0.05);
                 const double cT = vol * ((a == b) ? (1.0 / 60.0) : (1.0 / 120.0));
@@ -384,14 +383,23 @@ assemble_bsr_kernel(int n_blocks, int n_vert, int n_tet, const int* __restrict__
                 ppsum -= Kab * eps;
                 sMab += Mab;
                 scT += cT;
-                const double w1 = (role == 0) ? Ga : ((role == 1) ? kab * mb : cT);
-                const double w2 = (role == 0) ? kab : 0.0;
-                acc += w1 * m1 + w2 * m2;
+                accQ += Ga * mq + kab * mi;
+                accP += (kab * mb) * ms;
+                accT += cT * ms;
             }
         }
-        if (role == 2) acc += (up[(long)va * NC + li] + up[(long)vb * NC + li]) * scT;    // nodal part of T_s
+        // combine the four groups (every lane ends up with the block totals)
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+            accQ += __shfl_xor_sync(0xffffffffu, accQ, o); accP += __shfl_xor_sync(0xffffffffu, accP, o);
+            accT += __shfl_xor_sync(0xffffffffu, accT, o); dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+            zsum += __shfl_xor_sync(0xffffffffu, zsum, o); ppsum += __shfl_xor_sync(0xffffffffu, ppsum, o);
+            sMab += __shfl_xor_sync(0xffffffffu, sMab, o); scT += __shfl_xor_sync(0xffffffffu, scT, o);
+        }
+        accT += (up[(long)va * NC + li] + up[(long)vb * NC + li]) * scT;      // nodal part of T_s
         __syncwarp();                                    // previous block's expansion reads are done
-        sw[lane] = (lane == 24) ? sMab : acc;
+        if (cs == 0) { sw[li] = accQ; sw[8 + li] = accP; sw[16 + li] = accT; }
+        if (lane == 24) sw[24] = sMab;
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
