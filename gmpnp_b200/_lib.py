@@ -75,6 +75,7 @@ SIGNATURES = {
     "gmpnp_vec_lincomb": (_i, [_vp, _vp, C.c_longlong, _i, _vp, _d, _vp, _vp, C.c_longlong, _vp]),
     "gmpnp_bjacobi_setup_3d": (_i, [_vp, _vp, _vp]),
     "gmpnp_bjacobi_apply_3d": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "gmpnp_set_facet_terms_3d": (_i, [_vp, _pd, _pi, _pd, _i, _pd, _pd, _i]),
     "gmpnp_grad_project_3d": (_i, [_vp, _vp, _vp, _i, _vp]),
     "gmpnp_set_aggregates_3d": (_i, [_vp, _pi]),
     "gmpnp_coarse_accumulate_3d": (_i, [_vp, _vp, _i, _vp, _vp]),

@@ -233,10 +233,17 @@ tet_moments_kernel(int n_tet, int n_vert, const int* __restrict__ tets, const do
 // ---------------------------------------------------------------------------------------
 // Kernel B: residual gather per (problem, vertex) + Dirichlet rows
 // ---------------------------------------------------------------------------------------
+// Facet terms of the INTENDED boundary physics (3D:474-499, 560-750; dead code as executed -- SURVEY finding 3;
+// live in 3D/rxn_diff_CO2ER_pore.py:480-511): `J_wall_i v_i ds(2)` = J_wall_i * (lumped wall area of the vertex) and the
+// Robin exit term `k_i (u_i - 1) v_i ds(3)` = k_i sum_w E_vw (u_w,i - 1) with the exit-facet mass matrix E on the
+// BSR pattern.  wall_w == nullptr: as executed (no facet terms).
 __global__ void residual_gather_kernel(int n_vert, int n_tet, int n_dir, const int* __restrict__ node_ptr,
                                        const int* __restrict__ node_src, const int* __restrict__ dir_flag,
                                        const double* __restrict__ dir_val, const double* __restrict__ Fe,
-                                       const double* __restrict__ u, double* __restrict__ F) {
+                                       const double* __restrict__ u, double* __restrict__ F,
+                                       const double* __restrict__ wall_w, const double* __restrict__ exit_m,
+                                       const int* __restrict__ exit_flag, const double* __restrict__ bc,
+                                       const int* __restrict__ row_ptr, const int* __restrict__ col_idx) {
     const int prob = blockIdx.y;
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)n_vert * NC) return;
@@ -251,6 +258,16 @@ __global__ void residual_gather_kernel(int n_vert, int n_tet, int n_dir, const i
         for (int s = node_ptr[v]; s < node_ptr[v + 1]; ++s) {
             const int src = node_src[s];
             f += fe[(long)(src >> 2) * 36 + (src & 3) * NC + i];
+        }
+        if (wall_w != nullptr && i < NS) {
+            const double* bcp = bc + (long)prob * 16;
+            f += bcp[i] * wall_w[v];
+            if (exit_flag[v]) {
+                const double* up = u + (long)prob * n_vert * NC;
+                double e = 0.0;
+                for (int s = row_ptr[v]; s < row_ptr[v + 1]; ++s) e += exit_m[s] * (up[(long)col_idx[s] * NC + i] - 1.0);
+                f += bcp[8 + i] * e;
+            }
         }
     }
     F[(long)prob * n_vert * NC + idx] = f;
@@ -327,12 +344,13 @@ assemble_bsr_kernel(int n_blocks, int n_vert, int n_tet, const int* __restrict__
                     const int* __restrict__ blk_src, const double2* __restrict__ blk_geo,
                     const int* __restrict__ blk_row, const int* __restrict__ col_idx,
                     const int* __restrict__ dir_flag, const double* __restrict__ params, const double* __restrict__ u,
-                    const double* __restrict__ mom, double* __restrict__ J) {
+                    const double* __restrict__ mom, double* __restrict__ J, const double* __restrict__ exit_m,
+                    const double* __restrict__ bc) {
     __shared__ double P[GMPNP_NPAR];
     __shared__ double sums[ASM_WARPS][32];   // per warp: Q[0..7] | Pc[8..15] | Tt[16..23] | sMab [24]
     // per-entry constants of the 81 block entries, shared by the CTA (kept out of registers: the kernel is bound by
     // the latency of its dependent gather loads, so occupancy matters more than a few shared-memory reads)
-    __shared__ double Ed[9][96];             // cQ, cD, cZ (= cDz + cE), cP, cM, c8, rc0, rc1, rc2
+    __shared__ double Ed[10][96];            // cQ, cD, cZ (= cDz + cE), cP, cM, c8, rc0, rc1, rc2, cX (exit Robin k_i)
     __shared__ int Ei[5][96];                // i7, i, rs0, rs1, rs2
     const int prob = blockIdx.y;
     for (int i = threadIdx.x; i < GMPNP_NPAR; i += blockDim.x) P[i] = params[(long)prob * GMPNP_NPAR + i];
@@ -344,6 +362,7 @@ assemble_bsr_kernel(int n_blocks, int n_vert, int n_tet, const int* __restrict__
         const int e = threadIdx.x;
         Ed[0][e] = E.cQ; Ed[1][e] = E.cD; Ed[2][e] = E.cDz + E.cE; Ed[3][e] = E.cP; Ed[4][e] = E.cM; Ed[5][e] = E.c8;
         Ed[6][e] = E.rc[0]; Ed[7][e] = E.rc[1]; Ed[8][e] = E.rc[2];
+        Ed[9][e] = (exit_m != nullptr && E.cD != 0.0) ? bc[(long)prob * 16 + 8 + E.i] : 0.0;
         Ei[0][e] = E.i7; Ei[1][e] = E.i; Ei[2][e] = E.rs[0]; Ei[3][e] = E.rs[1]; Ei[4][e] = E.rs[2];
     }
     __syncthreads();
@@ -409,6 +428,7 @@ assemble_bsr_kernel(int n_blocks, int n_vert, int n_tet, const int* __restrict__
             double val = Ed[0][e] * sw[i7] + Ed[3][e] * sw[8 + i7];
             val += Ed[1][e] * dsum + Ed[2][e] * zsum + Ed[4][e] * sMab + Ed[5][e] * ppsum;
             val += Ed[6][e] * sw[16 + Ei[2][e]] + Ed[7][e] * sw[16 + Ei[3][e]] + Ed[8][e] * sw[16 + Ei[4][e]];
+            if (exit_m != nullptr) val += Ed[9][e] * exit_m[blk];
             // Dirichlet rows: identity
             if (dir_flag[(long)va * NC + ei] >= 0) val = (va == vb && e == ei * 10) ? 1.0 : 0.0;
             Jp[(long)blk * 81 + e] = val;
@@ -1029,6 +1049,11 @@ struct Host3D {   // device arrays that only the 3D path needs and common.cuh do
     double* d_Aci = nullptr;
     double* d_yc = nullptr;
     double* d_mass = nullptr;       // scalar P1 mass matrix on the BSR pattern [nb] (gradient projection)
+    double* d_wall_w = nullptr;     // intended BCs: lumped wall-facet area per vertex [V]
+    double* d_exit_m = nullptr;     // intended BCs: exit-facet mass matrix on the BSR pattern [nb]
+    int* d_exit_flag = nullptr;     // [V] vertex lies on an exit facet
+    double* d_bc = nullptr;         // [batch][16]: J_wall[8] | k_exit[8]
+    bool facet_terms = false;
     double* d_gp = nullptr;         // gradient-projection work vectors [4][batch][V][27] + scalars
     double* d_partial = nullptr;    // first-stage partial sums of the partitioned-mode reductions
     size_t partial_doubles = 0;
@@ -1046,7 +1071,7 @@ void pore3d_free_ext(gmpnp_handle* h) {
     auto it = g_ext.find(h);
     if (it == g_ext.end()) return;
     Host3D* e = it->second;
-    void* bufs[] = {e->d_mass, e->d_gp, e->d_partial, e->d_blk_row, e->d_blk_geo, e->d_agg, e->d_agg_ptr, e->d_agg_nodes, e->d_Aci, e->d_yc, e->d_V, e->d_w, e->d_z,
+    void* bufs[] = {e->d_wall_w, e->d_exit_m, e->d_exit_flag, e->d_bc, e->d_mass, e->d_gp, e->d_partial, e->d_blk_row, e->d_blk_geo, e->d_agg, e->d_agg_ptr, e->d_agg_nodes, e->d_Aci, e->d_yc, e->d_V, e->d_w, e->d_z,
                     e->d_dx, e->d_d1, e->d_d2, e->d_nrm, e->d_H, e->d_cs, e->d_sn, e->d_g, e->d_tol, e->d_coef,
                     e->d_beta, e->d_dxmax, e->d_umax, e->d_jdone, e->d_active};
     for (void* b : bufs) if (b) cudaFree(b);
@@ -1253,7 +1278,9 @@ static int launch_assemble(gmpnp_handle* h, const double* d_u, const double* d_u
     if (d_F) {
         dim3 gB(((long)V * NC + 255) / 256, B);
         residual_gather_kernel<<<gB, 256, 0, st>>>(V, T, h->n_dir, h->d_node_ptr, h->d_node_src, h->d_dir_flag,
-                                                   h->d_dir_val, h->d_Fe, d_u, d_F);
+                                                   h->d_dir_val, h->d_Fe, d_u, d_F,
+                                                   ext(h)->facet_terms ? ext(h)->d_wall_w : nullptr, ext(h)->d_exit_m,
+                                                   ext(h)->d_exit_flag, ext(h)->d_bc, h->d_row_ptr, h->d_col_idx);
         h->launches++;
     }
     if (d_J) {
@@ -1261,7 +1288,8 @@ static int launch_assemble(gmpnp_handle* h, const double* d_u, const double* d_u
         dim3 gC(gx, B);
         assemble_bsr_kernel<<<gC, ASM_WARPS * 32, 0, st>>>(h->n_blocks, V, T, h->d_blk_ptr, h->d_blk_src,
                                                            ext(h)->d_blk_geo, ext(h)->d_blk_row, h->d_col_idx,
-                                                           h->d_dir_flag, h->d_params, d_u, h->d_mom, d_J);
+                                                           h->d_dir_flag, h->d_params, d_u, h->d_mom, d_J,
+                                                           ext(h)->facet_terms ? ext(h)->d_exit_m : nullptr, ext(h)->d_bc);
         h->launches++;
     }
     GMPNP_CUDA_TRY(h, cudaGetLastError());
@@ -1561,6 +1589,48 @@ int gmpnp_bjacobi_apply_3d(gmpnp_handle* h, const double* d_r, double* d_z, int 
     bjacobi_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n_rows, h->d_Dinv, d_r, d_z);
     h->launches++;
     GMPNP_CUDA_TRY(h, cudaGetLastError());
+    return GMPNP_OK;
+}
+
+int gmpnp_set_facet_terms_3d(gmpnp_handle* h, const double* h_wall_w, const int* h_exit_facets,
+                             const double* h_exit_area, int n_exit, const double* h_jwall, const double* h_kexit, int batch) {
+    if (!h || h->dim != 3) return GMPNP_ERR_ARG;
+    Host3D* e = ext(h);
+    if (!h_wall_w) { e->facet_terms = false; return GMPNP_OK; }          // back to the as-executed form
+    if (n_exit < 0 || (n_exit > 0 && (!h_exit_facets || !h_exit_area)) || !h_jwall || !h_kexit || batch != h->batch)
+        return GMPNP_ERR_ARG;
+    GMPNP_CUDA_TRY(h, cudaSetDevice(h->device));
+    const int V = h->n_nodes, nb = h->n_blocks;
+    std::vector<double> em(nb, 0.0);
+    std::vector<int> flag(V, 0);
+    for (int f = 0; f < n_exit; ++f) {
+        for (int a = 0; a < 3; ++a) {
+            const int va = h_exit_facets[3 * f + a];
+            if (va < 0 || va >= V) return GMPNP_ERR_ARG;
+            flag[va] = 1;
+            for (int b = 0; b < 3; ++b) {
+                const int vb = h_exit_facets[3 * f + b];
+                const int* b0 = h->h_col_idx.data() + h->h_row_ptr[va];
+                const int* b1 = h->h_col_idx.data() + h->h_row_ptr[va + 1];
+                const int* it = std::lower_bound(b0, b1, vb);
+                if (it == b1 || *it != vb) return GMPNP_ERR_ARG;        // a facet edge is always a tet edge
+                em[it - h->h_col_idx.data()] += h_exit_area[f] * ((a == b) ? (1.0 / 6.0) : (1.0 / 12.0));
+            }
+        }
+    }
+    std::vector<double> bc((size_t)batch * 16);
+    for (int p = 0; p < batch; ++p)
+        for (int i = 0; i < 8; ++i) { bc[(size_t)p * 16 + i] = h_jwall[p * 8 + i]; bc[(size_t)p * 16 + 8 + i] = h_kexit[p * 8 + i]; }
+    void* old[] = {e->d_wall_w, e->d_exit_m, e->d_exit_flag, e->d_bc};
+    for (void* b : old) if (b) cudaFree(b);
+    e->d_wall_w = nullptr; e->d_exit_m = nullptr; e->d_exit_flag = nullptr; e->d_bc = nullptr;
+    std::vector<double> ww(h_wall_w, h_wall_w + V);
+    int rc;
+    if ((rc = dev_upload(h, &e->d_wall_w, ww))) return rc;
+    if ((rc = dev_upload(h, &e->d_exit_m, em))) return rc;
+    if ((rc = dev_upload(h, &e->d_exit_flag, flag))) return rc;
+    if ((rc = dev_upload(h, &e->d_bc, bc))) return rc;
+    e->facet_terms = true;
     return GMPNP_OK;
 }
 

@@ -85,3 +85,20 @@ def dirichlet_values(kind: np.ndarray, V: float, co2: float, co: float, h2: floa
     """Values for the DOF list of :func:`dirichlet_sets`."""
     table = np.array([0.0, V, co2, co, h2])
     return table[kind.astype(np.int64)]
+
+
+def facet_terms(mesh: meshio.Mesh, L: float, R: float):
+    """Geometry of the INTENDED boundary integrals (3D:474-499; `ds(2)` wall, `ds(3)` pore exit; dolfin's ``ds``
+    runs over EXTERIOR facets only, so interior facets that carry marker 2 do not contribute).
+
+    Returns (wall_w[nv] = sum over the exterior wall facets of a vertex of area/3  -- the P1 integral of a
+    constant flux --, exit_facets[nf, 3], exit_area[nf])."""
+    facets, cnt, marker = mark_facets(mesh, R / L, wall_tolerance(L, R))
+    ext = cnt == 1
+    X = mesh.x[facets]
+    area = 0.5 * np.linalg.norm(np.cross(X[:, 1] - X[:, 0], X[:, 2] - X[:, 0]), axis=1)
+    wall = ext & (marker == 2)
+    wall_w = np.zeros(mesh.x.shape[0])
+    np.add.at(wall_w, facets[wall].ravel(), np.repeat(area[wall] / 3.0, 3))
+    ex = ext & (marker == 3)
+    return wall_w, np.ascontiguousarray(facets[ex], dtype=np.int32), np.ascontiguousarray(area[ex])

@@ -34,7 +34,7 @@ def solveEDL(concentration_elec=1.0, voltage_multiplier=-1.0, H2_FE=0.05, curren
              cation="K", R=5.0e-9, press_gas=1.0, pore_geom_multiplier=1.0, porosity_eff=0.5, tortuosity_eff=1.5,
              constrictivity_eff=0.9, params_file="parameters_pore", y_CO2=0.95, electrolyte_flow_geom_multiplier=1.0,
              roughness_factor=150.0, *, utilities_dir=None, out_dir=None, n_steps=None, mesh_file=None, device=0,
-             write=True):
+             write=True, intended_bcs=False):
     from . import meshio, params as _params, solver3d
 
     stamp = datetime.now().strftime("%y-%m-%d-%H-%M-%S")
@@ -50,7 +50,7 @@ def solveEDL(concentration_elec=1.0, voltage_multiplier=-1.0, H2_FE=0.05, curren
     tot_num_steps = int(total_sim_time / time_step) if n_steps is None else int(n_steps)
     T = total_sim_time / prm.time_constant
 
-    pp = solver3d.PoreProblem(mesh, L, R, [prm], device=device)
+    pp = solver3d.PoreProblem(mesh, L, R, [prm], device=device, intended_bcs=intended_bcs)
     out = pp.march(tot_num_steps, history=True)
     end_time = datetime.now().strftime("%y-%m-%d-%H-%M-%S")
     hist = out["history"][:, 0]                                   # [steps+1, nvert, 9]
@@ -121,6 +121,9 @@ def build_parser():
     p.add_argument("--n_steps", default=None, type=int)
     p.add_argument("--mesh_file", default=None)
     p.add_argument("--device", default=0, type=int)
+    p.add_argument("--intended_bcs", action="store_true",
+                   help="add the wall-flux / pore-exit Robin boundary integrals that the reference writes but Python "
+                        "discards (3D:474-499, 560-750); default: as executed")
     return p
 
 

@@ -81,6 +81,22 @@ class Solver3D:
         check(self.lib.gmpnp_set_dirichlet_3d(self._h, vals.ctypes.data_as(C.POINTER(C.c_double)), self.batch),
               self._h)
 
+    def set_facet_terms(self, wall_w=None, exit_facets=None, exit_area=None, jwall=None, kexit=None):
+        """Switch the intended boundary integrals on (3D:474-499; arrays from ``marking.facet_terms`` and the
+        per-problem ``J_wall`` / ``k_exit`` of ``params_3d``) or, with no arguments, back off (as executed)."""
+        if wall_w is None:
+            check(self.lib.gmpnp_set_facet_terms_3d(self._h, None, None, None, 0, None, None, self.batch), self._h)
+            return
+        ww = np.ascontiguousarray(wall_w, dtype=np.float64)
+        ef = np.ascontiguousarray(exit_facets, dtype=np.int32).reshape(-1, 3)
+        ea = np.ascontiguousarray(exit_area, dtype=np.float64)
+        jw = np.ascontiguousarray(jwall, dtype=np.float64).reshape(self.batch, 8)
+        ke = np.ascontiguousarray(kexit, dtype=np.float64).reshape(self.batch, 8)
+        pd, pi = C.POINTER(C.c_double), C.POINTER(C.c_int)
+        check(self.lib.gmpnp_set_facet_terms_3d(self._h, ww.ctypes.data_as(pd), ef.ctypes.data_as(pi),
+                                                ea.ctypes.data_as(pd), len(ea), jw.ctypes.data_as(pd),
+                                                ke.ctypes.data_as(pd), self.batch), self._h)
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -135,13 +151,20 @@ class PoreProblem:
     """One pore geometry + a batch of parameter points: Dirichlet sets per the reference's marking
     (3D:335-379, 460-467) and the drivers built on :class:`Solver3D`."""
 
-    def __init__(self, mesh, L: float, R: float, plist, device: int = 0):
+    def __init__(self, mesh, L: float, R: float, plist, device: int = 0, intended_bcs: bool = False):
+        """``intended_bcs``: add the wall-flux and pore-exit Robin integrals the reference's author wrote but Python
+        discards (3D:474-499, 560-750; SURVEY finding 3 / App. H).  Default False = parity with the script as executed."""
         self.mesh, self.L, self.R = mesh, L, R
         self.plist = list(plist)
         self.dofs, self.kind, self.info = marking.dirichlet_sets(mesh, L, R)
         self.solver = Solver3D(mesh, self.dofs, batch=len(self.plist), device=device)
         self.solver.set_params(self.plist)
         self.device = self.solver.device
+        self.intended_bcs = bool(intended_bcs)
+        if self.intended_bcs:
+            ww, ef, ea = marking.facet_terms(mesh, L, R)
+            self.solver.set_facet_terms(ww, ef, ea, np.stack([p.extras["J_wall"] for p in self.plist]),
+                                        np.stack([p.extras["k_exit"] for p in self.plist]))
 
     def dirichlet_values(self, co2_scaled, V=None):
         vals = []

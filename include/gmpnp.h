@@ -206,6 +206,16 @@ int gmpnp_coarse_invert_3d(gmpnp_handle* h, const double* d_Ac, void* stream);
 int gmpnp_coarse_restrict_3d(gmpnp_handle* h, const double* d_r, int n_rows, double* d_rc, void* stream);
 int gmpnp_coarse_prolong_3d(gmpnp_handle* h, const double* d_rc, double* d_z, int n_rows, void* stream);
 
+/* The INTENDED boundary physics of the 3D script (3D/MPNP_CO2ER_pore.py:474-499 and the `+ J_... * ds(k)` lines
+ * 560-750, which Python discards as executed -- SURVEY finding 3; the same terms are live in
+ * 3D/rxn_diff_CO2ER_pore.py:480-511): constant wall fluxes `J_wall_i v_i ds(2)` and Robin exit terms
+ * `k_exit_i (u_i - 1) v_i ds(3)`.  h_wall_w[n_vert] = sum over the exterior wall facets of a vertex of area/3;
+ * h_exit_facets[n_exit][3] / h_exit_area[n_exit] = the exterior exit facets; h_jwall, h_kexit [batch][8].
+ * h_wall_w == NULL switches back to the as-executed form (the default).                                        */
+int gmpnp_set_facet_terms_3d(gmpnp_handle* h, const double* h_wall_w, const int* h_exit_facets,
+                             const double* h_exit_area, int n_exit, const double* h_jwall, const double* h_kexit,
+                             int batch);
+
 /* L2 projection of grad(u_i) onto P1 vectors for all 9 components (dolfin project(grad(u), W) and
  * project(-grad(u_p), W), 3D:884-909): d_g[batch][n_vert][9][3] = M^-1 b with the consistent P1 mass matrix,
  * Jacobi-preconditioned CG with n_iter iterations (40 reach round-off on the reference meshes).  Post-processing. */

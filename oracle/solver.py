@@ -22,7 +22,7 @@ from . import forms, quadrature
 class Discretisation:
     """Mesh + fixed sparsity data for one (mesh, ncomp) pair."""
 
-    def __init__(self, x, cells, ncomp, jac_rule: int = 0):
+    def __init__(self, x, cells, ncomp, jac_rule: int = 0, facet_terms=None):
         """``jac_rule`` 0: FFC's rule pair (Jacobian integrated with the degree-4 rule, SURVEY App. B -- the
         reference's iteration path); 1: the Jacobian uses the residual's rule (exact derivative of the discrete
         residual: quadratic convergence, same converged solution)."""
@@ -38,6 +38,17 @@ class Discretisation:
         self.ruleF, self.ruleJ = quadrature.rules_for_dim(self.dim)
         if jac_rule == 1:
             self.ruleJ = self.ruleF
+        # intended 3D boundary integrals (3D/MPNP_CO2ER_pore.py:474-499, dead code as executed; live in
+        # 3D/rxn_diff_CO2ER_pore.py:480-511): facet_terms = (wall_w[nv], exit_facets[nf,3], exit_area[nf], J_wall[8], k_exit[8])
+        self.facet = None
+        if facet_terms is not None:
+            wall_w, ef, ea, jwall, kexit = facet_terms
+            ef = np.asarray(ef, dtype=np.int64).reshape(-1, 3)
+            r = np.repeat(ef, 3, axis=1).ravel()
+            c = np.tile(ef, (1, 3)).ravel()
+            w = np.where(np.repeat(np.arange(3), 3)[None, :] == np.tile(np.arange(3), 3)[None, :], 1.0 / 6.0, 1.0 / 12.0)
+            E = sp.coo_matrix(((w * np.asarray(ea)[:, None]).ravel(), (r, c)), shape=(self.nv, self.nv)).tocsr()
+            self.facet = (np.asarray(wall_w, float), E, np.asarray(jwall, float), np.asarray(kexit, float))
         dofs = (self.cells[:, :, None] * ncomp + np.arange(ncomp)[None, None, :])   # [c, a, i]
         self.cell_dofs = dofs
         nloc = dofs.shape[1] * ncomp
@@ -56,11 +67,25 @@ class Discretisation:
             ns = self.ncomp - 1
             for node in (0, self.nv - 1):
                 F[node * self.ncomp: node * self.ncomp + ns] += point_flux[:ns]
+        if self.facet is not None:
+            wall_w, E, jwall, kexit = self.facet
+            ns = self.ncomp - 1
+            U = u.reshape(self.nv, self.ncomp)
+            Ff = F.reshape(self.nv, self.ncomp)
+            Ff[:, :ns] += wall_w[:, None] * jwall[None, :ns] + (E @ (U[:, :ns] - 1.0)) * kexit[None, :ns]
         return F
 
     def jacobian(self, u, prm):
         Je = forms.element_jacobian(self.gather(u), self.g, self.vol, prm, self.ruleJ)
         A = sp.coo_matrix((Je.ravel(), (self.rows, self.cols)), shape=(self.ndof, self.ndof))
+        if self.facet is not None:
+            _, E, _, kexit = self.facet
+            Ec = E.tocoo()
+            ns = self.ncomp - 1
+            rr = (Ec.row[:, None] * self.ncomp + np.arange(ns)[None, :]).ravel()
+            cc = (Ec.col[:, None] * self.ncomp + np.arange(ns)[None, :]).ravel()
+            vv = (Ec.data[:, None] * kexit[None, :ns]).ravel()
+            A = A + sp.coo_matrix((vv, (rr, cc)), shape=(self.ndof, self.ndof))
         return A.tocsr()
 
 
@@ -230,13 +255,13 @@ def p1_gradient_projection_3d(mesh_x, mesh_cells, f):
 
 
 def march_3d(mesh_x, mesh_cells, prm, bc_dofs, bc_kind, n_steps, rtol=1e-4, atol=1e-4, maxit=50, relax=0.9,
-             sechenov=None):
+             sechenov=None, facet_terms=None):
     """The reference's 3D loop (3D:782-858): u starts at 0, u_n at (1,..,1,0); damped Newton
     (relaxation 0.9, 3D:796); after every step the CO2 entry value is re-evaluated from the MEDIANS of
     the nodal OH/HCO3/CO32/cation values (3D:817-838) via ``sechenov(med_OH, med_HCO3, med_CO32, med_cat)``.
     Returns (history [n_steps+1, nv, 9], Newton counts, list of CO2 entry values used)."""
     ncomp = prm.ns + 1
-    disc = Discretisation(mesh_x, mesh_cells, ncomp)
+    disc = Discretisation(mesh_x, mesh_cells, ncomp, facet_terms=facet_terms)
     nv = disc.nv
     eq = prm.extras["eq_scaled"]
     co2 = float(eq[0])

@@ -217,3 +217,34 @@ def test_solveEDL_drop_in_writes_reference_outputs(lib, tmp_path):
     assert {"x", "psi", "c_H", "t_H", "H_grad", "field_values"} <= set(sc.files)
     md = json.load(open(os.path.join(d, "metadata.json")))
     assert md["newton_iterations"][0] == 6                        # golden count of the first reference step
+
+
+def test_intended_boundary_integrals_match_oracle(lib):
+    """`--intended_bcs` (3D:474-499; SURVEY finding 3 / App. H): wall fluxes J_i v_i ds(2) and Robin exit terms
+    k_i (u_i - 1) v_i ds(3).  Residual and Jacobian action vs the oracle at a random state, the first reference
+    time step vs the oracle's, and switching the terms off again restores the as-executed residual."""
+    from gmpnp_b200 import meshio, params, solver3d
+    g = np.load(os.path.join(GOLDEN, "intended_3d_L50R5.npz"))
+    mesh = meshio.load_mesh("L_50_R_5")
+    prm = params.params_3d(L=50e-9, R=5e-9)
+    pp = solver3d.PoreProblem(mesh, 50e-9, 5e-9, [prm], intended_bcs=True)
+    s = pp.solver
+    s.set_dirichlet(pp.dirichlet_values([float(prm.extras["eq_scaled"][0])]))
+    dev = s.device
+    u = torch.as_tensor(g["u"][None], device=dev).contiguous()
+    un = solver3d.bulk_state(1, s.n, dev)
+    F, J = s.assemble(u, un)
+    Fr = g["F"]
+    assert np.abs(F[0].cpu().numpy() - Fr).max() <= 1e-11 * np.abs(Fr).max()
+    Jx = s.spmv(J, torch.as_tensor(g["x"][None], device=dev).contiguous())[0].cpu().numpy()
+    assert np.abs(Jx - g["Jx"]).max() <= 1e-11 * np.abs(g["Jx"]).max()
+    out = pp.march(1, history=True)
+    assert out["iters"][:, 0].tolist() == g["its"].tolist()
+    for c in range(9):
+        assert rel_l2(out["history"][1][0][:, c], g["step1"][:, c]) < 1e-7, c
+    # the terms really are in: the as-executed residual differs on the wall / exit vertices
+    s.set_facet_terms()
+    F0, _ = s.assemble(u, un, want_J=False)
+    d = np.abs(F0[0].cpu().numpy() - Fr)
+    assert d.max() > 1e-3 and d[:, 8].max() <= 1e-11 * np.abs(Fr).max()     # species rows change, the Poisson row does not
+    pp.solver.close()
