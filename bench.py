@@ -334,9 +334,7 @@ def main():
         for g, hp, hv in zip(sw.groups, h_params, h_paths):
             g["solver"].set_params(hp.numpy())                  # H2D of the parameter records
             g["d_path"].copy_(hv, non_blocking=True)            # H2D of the continuation paths
-        o = sw.solve_resident()
-        for g, ho in zip(sw.groups, h_out):
-            ho.copy_(g["u"], non_blocking=True)                 # D2H of every solution profile
+        o = sw.solve_resident(host_out=h_out)                   # D2H of every solution profile, per mesh stream
         torch.cuda.synchronize()
         return o
 

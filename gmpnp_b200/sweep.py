@@ -141,13 +141,15 @@ class Sweep1D:
             g["d_path"] = torch.as_tensor(g["path"], device=self.device)
             g["u"] = torch.empty(g["solver"].batch, g["solver"].n, NC, dtype=torch.float64, device=self.device)
 
-    def solve_resident(self):
+    def solve_resident(self, host_out=None):
         """One pass of the hot path over the whole batch: every point from the bulk state to its
-        converged steady solution.  One launch per mesh, on concurrent streams."""
+        converged steady solution.  One launch per mesh, on concurrent streams.  ``host_out`` (one pinned host
+        tensor per mesh group, shaped like the group's ``u``): the solution profiles are copied back on the
+        group's own stream as soon as its launch finishes, overlapping the other meshes' compute."""
         opts = self.opts()
         cur = torch.cuda.current_stream(self.device)
         outs = []
-        for g in self.groups:
+        for k, g in enumerate(self.groups):
             st = g["stream"]
             st.wait_stream(cur)
             with torch.cuda.stream(st):
@@ -155,6 +157,8 @@ class Sweep1D:
                 u.fill_(1.0)
                 u[:, :, NC - 1] = 0.0
                 outs.append(g["solver"].steady(u, g["d_path"], opts))
+                if host_out is not None:
+                    host_out[k].copy_(u, non_blocking=True)
         for g in self.groups:
             cur.wait_stream(g["stream"])
         self.last = outs
