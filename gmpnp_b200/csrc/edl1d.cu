@@ -291,6 +291,7 @@ __device__ __forceinline__ void cell_columns(const double* __restrict__ P, const
 // ---------------------------------------------------------------------------------------
 struct Group {
     int c;            // lane in group (column id)
+    bool live;        // newton1d_kernel: the pair works on a real problem (false: padding pair of the last CTA)
     unsigned mask;    // participation mask of the 8 lanes
     int base;         // first lane of the group inside the warp
     const double* P;  // parameter record of the problem (shared memory)
@@ -358,7 +359,7 @@ __device__ __forceinline__ void eliminate_row(const Group& g, const double* __re
                 pcs[0] = make_double2(B[0], B[1]); pcs[1] = make_double2(B[2], B[3]);
                 pcs[2] = make_double2(B[4], B[5]); pcs[3] = make_double2(B[6], 0.0);
             }
-            __syncwarp(g.mask);
+            __syncwarp();
             const double2 p0 = pcs[0], p1 = pcs[1], p2 = pcs[2], p3 = pcs[3];
             pc[0] = p0.x; pc[1] = p0.y; pc[2] = p1.x; pc[3] = p1.y; pc[4] = p2.x; pc[5] = p2.y; pc[6] = p3.x;
         }
@@ -408,7 +409,7 @@ template <bool PIVOT, int NQJ>
 __device__ double forward_sweep(const Group& g, const LaneConst& L, const double* __restrict__ x, int n,
                                 int first, int dir, int rows, const double* __restrict__ up,
                                 const double* __restrict__ unp, double* __restrict__ ws, double (&X)[NC],
-                                int& singular) {
+                                int& singular, double& f1_last) {
     const double* P = g.P;
     const int c = g.c;
     double* sF = g.sm + SM_M;                        // residual rows of the current node, gathered for lane 7
@@ -449,7 +450,7 @@ __device__ double forward_sweep(const Group& g, const LaneConst& L, const double
         double* sB_cur = g.sm + SM_B + (r & 1) * 56;
         double* sB_nxt = g.sm + SM_B + ((r + 1) & 1) * 56;
         cp_async_wait<RING - 2>();                   // node r+1 has landed (groups 0 .. r+RING-1 are in flight)
-        __syncwarp(g.mask);
+        __syncwarp();
         double B[NC], Y[NC];
         {
             // nodal values of the cell ahead (local node 0 = current node) straight from the staging ring
@@ -477,7 +478,7 @@ __device__ double forward_sweep(const Group& g, const LaneConst& L, const double
 #pragma unroll
             for (int i = 0; i < NC; ++i) B[i] += sB_cur[i * 8 + c];
         }
-        __syncwarp(g.mask);
+        __syncwarp();
         if (c == 7) {
 #pragma unroll
             for (int i = 0; i < NC; ++i) Y[i] = sF[i];      // lane 7: rhs lives in Y
@@ -511,23 +512,28 @@ __device__ double forward_sweep(const Group& g, const LaneConst& L, const double
         eliminate_row<PIVOT>(g, r > 0 ? sA_cur : nullptr, B, Y, X, singular);
         // ---- store (coupling'_k | d'_k) ------------------------------------------------------
         double* w = ws + (long)k * 56;
+        if (g.live) {
 #pragma unroll
-        for (int i = 0; i < NC; ++i) { w[i * 8 + c] = Y[i]; X[i] = Y[i]; }
+            for (int i = 0; i < NC; ++i) w[i * 8 + c] = Y[i];
+        }
+#pragma unroll
+        for (int i = 0; i < NC; ++i) X[i] = Y[i];
     }
+    f1_last = f1_behind;
     cp_async_wait<0>();
-    __syncwarp(g.mask);
+    __syncwarp();
     // broadcast this half's residual sum from lane 7
-    rsq = __shfl_sync(g.mask, rsq, g.base + 7);
+    rsq = __shfl_sync(0xffffffffu, rsq, g.base + 7);
     return rsq;
 }
 
 // Back substitution x_k = d'_k - coupling'_k x_(k-dir') over `rows` rows starting at node `first`, moving in
 // direction `dir`, seeded with the already known neighbour solution xn; updates u <- u - relax * x and
 // accumulates max|dx|, max|u_new| in this lane.
-__device__ void backward_sweep(const Group& g, int first, int dir, int rows, double (&xn)[NC],
-                               double* __restrict__ up, const double* __restrict__ ws, double relax,
+__device__ void backward_sweep(const Group& g, int first, int dir, int rows, int rows_max, bool store,
+                               double (&xn)[NC], double* __restrict__ up, const double* __restrict__ ws, double relax,
                                double& mdx, double& mu) {
-    if (rows <= 0) return;
+    // rows_max: the warp-uniform trip count (the other half may have one row more); rows beyond `rows` are idle
     const int c = g.c;
     double2* bwc = reinterpret_cast<double2*>(g.ring) + c;     // [RING][4][8]: lane c's row of the workspace
     double* buc = g.ring + RING * 64 + c;                      // [RING][8]:    lane c's component of u
@@ -550,13 +556,13 @@ __device__ void backward_sweep(const Group& g, int first, int dir, int rows, dou
     };
 #pragma unroll
     for (int s = 0; s < RING; ++s) issue(s);
-    for (int q0 = 0; q0 < rows; q0 += RING) {
+    for (int q0 = 0; q0 < rows_max; q0 += RING) {
 #pragma unroll
         for (int s = 0; s < RING; ++s) {
-            if (q0 + s < rows) {                               // group-uniform
+            if (q0 + s < rows_max) {                           // warp-uniform
                 cp_async_wait<RING - 1>();
                 double xi = 0.0;
-                if (c < NC) {
+                if (c < NC && q0 + s < rows) {
                     const double2 r0 = bwc[(s * 4 + 0) * 8], r1 = bwc[(s * 4 + 1) * 8];
                     const double2 r2 = bwc[(s * 4 + 2) * 8], r3 = bwc[(s * 4 + 3) * 8];
                     const double ucur = buc[s * 8];
@@ -564,7 +570,7 @@ __device__ void backward_sweep(const Group& g, int first, int dir, int rows, dou
                     xi -= r0.x * xn[0]; xi -= r0.y * xn[1]; xi -= r1.x * xn[2]; xi -= r1.y * xn[3];
                     xi -= r2.x * xn[4]; xi -= r2.y * xn[5]; xi -= r3.x * xn[6];
                     const double un = ucur - relax * xi;
-                    *udst = un;
+                    if (store) *udst = un;
                     mdx = fmax(mdx, fabs(xi));
                     mu = fmax(mu, fabs(un));
                 }
@@ -573,7 +579,7 @@ __device__ void backward_sweep(const Group& g, int first, int dir, int rows, dou
                 // x_k of all components to every lane (double-buffered: one group barrier per row)
                 double* sxq = sx + (s & 1) * 8;
                 sxq[c] = xi;
-                __syncwarp(g.mask);
+                __syncwarp();
                 const double2* xs = reinterpret_cast<const double2*>(sxq);
                 const double2 a0 = xs[0], a1 = xs[1], a2 = xs[2];
                 xn[0] = a0.x; xn[1] = a0.y; xn[2] = a1.x; xn[3] = a1.y; xn[4] = a2.x; xn[5] = a2.y; xn[6] = sxq[6];
@@ -581,81 +587,134 @@ __device__ void backward_sweep(const Group& g, int first, int dir, int rows, dou
         }
     }
     cp_async_wait<0>();
-    __syncwarp(g.mask);
+    __syncwarp();
 }
 
 struct NewtonOut { int iters; double r0, r; int status; };
 
-// Factorisation sweep of both halves + merge.  Top half: rows 0..m-1 (stores C'_k, d'_k); bottom half: rows
-// n-1..m (stores A'_k, d'_k).  The merge eliminates the virtual row (I - A'_m C'_{m-1}) x_m = d'_m - A'_m d'_{m-1}
-// in the top group and broadcasts x_m to the pair.  Returns ||b||^2 of the whole problem.
+// Factorisation sweep of both halves + merge.  Both halves eliminate m = n/2 rows (top: 0..m-1 downwards, bottom:
+// n-1 .. n-m upwards), so the two groups of a pair -- and with the warp-uniform drivers below all four groups of a
+// warp -- run the same number of rows.  Even n: the bottom's last row is node m and the merge eliminates the virtual
+// row (I - A'_m C'_{m-1}) x_m = d'_m - A'_m d'_{m-1}.  Odd n: node m is left over and is eliminated in the merge from
+// the blocks both halves stashed for it: (B_m - A_m C'_{m-1} - C_m A'_{m+1}) x_m = d_m - A_m d'_{m-1} - C_m d'_{m+1}.
+// x_m is broadcast to the pair.  Returns ||b||^2 of the whole problem.  Executed by all 32 lanes in lock step.
 template <bool PIVOT, int NQJ>
 __device__ double factor_problem(const Group& g, const LaneConst& L, const double* x, int n, const double* up,
                                  const double* unp, double* ws, double (&xm)[NC], int& singular) {
     const int m = n >> 1;
+    const bool odd = (n & 1) != 0;
+    const int c = g.c;
     double X[NC];
-    const int first = g.half ? n - 1 : 0, dir = g.half ? -1 : 1, rows = g.half ? n - m : m;
-    double rsq = forward_sweep<PIVOT, NQJ>(g, L, x, n, first, dir, rows, up, unp, ws, X, singular);
-    // merge: bottom publishes (A'_m | d'_m) row-major: psm[i*8 + c], column 7 = d'_m
-    if (g.half) {
-#pragma unroll
-        for (int i = 0; i < NC; ++i) g.psm[i * 8 + g.c] = X[i];
-    }
-    __syncwarp(g.pmask);
+    const int first = g.half ? n - 1 : 0, dir = g.half ? -1 : 1;
+    double f1_last;
+    double rsq = forward_sweep<PIVOT, NQJ>(g, L, x, n, first, dir, m, up, unp, ws, X, singular, f1_last);
     double Y[NC];
 #pragma unroll
     for (int i = 0; i < NC; ++i) Y[i] = 0.0;
-    if (!g.half) {
+    if (!odd) {
+        // bottom publishes (A'_m | d'_m) row-major: psm[i*8 + c], column 7 = d'_m
+        if (g.half) {
+#pragma unroll
+            for (int i = 0; i < NC; ++i) g.psm[i * 8 + c] = X[i];
+        }
+        __syncwarp();
         double B[NC];
 #pragma unroll
-        for (int i = 0; i < NC; ++i) B[i] = (i == g.c) ? 1.0 : 0.0;
-        if (g.c == 7) {
+        for (int i = 0; i < NC; ++i) B[i] = (i == c) ? 1.0 : 0.0;
+        if (c == 7) {
 #pragma unroll
             for (int i = 0; i < NC; ++i) Y[i] = g.psm[i * 8 + 7];          // rhs d'_m
         }
-        eliminate_row<PIVOT>(g, g.psm, B, Y, X, singular);
-    }
-    __syncwarp(g.pmask);
+        int sing_m = 0;
+        eliminate_row<PIVOT>(g, g.psm, B, Y, X, sing_m);                    // only the top group's result is used
+        if (!g.half) singular |= sing_m;
+    } else {
+        // each half: its part of row m = (block (1,1) | residual row) of its last cell minus (block (1,0)) * X
+        const double* sA_last = g.sm + SM_A + (m & 1) * 56;
+        const double* sB_last = g.sm + SM_B + (m & 1) * 56;
+        double* sF = g.sm + SM_M;
+        sF[c] = f1_last;
+        __syncwarp();
+        double part[NC];
 #pragma unroll
-    for (int i = 0; i < NC; ++i) xm[i] = __shfl_sync(g.pmask, Y[i], g.pbase + 7);
-    rsq += __shfl_xor_sync(g.pmask, rsq, 8);
-    singular |= __shfl_xor_sync(g.pmask, singular, 8);
+        for (int i = 0; i < NC; ++i) {
+            const double2* row = reinterpret_cast<const double2*>(sA_last + i * 8);
+            const double2 a0 = row[0], a1 = row[1], a2 = row[2], a3 = row[3];
+            const double t = a0.x * X[0] + a0.y * X[1] + a1.x * X[2] + a1.y * X[3] + a2.x * X[4] + a2.y * X[5] + a3.x * X[6];
+            part[i] = ((c < NC) ? sB_last[i * 8 + c] : sF[i]) - t;
+        }
+        if (g.half) {
+#pragma unroll
+            for (int i = 0; i < NC; ++i) g.psm[i * 8 + c] = part[i];
+            if (c < NC) g.psm[56 + c] = f1_last;                            // raw residual row (for ||b||)
+        }
+        __syncwarp();
+        double B[NC];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            const double tot = part[i] + g.psm[i * 8 + c];
+            B[i] = (c < NC) ? tot : 0.0;
+            Y[i] = (c < NC) ? 0.0 : tot;
+        }
+        if (c == 7 && !g.half) {
+            // ||b||^2 of row m: raw residual rows of both halves, Poisson row unscaled
+            const double qscale = g.P[GMPNP_P_Q];
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                double d = sF[i] + g.psm[56 + i];
+                if (i == NS) d *= qscale;
+                rsq += d * d;
+            }
+        }
+        int sing_m = 0;
+        eliminate_row<PIVOT>(g, nullptr, B, Y, X, sing_m);                  // only the top group's result is used
+        if (!g.half) singular |= sing_m;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < NC; ++i) xm[i] = __shfl_sync(0xffffffffu, Y[i], g.pbase + 7);
+    rsq = __shfl_sync(0xffffffffu, rsq, g.base + 7);                        // lane 7 holds the group's sum
+    rsq += __shfl_xor_sync(0xffffffffu, rsq, 8);
+    singular |= __shfl_xor_sync(0xffffffffu, singular, 8);
     return rsq;
 }
 
-// Back substitution of both halves and the Newton update; returns max|dx|, max|u| over the problem.
+// Back substitution of both halves and the Newton update (stores only if `store`); returns max|dx|, max|u| over the
+// problem.  Row m (x_m known from the merge) is updated by the bottom group.
 __device__ void solve_problem(const Group& g, int n, const double (&xm)[NC], double* up, const double* ws,
-                              double relax, double& dxmax, double& umax) {
+                              double relax, bool store, double& dxmax, double& umax) {
     const int m = n >> 1;
     double xn[NC];
 #pragma unroll
     for (int i = 0; i < NC; ++i) xn[i] = xm[i];
     double mdx = 0.0, mu = 0.0;
-    if (!g.half) {
-        backward_sweep(g, m - 1, -1, m, xn, up, ws, relax, mdx, mu);
-    } else {
-        if (g.c < NC) {                       // row m itself: x_m is known
-            double xi = xm[0];
+    if (g.half && g.c < NC) {
+        double xi = xm[0];
 #pragma unroll
-            for (int i = 1; i < NC; ++i) if (i == g.c) xi = xm[i];
-            const double un = up[(long)m * NC + g.c] - relax * xi;
-            up[(long)m * NC + g.c] = un;
-            mdx = fabs(xi); mu = fabs(un);
-        }
-        backward_sweep(g, m + 1, 1, n - 1 - m, xn, up, ws, relax, mdx, mu);
+        for (int i = 1; i < NC; ++i) if (i == g.c) xi = xm[i];
+        const double un = up[(long)m * NC + g.c] - relax * xi;
+        if (store) up[(long)m * NC + g.c] = un;
+        mdx = fabs(xi); mu = fabs(un);
     }
+    const int first = g.half ? m + 1 : m - 1, dir = g.half ? 1 : -1, rows = g.half ? n - 1 - m : m;
+    backward_sweep(g, first, dir, rows, m, store, xn, up, ws, relax, mdx, mu);
 #pragma unroll
     for (int o = 8; o >= 1; o >>= 1) {
-        mdx = fmax(mdx, __shfl_xor_sync(g.pmask, mdx, o));
-        mu = fmax(mu, __shfl_xor_sync(g.pmask, mu, o));
+        mdx = fmax(mdx, __shfl_xor_sync(0xffffffffu, mdx, o));
+        mu = fmax(mu, __shfl_xor_sync(0xffffffffu, mu, o));
     }
     dxmax = mdx; umax = mu;
 }
 
-// dolfin NewtonSolver semantics for one problem handled by one pair of groups.
+// dolfin NewtonSolver semantics for the problem handled by a pair of groups.  The loop is
+// WARP-UNIFORM: the two pairs of a warp iterate together until both are done; a pair that has converged (or is
+// not `enabled`: padding pair, finished continuation path, failed earlier) keeps executing the sweeps but does not
+// store its u.  This costs nothing (the warp occupies its slot until its slower pair finishes anyway) and lets
+// every barrier and shuffle of the sweeps use the full-warp mask: the runtime 8-lane masks expanded to a
+// MATCH/VOTE sequence of six instructions per barrier, eleven barriers per block row.
 template <bool PIVOT, int NQJ>
 __device__ NewtonOut newton_solve(const Group& g, const LaneConst& L, const double* x, int n, double* up,
-                                  const double* unp, double* ws, const gmpnp_newton_opts& o) {
+                                  const double* unp, double* ws, const gmpnp_newton_opts& o, bool enabled) {
     NewtonOut out;
     int singular = 0;
     double xm[NC];
@@ -666,25 +725,34 @@ __device__ NewtonOut newton_solve(const Group& g, const LaneConst& L, const doub
     bool conv = (o.criterion == 0) ? (r < o.atol) : false;
     bool bad = !isfinite(r) || singular;
     double dx_prev = INFINITY;
-    while (!conv && !bad && k < o.maxit) {
+    bool active = enabled && !conv && !bad && k < o.maxit;
+    while (__any_sync(0xffffffffu, active)) {
         double dxmax, umax;
-        solve_problem(g, n, xm, up, ws, o.relax, dxmax, umax);
-        ++k;
-        if (o.criterion == 1) {
-            const double scale = fmax(1.0, umax);
-            conv = dxmax <= o.xtol * scale;
-            // round-off floor (consistent Jacobian only, where convergence is quadratic): an increment that is
-            // already small but no longer contracts sits at cond(J)*eps, above xtol -- accept it
-            if (!conv && NQJ == 2 && k >= 3 && dxmax <= 1.0e-6 * scale && dxmax >= 0.25 * dx_prev) conv = true;
-            dx_prev = dxmax;
-            if (!isfinite(dxmax)) bad = true;
-            if (conv || bad) break;
+        solve_problem(g, n, xm, up, ws, o.relax, active, dxmax, umax);
+        bool still = active;
+        if (active) {
+            ++k;
+            if (o.criterion == 1) {
+                const double scale = fmax(1.0, umax);
+                conv = dxmax <= o.xtol * scale;
+                // round-off floor (consistent Jacobian only, where convergence is quadratic): an increment that is
+                // already small but no longer contracts sits at cond(J)*eps, above xtol -- accept it
+                if (!conv && NQJ == 2 && k >= 3 && dxmax <= 1.0e-6 * scale && dxmax >= 0.25 * dx_prev) conv = true;
+                dx_prev = dxmax;
+                if (!isfinite(dxmax)) bad = true;
+                if (conv || bad) still = false;           // dolfin-like: no re-assembly after an increment stop
+            }
         }
-        __syncwarp(g.pmask);        // the other half's u updates must be visible before re-assembly
-        rsq = factor_problem<PIVOT, NQJ>(g, L, x, n, up, unp, ws, xm, singular);
-        r = sqrt(rsq);
-        if (!isfinite(r) || singular) bad = true;
-        if (o.criterion == 0) conv = (r / out.r0 < o.rtol) || (r < o.atol);
+        if (!__any_sync(0xffffffffu, still)) break;   // nobody needs the re-assembly (increment stop / failure)
+        __syncwarp();               // the other half's u updates must be visible before re-assembly
+        int sing2 = 0;
+        const double rsq2 = factor_problem<PIVOT, NQJ>(g, L, x, n, up, unp, ws, xm, sing2);
+        if (still) {
+            r = sqrt(rsq2);
+            if (!isfinite(r) || sing2) bad = true;
+            if (o.criterion == 0) conv = (r / out.r0 < o.rtol) || (r < o.atol);
+        }
+        active = still && !conv && !bad && k < o.maxit;
     }
     out.iters = k;
     out.r = r;
@@ -694,7 +762,7 @@ __device__ NewtonOut newton_solve(const Group& g, const LaneConst& L, const doub
 
 constexpr int PROBLEMS_PER_BLOCK = GROUPS_PER_BLOCK / 2;
 
-__device__ __forceinline__ bool group_setup(Group& g, int batch, int& prob, double* smem) {
+__device__ __forceinline__ void group_setup(Group& g, int batch, int& prob, double* smem) {
     const int lane = threadIdx.x & 31;
     g.c = lane & 7;
     g.base = lane & ~7;
@@ -709,19 +777,22 @@ __device__ __forceinline__ bool group_setup(Group& g, int batch, int& prob, doub
     g.P = smem + GROUPS_PER_BLOCK * (SM_GROUP + SM_RING) + (gid >> 1) * GMPNP_NPAR;
     g.su = nullptr;
     prob = blockIdx.x * PROBLEMS_PER_BLOCK + (threadIdx.x >> 4);
-    return prob < batch;
+    // padding pairs of the last CTA shadow the last problem (valid memory to read) but never store
+    g.live = prob < batch;
+    if (!g.live) prob = batch - 1;
 }
 
 // parameter record of the pair's problem -> shared memory (both groups of the pair cooperate)
 __device__ __forceinline__ void load_params(const Group& g, const double* __restrict__ params, int prob) {
     double* P = const_cast<double*>(g.P);
     for (int i = (threadIdx.x & 15); i < GMPNP_NPAR; i += 16) P[i] = params[(long)prob * GMPNP_NPAR + i];
-    __syncwarp(g.pmask);
+    __syncwarp();
 }
 
 // mode 0: single Newton solve (gmpnp_newton_1d)
 // mode 1: pseudo-time march  (gmpnp_march_1d): n_stage steps, H_OHP controller, u_n <- u
 // mode 2: steady continuation (gmpnp_steady_continuation_1d): kappa = 0, V from Vpath
+// Control flow is warp-uniform (see newton_solve): per-pair outcomes are flags, never early exits.
 #ifndef GMPNP_NEWTON_MIN_BLOCKS
 #define GMPNP_NEWTON_MIN_BLOCKS 3
 #endif
@@ -735,18 +806,18 @@ newton1d_kernel(int mode, int batch, int n, const double* __restrict__ x, const 
                 int* __restrict__ stage_out, int* __restrict__ status) {
     extern __shared__ double smem[];
     Group g; int prob;
-    if (!group_setup(g, batch, prob, smem)) return;
+    group_setup(g, batch, prob, smem);
     load_params(g, params, prob);
     double* P = const_cast<double*>(g.P);
     double* up = u + (long)prob * n * NC;
     double* ws = wsall + (long)prob * n * 56;
     LaneConst L;
     lane_consts(P, g.c, L);
-    const bool writer = (g.c == 0 && g.half == 0);
+    const bool writer = (g.c == 0 && g.half == 0 && g.live);
     const int lane16 = (threadIdx.x & 15);
     if (mode == 0) {
         const double* unp = un_ro + (long)prob * n * NC;
-        NewtonOut o = newton_solve<PIVOT, NQJ>(g, L, x, n, up, unp, ws, opts);
+        NewtonOut o = newton_solve<PIVOT, NQJ>(g, L, x, n, up, unp, ws, opts, g.live);
         if (writer) {
             if (iters) iters[prob] = o.iters;
             if (r0out) r0out[prob] = o.r0;
@@ -760,20 +831,26 @@ newton1d_kernel(int mode, int batch, int n, const double* __restrict__ x, const 
         double frac = P[GMPNP_P_HFRAC];
         const double hohp = P[GMPNP_P_HOHP];
         int st = GMPNP_CONVERGED, done = 0;
+        bool alive = g.live;
         for (int s = 0; s < n_stage; ++s) {
-            NewtonOut o = newton_solve<PIVOT, NQJ>(g, L, x, n, up, unp, ws, opts);
-            if (writer && iters) iters[(long)prob * n_stage + s] = o.iters;
-            if (o.status != GMPNP_CONVERGED) { st = o.status; break; }
-            ++done;
-            __syncwarp(g.pmask);
-            // u_n <- u (1D:796) and history row
-            for (long i = lane16; i < (long)n * NC; i += 16) {
-                const double v = up[i];
-                unp[i] = v;
-                if (hist) hist[((long)prob * n_stage + s) * n * NC + i] = v;
+            if (!__any_sync(0xffffffffu, alive)) break;
+            NewtonOut o = newton_solve<PIVOT, NQJ>(g, L, x, n, up, unp, ws, opts, alive);
+            if (alive) {
+                if (writer && iters) iters[(long)prob * n_stage + s] = o.iters;
+                if (o.status != GMPNP_CONVERGED) { st = o.status; alive = false; }
+                else ++done;
             }
-            __syncwarp(g.pmask);
-            if (hohp >= 0.0) {
+            __syncwarp();
+            if (alive) {
+                // u_n <- u (1D:796) and history row
+                for (long i = lane16; i < (long)n * NC; i += 16) {
+                    const double v = up[i];
+                    unp[i] = v;
+                    if (hist) hist[((long)prob * n_stage + s) * n * NC + i] = v;
+                }
+            }
+            __syncwarp();
+            if (alive && hohp >= 0.0) {
                 // proton-current controller, 1D:766-793
                 const double f = up[0];
                 if (f < 0) frac = frac / 1.1;
@@ -781,13 +858,13 @@ newton1d_kernel(int mode, int batch, int n, const double* __restrict__ x, const 
                 else if (f < (hohp - 0.025)) frac = frac / 1.01;
                 else if (f > hohp && f <= (hohp + 0.4) && frac <= 1.0) frac = frac * 1.04;
                 else if (f > (hohp + 0.4) && frac <= 1.0) frac = frac * 1.15;
-                __syncwarp(g.pmask);
-                if (writer) {
-                    P[GMPNP_P_JFLUX + 1] = -1.0 * P[GMPNP_P_JOHPRE] * (1 - frac);
-                    P[GMPNP_P_JFLUX + 0] = P[GMPNP_P_JHPRE] * frac;
-                }
-                __syncwarp(g.pmask);
             }
+            __syncwarp();
+            if (writer && alive && hohp >= 0.0) {
+                P[GMPNP_P_JFLUX + 1] = -1.0 * P[GMPNP_P_JOHPRE] * (1 - frac);
+                P[GMPNP_P_JFLUX + 0] = P[GMPNP_P_JHPRE] * frac;
+            }
+            __syncwarp();
         }
         if (writer) {
             if (status) status[prob] = st;
@@ -799,23 +876,28 @@ newton1d_kernel(int mode, int batch, int n, const double* __restrict__ x, const 
     // mode 2: steady continuation
     {
         if (writer) P[GMPNP_P_KAPPA] = 0.0;
-        __syncwarp(g.pmask);
+        __syncwarp();
         int st = GMPNP_CONVERGED, done = 0;
         const double xtol_final = opts.xtol;
+        bool alive = g.live;
         for (int s = 0; s < n_stage; ++s) {
             const double Vs = Vpath[(long)prob * n_stage + s];
-            if (isnan(Vs)) break;                       // ragged path: this problem is done
+            if (isnan(Vs)) alive = false;               // ragged path: this problem is done
+            if (!__any_sync(0xffffffffu, alive)) break;
             const bool final_stage = (s + 1 == n_stage) || isnan(Vpath[(long)prob * n_stage + s + 1]);
-            opts.xtol = (final_stage || !(opts.xtol_path > 0.0)) ? xtol_final : opts.xtol_path;
-            __syncwarp(g.pmask);
-            if (writer) P[GMPNP_P_V] = Vs;
-            __syncwarp(g.pmask);
+            gmpnp_newton_opts o2 = opts;
+            o2.xtol = (final_stage || !(opts.xtol_path > 0.0)) ? xtol_final : opts.xtol_path;
+            __syncwarp();
+            if (writer && alive) P[GMPNP_P_V] = Vs;
+            __syncwarp();
             // kappa = 0: u_n is never read for its value; pass u itself
-            NewtonOut o = newton_solve<PIVOT, NQJ>(g, L, x, n, up, up, ws, opts);
-            if (writer && iters) iters[(long)prob * n_stage + s] = o.iters;
-            if (writer && rout) rout[prob] = o.r;
-            if (o.status != GMPNP_CONVERGED) { st = o.status; break; }
-            ++done;
+            NewtonOut o = newton_solve<PIVOT, NQJ>(g, L, x, n, up, up, ws, o2, alive);
+            if (alive) {
+                if (writer && iters) iters[(long)prob * n_stage + s] = o.iters;
+                if (writer && rout) rout[prob] = o.r;
+                if (o.status != GMPNP_CONVERGED) { st = o.status; alive = false; }
+                else ++done;
+            }
         }
         if (writer) {
             if (status) status[prob] = st;
