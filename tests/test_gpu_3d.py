@@ -248,3 +248,30 @@ def test_intended_boundary_integrals_match_oracle(lib):
     d = np.abs(F0[0].cpu().numpy() - Fr)
     assert d.max() > 1e-3 and d[:, 8].max() <= 1e-11 * np.abs(Fr).max()     # species rows change, the Poisson row does not
     pp.solver.close()
+
+
+def test_geometry_voltage_sweep_parks_failed_points(lib):
+    """Config 4 in miniature: two pore meshes x a few wall voltages, batched per mesh, ramped to steady state.
+    Points inside the convergent range reproduce the single-problem steady solve; a point far beyond it fails,
+    is parked and reported without disturbing its batch."""
+    from gmpnp_b200 import meshio, params, solver3d, sweep3d
+    pts = [sweep3d.PorePoint("L_50_R_5", 50e-9, 5e-9, V, i) for i, V in enumerate((-0.5, -1.0, -12.5))]
+    pts += [sweep3d.PorePoint("L_10_R_5", 10e-9, 5e-9, -0.5, 3)]
+    sw = sweep3d.Sweep3D(pts, dv_max=0.5, tol=1e-8, max_steps=40)
+    res = sw.solve()
+    assert res[:, 0].tolist()[:2] == [0.0, 0.0] and res[3, 0] == 0.0
+    assert res[2, 0] != 0.0                                        # -12.5 V_T: the discrete problem breaks down
+    # the V = -1 point equals the single-problem steady solve with the SAME pseudo-time schedule (the batch ramps over
+    # ceil(12.5 / 0.5) = 25 steps; the march has slow reaction modes, so states after different numbers of steps
+    # agree only to ~1e-4 although their last increments are below 1e-8)
+    mesh = meshio.load_mesh("L_50_R_5")
+    prm = params.params_3d(L=50e-9, R=5e-9, voltage_multiplier=-1.0)
+    pp = solver3d.PoreProblem(mesh, 50e-9, 5e-9, [prm])
+    from gmpnp_b200._lib import NewtonOpts
+    out = pp.steady(opts=NewtonOpts.sweep_3d(), tol=1e-8, max_steps=40, dv_max=1.0 / 25)
+    assert out["steps"] == int(res[1, 1])
+    med = [float(pp.solver.median(out["u"], c)[0]) for c in (1, 2, 3, 7)]
+    for j in range(4):
+        assert abs(res[1, 3 + j] - med[j]) <= 1e-6 * abs(med[j]), (j, res[1, 3 + j], med[j])
+    assert abs(res[1, 7] - out["co2_entry"][0]) <= 1e-6 * out["co2_entry"][0]
+    pp.solver.close()
