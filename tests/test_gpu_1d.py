@@ -376,3 +376,35 @@ def test_tiny_even_and_odd_meshes_match_the_oracle(lib, fine, coarse):
             for c in range(7):
                 assert rel_l2(got[1][:, c], uo.reshape(n, 7)[:, c]) < 1e-8, (n, jac_rule, pivot, c)
             s.close()
+
+
+def test_rxn_diff_drop_in_matches_oracle(lib, tmp_path):
+    """`1D/rxn_diff_planar.py` on the GMPNP kernels (nu = 0, z = 0): the first steps of the reference march vs the
+    oracle with the same parameter mapping, the passenger components stay put, and the reference's output keys."""
+    from gmpnp_b200 import meshio, rxn_diff
+    from oracle import solver as osolver
+    meta = rxn_diff.solve_rxn_diff(L_n=1.0e-6, n_steps=3, out_dir=str(tmp_path))
+    un = np.load(os.path.join(meta["output_dir"], "arrays_unscaled.npz"))
+    assert set(un.files) == {"H", "OH", "HCO3", "CO32", "CO2", "coor_array", "tau_array"}
+    assert un["H"].shape == (4, 1091) and np.all(un["H"][0] == 1.0)
+    sc = np.load(os.path.join(meta["output_dir"], "arrays_scaled.npz"))
+    assert {"x", "t_H", "c_H", "c_CO2", "c_cat"} <= set(sc.files)
+    prm = rxn_diff.params_rxn_diff(L_n=1.0e-6)
+    x = meshio.load_mesh("1D_variable_1um_mesh_1090").x[:, 0]
+    n = len(x)
+    disc = osolver.Discretisation(x, np.stack([np.arange(n - 1), np.arange(1, n)], 1), 7, jac_rule=1)
+    bd, bv = osolver.bc_1d(n, 7, 0.0)
+    u = np.zeros((n, 7)); u[:, 5] = 1.0
+    unn = np.tile(np.array([1.0] * 6 + [0.0]), n)
+    its = []
+    u = u.ravel()
+    for _ in range(3):
+        u, k, conv, r0, r = osolver.newton(disc, prm, u, unn, bd, bv, point_flux=prm.jflux, rtol=1e-6, atol=1e-6, maxit=100)
+        assert conv
+        its.append(k)
+        unn = u.copy()
+    assert meta["newton_iterations"] == its
+    U = u.reshape(n, 7)
+    for i, nm in enumerate(("H", "OH", "HCO3", "CO32", "CO2")):
+        assert rel_l2(un[nm][3], U[:, i]) < 1e-8, nm
+    assert np.abs(U[:, 5] - 1.0).max() < 1e-12 and np.abs(U[:, 6]).max() < 1e-12
