@@ -275,3 +275,36 @@ def test_geometry_voltage_sweep_parks_failed_points(lib):
         assert abs(res[1, 3 + j] - med[j]) <= 1e-6 * abs(med[j]), (j, res[1, 3 + j], med[j])
     assert abs(res[1, 7] - out["co2_entry"][0]) <= 1e-6 * out["co2_entry"][0]
     pp.solver.close()
+
+
+def test_api_errors_3d(lib):
+    """Error behaviour of the 3D C-ABI: argument and state errors are negative return codes raised as GmpnpError,
+    never crashes; numerical failure is a per-problem status."""
+    import ctypes as C
+    from gmpnp_b200 import _lib, meshio, params, solver3d
+    from gmpnp_b200._lib import GmpnpError
+    m = cube_tet_mesh(2)
+    bad = meshio.Mesh(x=m.x, cells=np.where(m.cells == 0, m.x.shape[0] + 5, m.cells).astype(np.int32), name="bad")
+    with pytest.raises(GmpnpError):
+        solver3d.Solver3D(bad, np.zeros(0, dtype=np.int32))                     # vertex index out of range
+    with pytest.raises(GmpnpError):
+        solver3d.Solver3D(m, np.array([9 * m.x.shape[0] + 1], dtype=np.int32))  # Dirichlet dof out of range
+    s = solver3d.Solver3D(m, np.array([8], dtype=np.int32), batch=2)
+    u = solver3d.bulk_state(2, s.n, s.device)
+    with pytest.raises(GmpnpError):
+        s.assemble(u, u.clone())                                               # parameters / Dirichlet values not set
+    prm = params.params_3d(L=50e-9, R=5e-9)
+    s.set_params([prm, prm])
+    s.set_dirichlet(np.zeros((2, 1)))
+    with pytest.raises(GmpnpError):                                            # wrong batch size
+        _lib.check(lib.gmpnp_set_dirichlet_3d(s._h, np.zeros(3).ctypes.data_as(C.POINTER(C.c_double)), 3), s._h)
+    with pytest.raises(GmpnpError):
+        s.set_facet_terms(np.zeros(s.n), np.array([[0, 1, s.n + 3]]), np.ones(1), np.zeros((2, 8)), np.zeros((2, 8)))
+    F, J = s.assemble(u, u.clone())
+    assert torch.isfinite(F).all() and torch.isfinite(J).all()
+    # a non-finite state ends as a per-problem status (the other problem of the batch still converges), not an exception
+    ubad = u.clone()
+    ubad[1, 3, 2] = float("nan")
+    out = s.newton(ubad, u.clone())
+    assert int(out["status"][1]) == 2 and int(out["status"][0]) == 0
+    s.close()
