@@ -397,6 +397,18 @@ def main():
                          "algorithmic_bytes_per_step": bytes_total / world},
             "clocks": sampler.summary(),
         }
+        # fp64: executed flops of the hot kernel (thread-level DFMA x2 + DMUL + DADD per block row and Newton iteration,
+        # counted by ncu on the v10 kernel: profiles/r01_newton1d_v10_ncu_summary.md) against the measured DFMA peak
+        import ctypes as C
+        from gmpnp_b200 import _lib
+        pk64 = C.c_double(0.0)
+        _lib.check(_lib.load().gmpnp_fp64_peak(local, C.byref(pk64)))
+        flops_row = 6233.0
+        ach64 = flops_row * (bytes_total / world / 1072.0) / (ms * 1e-3) / 1e12
+        line["fp64"] = {"peak_tflops_measured": pk64.value, "achieved_tflops_executed": ach64,
+                        "frac": ach64 / pk64.value if pk64.value > 0 else None,
+                        "flops_per_block_row_iteration": flops_row,
+                        "note": "executed (not minimal) fp64 flops incl. the per-lane redundancy of the quadrature"}
         if pore3d is not None:
             if world == 1 and not args.no_cpu_baseline:
                 pore3d["cpu_baseline"] = run_cpu_3d(pore3d["newton_iterations_per_problem"])

@@ -54,6 +54,7 @@ SIGNATURES = {
     "gmpnp_strerror": (C.c_char_p, [_i]),
     "gmpnp_last_cuda_error": (C.c_char_p, [_vp]),
     "gmpnp_version": (_i, []),
+    "gmpnp_fp64_peak": (_i, [_i, _pd]),
     "gmpnp_destroy": (None, [_vp]),
     "gmpnp_launch_count": (C.c_longlong, [_vp]),
     "gmpnp_create_1d": (_i, [C.POINTER(_vp), _i, _pd, _i, _i, _i]),

@@ -87,6 +87,9 @@ typedef struct gmpnp_newton_opts {
 #define GMPNP_ERR_ALLOC       -3
 #define GMPNP_ERR_STATE       -4
 
+/* fp64 FMA micro-benchmark of the device (TFLOP/s, DFMA = 2 flops): the measured denominator for fp64 fractions. */
+int gmpnp_fp64_peak(int device, double* tflops);
+
 const char* gmpnp_strerror(int code);
 const char* gmpnp_last_cuda_error(const gmpnp_handle* h);
 int  gmpnp_version(void);
