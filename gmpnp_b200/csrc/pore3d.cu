@@ -14,6 +14,7 @@
 // row sorted by column);  per-tet moment records mom[problem][tet][60], Fe[problem][tet][4][9].
 #include <algorithm>
 #include <map>
+#include <mutex>
 #include <numeric>
 #include "common.cuh"
 
@@ -1063,20 +1064,31 @@ struct Host3D {   // device arrays that only the 3D path needs and common.cuh do
     double *d_coef = nullptr, *d_beta = nullptr, *d_dxmax = nullptr, *d_umax = nullptr;
     int *d_jdone = nullptr, *d_active = nullptr;
 };
-static std::map<gmpnp_handle*, Host3D*> g_ext;     // side table keyed by handle (handles are independent)
+// side table keyed by handle (handles are independent; the table itself is guarded so that different handles can be
+// created, used and destroyed from different threads)
+static std::map<gmpnp_handle*, Host3D*> g_ext;
+static std::mutex g_ext_mutex;
 
-static Host3D* ext(gmpnp_handle* h) { return g_ext[h]; }
+static Host3D* ext(gmpnp_handle* h) {
+    std::lock_guard<std::mutex> lk(g_ext_mutex);
+    auto it = g_ext.find(h);
+    return it == g_ext.end() ? nullptr : it->second;
+}
 
 void pore3d_free_ext(gmpnp_handle* h) {
-    auto it = g_ext.find(h);
-    if (it == g_ext.end()) return;
-    Host3D* e = it->second;
+    Host3D* e = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_ext_mutex);
+        auto it = g_ext.find(h);
+        if (it == g_ext.end()) return;
+        e = it->second;
+        g_ext.erase(it);
+    }
     void* bufs[] = {e->d_wall_w, e->d_exit_m, e->d_exit_flag, e->d_bc, e->d_mass, e->d_gp, e->d_partial, e->d_blk_row, e->d_blk_geo, e->d_agg, e->d_agg_ptr, e->d_agg_nodes, e->d_Aci, e->d_yc, e->d_V, e->d_w, e->d_z,
                     e->d_dx, e->d_d1, e->d_d2, e->d_nrm, e->d_H, e->d_cs, e->d_sn, e->d_g, e->d_tol, e->d_coef,
                     e->d_beta, e->d_dxmax, e->d_umax, e->d_jdone, e->d_active};
     for (void* b : bufs) if (b) cudaFree(b);
     delete e;
-    g_ext.erase(it);
 }
 
 extern "C" {
@@ -1095,7 +1107,10 @@ int gmpnp_create_3d(gmpnp_handle** out, int device, const double* h_xyz, int n_v
     h->n_nodes = n_vert; h->n_tet = n_tet; h->n_dir = n_dir;
     *out = h;
     Host3D* e = new Host3D();
-    g_ext[h] = e;
+    {
+        std::lock_guard<std::mutex> lk(g_ext_mutex);
+        g_ext[h] = e;
+    }
     GMPNP_CUDA_TRY(h, cudaSetDevice(device));
     upload_rules();
     // ---- geometry: grad lambda_a and volume (same formulas as oracle/forms.py:geometry) -------
