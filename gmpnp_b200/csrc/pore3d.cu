@@ -24,6 +24,9 @@ constexpr int NS = 8;
 constexpr int NC = 9;
 constexpr int NMOM = 64;     // mD[4] | mUD2[8][4] | iUD[8] | Ga[4] | gpa[4] | SU[8] | eps_r(mean) | pad[3]  (512-B records)
 constexpr int M_MD = 0, M_UD2 = 4, M_IUD = 36, M_GA = 44, M_GPA = 48, M_SU = 52, M_EPS = 60;
+#ifndef TET_MIN_BLOCKS
+#define TET_MIN_BLOCKS 2
+#endif
 constexpr int NZ = 16;       // z-slabs of the coarse space
 constexpr int NCO = NZ * NC; // coarse dimension (144)
 
@@ -69,7 +72,7 @@ static void upload_rules() {
 // ---------------------------------------------------------------------------------------
 // Kernel A: per (problem, tet) quadrature moments (14-point rule) and element residual (5-point)
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, TET_MIN_BLOCKS)
 tet_moments_kernel(int n_tet, int n_vert, const int* __restrict__ tets, const double* __restrict__ geom,
                    const double* __restrict__ params, const double* __restrict__ u, const double* __restrict__ un,
                    double* __restrict__ mom, double* __restrict__ Fe, int want_jac, int want_res) {
