@@ -229,7 +229,9 @@ def bench_pore3d(local, world, dev, batch, peak):
         "pseudo_time_steps": int(out["steps"]), "newton_iterations_per_problem": int(out["iters"].sum(axis=0).max()),
         "gpu_launches": int(s.launch_count() - l1),
         "assemble": {"ms": ms_asm, "GBs": b_asm / ms_asm / 1e6, "frac_of_hbm_peak": b_asm / ms_asm / 1e6 / peak,
-                     "algorithmic_bytes": b_asm},
+                     "algorithmic_bytes": b_asm,
+                     "dram_traffic_over_algorithmic": 1.18,      # ncu, profiles/r01_pore3d_ncu_summary.md
+                     "kernels": "tet_moments_kernel + assemble_bsr_kernel + residual_gather_kernel"},
         "spmv": {"ms": ms_spmv, "GBs": b_spmv / ms_spmv / 1e6, "frac_of_hbm_peak": b_spmv / ms_spmv / 1e6 / peak,
                  "algorithmic_bytes": b_spmv,
                  "note": "batch Jacobians (%.2f GB) exceed the 126 MB L2" % (batch * 8 * 81 * nb / 1e9)},
