@@ -116,13 +116,21 @@ class PartitionedPore:
 
     NZ = 16          # z-slabs of the coarse space (NZ in csrc/pore3d.cu)
 
-    def __init__(self, mesh, L: float, R: float, prm, parts, comm, device: int = 0, dirichlet=None, coarse: bool = True):
+    def __init__(self, mesh, L: float, R: float, prm, parts, comm, device: int = 0, dirichlet=None, coarse: bool = True,
+                 intended_bcs: bool = False):
+        """``intended_bcs``: the wall-flux / pore-exit Robin integrals of 3D:474-499 (see ``PoreProblem``).  The
+        lumped wall weights are per-vertex data and are simply restricted to a part; an exit facet is given to every
+        part that owns at least one of its vertices (its tet is local there, so all three vertices and the blocks
+        it touches exist locally; the owned rows receive every facet that touches them, ghost rows are unused)."""
         self.mesh, self.L, self.R, self.prm = mesh, L, R, prm
         self.parts, self.comm = list(parts), comm
         self.device = torch.device("cuda", int(device))
         self.dofs, self.kind, self.info = dirichlet if dirichlet is not None else marking.dirichlet_sets(mesh, L, R)
         self.solvers, self.dir_sel = [], []
         self.coarse = bool(coarse)
+        self.intended_bcs = bool(intended_bcs)
+        if self.intended_bcs:
+            wall_w, exit_f, exit_a = marking.facet_terms(mesh, L, R)
         z = np.asarray(mesh.x)[:, 2]
         zmin, zmax = float(z.min()), float(z.max())
         for p in self.parts:
@@ -134,6 +142,13 @@ class PartitionedPore:
                           0, self.NZ - 1)
             agg = np.ascontiguousarray(agg, dtype=np.int32)
             check(s.lib.gmpnp_set_aggregates_3d(s._h, agg.ctypes.data_as(C.POINTER(C.c_int))), s._h)
+            if self.intended_bcs:
+                g2l = -np.ones(mesh.x.shape[0], dtype=np.int64)
+                g2l[p.glob] = np.arange(p.n_local)
+                lf = g2l[np.asarray(exit_f, dtype=np.int64).reshape(-1, 3)]
+                keep = (lf >= 0).all(axis=1) & ((lf >= 0) & (lf < p.n_own)).any(axis=1)
+                s.set_facet_terms(wall_w[p.glob], lf[keep].astype(np.int32), np.asarray(exit_a)[keep],
+                                  prm.extras["J_wall"][None, :], prm.extras["k_exit"][None, :])
             self.solvers.append(s)
             self.dir_sel.append(sel)
         self.lib = self.solvers[0].lib

@@ -151,9 +151,14 @@ class PoreProblem:
     """One pore geometry + a batch of parameter points: Dirichlet sets per the reference's marking
     (3D:335-379, 460-467) and the drivers built on :class:`Solver3D`."""
 
-    def __init__(self, mesh, L: float, R: float, plist, device: int = 0, intended_bcs: bool = False):
+    def __init__(self, mesh, L: float, R: float, plist, device: int = 0, intended_bcs: bool = False,
+                 rxn_diff: bool = False):
         """``intended_bcs``: add the wall-flux and pore-exit Robin integrals the reference's author wrote but Python
-        discards (3D:474-499, 560-750; SURVEY finding 3 / App. H).  Default False = parity with the script as executed."""
+        discards (3D:474-499, 560-750; SURVEY finding 3 / App. H).  Default False = parity with the script as executed.
+        ``rxn_diff``: the parameter points describe ``3D/rxn_diff_CO2ER_pore.py`` (z = nu = 0, V = 0; see
+        ``gmpnp_b200/rxn_diff3d.py``): the cation starts at its bulk value instead of 0 and the Sechenov update takes
+        the electroneutral cation estimate of RD3:589-592."""
+        self.rxn_diff = bool(rxn_diff)
         self.mesh, self.L, self.R = mesh, L, R
         self.plist = list(plist)
         self.dofs, self.kind, self.info = marking.dirichlet_sets(mesh, L, R)
@@ -174,6 +179,21 @@ class PoreProblem:
             vals.append(marking.dirichlet_values(self.kind, v, co2_scaled[b], eq[1], eq[2]))
         return np.stack(vals)
 
+    def _sechenov_update(self, u):
+        """CO2 entry value of every problem from the nodal MEDIANS (3D:817-838; RD3:575-601)."""
+        s = self.solver
+        if not self.rxn_diff:
+            med = [s.median(u, c).cpu().numpy() for c in (1, 2, 3, 7)]
+            return [_params.sechenov_co2_scaled(p, med[0][b], med[1][b], med[2][b], med[3][b])
+                    for b, p in enumerate(self.plist)]
+        med = [s.median(u, c).cpu().numpy() for c in (0, 1, 2, 3)]
+        out = []
+        for b, p in enumerate(self.plist):
+            c0 = p.c0
+            cat = med[2][b] * c0[2] + 2 * med[3][b] * c0[3] + med[1][b] * c0[1] - med[0][b] * c0[0]   # RD3:589-592
+            out.append(_params.sechenov_co2_scaled(p, med[1][b], med[2][b], med[3][b], cat / c0[7]))
+        return out
+
     def march(self, n_steps: int, opts: NewtonOpts | None = None, history=True):
         """The reference's loop (3D:782-858): u = 0, u_n = (1,..,1,0); per step one damped Newton solve,
         then the CO2 entry Dirichlet value is re-evaluated from the nodal MEDIANS (3D:817-838)."""
@@ -181,6 +201,8 @@ class PoreProblem:
         s = self.solver
         B = s.batch
         u = torch.zeros(B, s.n, NC, dtype=torch.float64, device=self.device)
+        if self.rxn_diff:
+            u[:, :, 7] = 1.0                               # passenger cation: stays at its bulk value
         un = bulk_state(B, s.n, self.device)
         co2 = [float(p.extras["eq_scaled"][0]) for p in self.plist]
         hist, its, lin, co2s = [un.cpu().numpy().copy()], [], [], []
@@ -193,9 +215,7 @@ class PoreProblem:
                 raise RuntimeError(f"Newton solver did not converge: status {st.tolist()}")   # dolfin raises too
             its.append(out["iters"].cpu().numpy().copy())
             lin.append(out["lin_iters"].cpu().numpy().copy())
-            med = [s.median(u, c).cpu().numpy() for c in (1, 2, 3, 7)]
-            co2 = [_params.sechenov_co2_scaled(p, med[0][b], med[1][b], med[2][b], med[3][b])
-                   for b, p in enumerate(self.plist)]
+            co2 = self._sechenov_update(u)
             if history:
                 hist.append(u.cpu().numpy().copy())
             un.copy_(u)
@@ -237,9 +257,7 @@ class PoreProblem:
             if (st != 0).any():
                 raise RuntimeError(f"Newton solver did not converge in pseudo-time step {step}: status {st.tolist()}")
             its.append(out["iters"].cpu().numpy().copy())
-            med = [s.median(u, c).cpu().numpy() for c in (1, 2, 3, 7)]
-            co2 = [_params.sechenov_co2_scaled(p, med[0][b], med[1][b], med[2][b], med[3][b])
-                   for b, p in enumerate(self.plist)]
+            co2 = self._sechenov_update(u)
             inc = float((u - un).abs().max() / max(1.0, float(u.abs().max())))
             incs.append(inc)
             un.copy_(u)

@@ -250,6 +250,33 @@ def test_intended_boundary_integrals_match_oracle(lib):
     pp.solver.close()
 
 
+def test_rxn_diff_3d_drop_in_matches_independent_oracle(lib, tmp_path):
+    """`3D/rxn_diff_CO2ER_pore.py` on the GMPNP kernels (z = nu = 0, passenger cation and potential) against the
+    independent 7-species CPU oracle (tests/golden/make_golden_rd3.py): two reference time steps incl. the Sechenov
+    update with the electroneutral cation; Newton counts equal, fields to 1e-7, passengers untouched; files and keys
+    of RD3:659-790."""
+    import json
+    from gmpnp_b200 import rxn_diff3d
+    g = np.load(os.path.join(GOLDEN, "rxn_diff_3d_L10R5.npz"))
+    meta = rxn_diff3d.solveEDL(L=10e-9, R=5e-9, n_steps=2, out_dir=str(tmp_path))
+    assert meta["newton_iterations"] == g["its"].tolist()
+    assert np.allclose(meta["CO2_entry_scaled"], g["co2_entry"], rtol=1e-9, atol=0)
+    d = meta["output_dir"]
+    un = np.load(os.path.join(d, "arrays_unscaled.npz"))
+    names = ["H", "OH", "HCO3", "CO32", "CO2", "CO", "H2"]
+    assert set(un.files) == set(names) | {n + "_grad" for n in names} | {"coor", "tau"}
+    for i, n in enumerate(names):
+        assert un[n].shape == (3, 1767) and (un[n][0] == 1.0).all()
+        for s_ in range(2):
+            assert rel_l2(un[n][s_ + 1], g["steps"][s_][:, i]) < 1e-7, (n, s_)
+    sc = np.load(os.path.join(d, "arrays_scaled.npz"))
+    assert {"coor_scaled", "c_cat", "c_CO", "t_H2", "CO2_grad"} <= set(sc.files)
+    assert np.allclose(sc["c_cat"], sc["c_HCO3"] + 2 * sc["c_CO32"] + sc["c_OH"] - sc["c_H"])
+    md = json.load(open(os.path.join(d, "metadata.json")))
+    assert md["CO2_min"] == float(un["CO2"][-1].min()) and md["current_planar"] == 20.0
+    assert md["passenger_drift"] <= 1e-12
+
+
 def test_geometry_voltage_sweep_parks_failed_points(lib):
     """Config 4 in miniature: two pore meshes x a few wall voltages, batched per mesh, ramped to steady state.
     Points inside the convergent range reproduce the single-problem steady solve; a point far beyond it fails,

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 
-def _setup(world, mesh=None, kappa_scale=1.0, coarse=True):
+def _setup(world, mesh=None, kappa_scale=1.0, coarse=True, intended_bcs=False):
     from gmpnp_b200 import meshio, params, partition, solver3d
     from gmpnp_b200.dist3d import LocalComm, PartitionedPore
     mesh = mesh or meshio.load_mesh("L_50_R_5")
@@ -20,8 +20,8 @@ def _setup(world, mesh=None, kappa_scale=1.0, coarse=True):
         # species blocks of the reference step (dt_scaled = 73.84) converge too slowly for a unit test
         prm = prm.with_(kappa=prm.kappa * kappa_scale)
     parts = partition.partition_z(mesh, world)
-    pp = PartitionedPore(mesh, 50e-9, 5e-9, prm, parts, LocalComm(parts), coarse=coarse)
-    ref = solver3d.PoreProblem(mesh, 50e-9, 5e-9, [prm])
+    pp = PartitionedPore(mesh, 50e-9, 5e-9, prm, parts, LocalComm(parts), coarse=coarse, intended_bcs=intended_bcs)
+    ref = solver3d.PoreProblem(mesh, 50e-9, 5e-9, [prm], intended_bcs=intended_bcs)
     ref.solver.set_dirichlet(ref.dirichlet_values([float(prm.extras["eq_scaled"][0])]))
     return mesh, prm, parts, pp, ref
 
@@ -128,6 +128,48 @@ def test_partitioned_newton_on_config3_with_distributed_coarse_space(lib):
     out = pp.newton(us, uns, lin_rtol=1e-10, lin_restart=100)
     assert out["converged"] and out["iters"] == int(out_ref["iters"][0])
     assert out["lin_iters"] <= 1.5 * int(out_ref["lin_iters"][0]) + 50, (out["lin_iters"], int(out_ref["lin_iters"][0]))
+    ud = partition.gather_owned(parts, [x[0].cpu().numpy() for x in us], nv)
+    ur = u[0].cpu().numpy()
+    for c in range(9):
+        assert np.linalg.norm(ud[:, c] - ur[:, c]) <= 1e-7 * max(np.linalg.norm(ur[:, c]), 1e-300), c
+
+
+def test_partitioned_mode_with_intended_boundary_integrals(lib):
+    """`--intended_bcs` (3D:474-499) in the mesh-partitioned mode: exit facets are given to every part that owns one
+    of their vertices, wall weights are restricted per vertex; residual, Jacobian action and the damped Newton solve
+    equal the single-mesh path with the same terms -- and differ from the as-executed form."""
+    from gmpnp_b200 import partition
+    from gmpnp_b200._lib import NewtonOpts
+    mesh, prm, parts, pp, ref = _setup(3, intended_bcs=True)
+    rng = np.random.default_rng(8)
+    nv = mesh.x.shape[0]
+    ug = np.ones((nv, 9)); ug[:, 8] = 0.0
+    ug += 0.01 * rng.random((nv, 9))
+    ung = np.ones((nv, 9)); ung[:, 8] = 0.0
+    dev = pp.device
+    Fg, Jg = ref.solver.assemble(torch.as_tensor(ug[None], device=dev), torch.as_tensor(ung[None], device=dev))
+    us, uns = pp.from_global(ug), pp.from_global(ung)
+    Fs, nrm = pp.assemble(us, uns)
+    Fd = partition.gather_owned(parts, [F[0].cpu().numpy() for F in Fs], nv)
+    Fr = Fg[0].cpu().numpy()
+    assert np.abs(Fd - Fr).max() <= 1e-12 * np.abs(Fr).max()
+    xg = rng.normal(size=(nv, 9))
+    yr = ref.solver.spmv(Jg, torch.as_tensor(xg[None], device=dev))[0].cpu().numpy()
+    ys = pp.spmv(pp.from_global(xg))
+    yd = partition.gather_owned(parts, [y[0].cpu().numpy() for y in ys], nv)
+    assert np.abs(yd - yr).max() <= 1e-12 * np.abs(yr).max()
+    ref.solver.set_facet_terms()                                  # as executed: the terms really were in
+    F0, _ = ref.solver.assemble(torch.as_tensor(ug[None], device=dev), torch.as_tensor(ung[None], device=dev), want_J=False)
+    assert np.abs(F0[0].cpu().numpy() - Fr).max() > 1e-3
+    # one reference solve() from u = 0
+    mesh, prm, parts, pp, ref = _setup(2, intended_bcs=True)
+    ug = np.ones((nv, 9)); ug[:, 8] = 0.0
+    u = torch.zeros(1, nv, 9, dtype=torch.float64, device=dev)
+    un = torch.as_tensor(ug[None], device=dev).contiguous()
+    out_ref = ref.solver.newton(u, un, NewtonOpts.reference_3d())
+    us = pp.from_global(ug * 0); uns = pp.from_global(ug)
+    out = pp.newton(us, uns, lin_rtol=1e-10, lin_restart=100)
+    assert out["converged"] and out["iters"] == int(out_ref["iters"][0])
     ud = partition.gather_owned(parts, [x[0].cpu().numpy() for x in us], nv)
     ur = u[0].cpu().numpy()
     for c in range(9):
