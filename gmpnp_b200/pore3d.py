@@ -10,7 +10,8 @@ built with int() truncation.  Additions: ``--utilities_dir`` / ``--out_dir`` ins
 ``--n_steps`` (the reference always runs 1000 steps, of which all but the first few are no-ops once the residual is
 below its 1e-4 tolerance), ``--mesh_file`` override.  The P1 gradient projections (``field_values``, ``*_grad``,
 3D:884-909) are computed on the device (``gmpnp_grad_project_3d``) and written with the reference's keys and
-component-major layout; the PVD files (3D:863-880) are not written.
+component-major layout; the final fields also go to ``solution_{CO,K,H2,CO2,OH,H,HCO3,CO32,p}.pvd`` (3D:863-880,
+``gmpnp_b200/vtkio.py``; ``--no_pvd`` skips them).
 """
 from __future__ import annotations
 
@@ -34,7 +35,7 @@ def solveEDL(concentration_elec=1.0, voltage_multiplier=-1.0, H2_FE=0.05, curren
              cation="K", R=5.0e-9, press_gas=1.0, pore_geom_multiplier=1.0, porosity_eff=0.5, tortuosity_eff=1.5,
              constrictivity_eff=0.9, params_file="parameters_pore", y_CO2=0.95, electrolyte_flow_geom_multiplier=1.0,
              roughness_factor=150.0, *, utilities_dir=None, out_dir=None, n_steps=None, mesh_file=None, device=0,
-             write=True, intended_bcs=False):
+             write=True, intended_bcs=False, pvd=True):
     from . import meshio, params as _params, solver3d
 
     stamp = datetime.now().strftime("%y-%m-%d-%H-%M-%S")
@@ -92,6 +93,12 @@ def solveEDL(concentration_elec=1.0, voltage_multiplier=-1.0, H2_FE=0.05, curren
         np.savez(os.path.join(newpath, "arrays_scaled.npz"), x=mesh.x * L, psi=psi, **scaled)          # 3D:1026-1056
         with open(os.path.join(newpath, "metadata.json"), "w") as f:
             f.write(json.dumps(metadata, indent=0))
+        if pvd:                                                    # File(newpath + '/solution_X.pvd') << _u_X, 3D:863-880
+            from . import vtkio
+            for fname, key in (("CO", "CO"), ("K", "cat"), ("H2", "H2"), ("CO2", "CO2"), ("OH", "OH"), ("H", "H"),
+                               ("HCO3", "HCO3"), ("CO32", "CO32"), ("p", "p")):
+                vtkio.write_pvd(os.path.join(newpath, "solution_" + fname + ".pvd"), mesh.x, mesh.cells,
+                                arrays[key][-1], name=key)
         metadata["output_dir"] = newpath
     pp.solver.close()
     return metadata
@@ -121,6 +128,7 @@ def build_parser():
     p.add_argument("--n_steps", default=None, type=int)
     p.add_argument("--mesh_file", default=None)
     p.add_argument("--device", default=0, type=int)
+    p.add_argument("--no_pvd", dest="pvd", action="store_false", help="do not write the solution_*.pvd files")
     p.add_argument("--intended_bcs", action="store_true",
                    help="add the wall-flux / pore-exit Robin boundary integrals that the reference writes but Python "
                         "discards (3D:474-499, 560-750); default: as executed")

@@ -50,7 +50,7 @@ def params_rxn_diff_3d(concentration_elec=1.0, H2_FE=0.05, current_rough=3000.0,
 def solveEDL(concentration_elec=1.0, H2_FE=0.05, current_rough=3000.0, L=100.0e-9, cation="K", R=5.0e-9,
              press_gas=1.0, pore_geom_multiplier=1.0, porosity_eff=0.5, tortuosity_eff=1.5, constrictivity_eff=0.9,
              params_file="parameters_pore", y_CO2=0.95, electrolyte_flow_geom_multiplier=1.0, roughness_factor=150.0,
-             *, utilities_dir=None, out_dir=None, n_steps=None, mesh_file=None, device=0, write=True):
+             *, utilities_dir=None, out_dir=None, n_steps=None, mesh_file=None, device=0, write=True, pvd=True):
     """Signature of RD3:96-111 plus the keyword-only additions of ``gmpnp_b200.pore3d.solveEDL``."""
     from . import meshio, params as _params, solver3d
     from .pore3d import scale_conc_time
@@ -103,6 +103,10 @@ def solveEDL(concentration_elec=1.0, H2_FE=0.05, current_rough=3000.0, L=100.0e-
         np.savez(os.path.join(newpath, "arrays_scaled.npz"), coor_scaled=mesh.x * L, **scaled)
         with open(os.path.join(newpath, "metadata.json"), "w") as f:
             f.write(json.dumps(metadata, indent=0))
+        if pvd:                                                    # File(newpath + '/solution_X.pvd') << _u_X, RD3:619-632
+            from . import vtkio
+            for n in ("CO", "H2", "CO2", "OH", "H", "HCO3", "CO32"):
+                vtkio.write_pvd(os.path.join(newpath, "solution_" + n + ".pvd"), mesh.x, mesh.cells, arrays[n][-1], name=n)
         metadata["output_dir"] = newpath
     metadata["final_state"] = hist[-1][:, :7]
     pp.solver.close()
@@ -132,6 +136,7 @@ def build_parser():
     p.add_argument("--n_steps", default=None, type=int)
     p.add_argument("--mesh_file", default=None)
     p.add_argument("--device", default=0, type=int)
+    p.add_argument("--no_pvd", dest="pvd", action="store_false", help="do not write the solution_*.pvd files")
     return p
 
 

@@ -217,6 +217,11 @@ def test_solveEDL_drop_in_writes_reference_outputs(lib, tmp_path):
     assert {"x", "psi", "c_H", "t_H", "H_grad", "field_values"} <= set(sc.files)
     md = json.load(open(os.path.join(d, "metadata.json")))
     assert md["newton_iterations"][0] == 6                        # golden count of the first reference step
+    from gmpnp_b200 import vtkio
+    for n in ("CO", "K", "H2", "CO2", "OH", "H", "HCO3", "CO32", "p"):                      # 3D:863-880
+        assert os.path.exists(os.path.join(d, "solution_" + n + ".pvd")), n
+    pts, cells, data = vtkio.read_vtu_point_data(os.path.join(d, "solution_K000000.vtu"))
+    assert pts.shape == (nv, 3) and cells.shape == (17297, 4) and np.array_equal(data["cat"], un["cat"][-1])
 
 
 def test_intended_boundary_integrals_match_oracle(lib):
@@ -275,6 +280,7 @@ def test_rxn_diff_3d_drop_in_matches_independent_oracle(lib, tmp_path):
     md = json.load(open(os.path.join(d, "metadata.json")))
     assert md["CO2_min"] == float(un["CO2"][-1].min()) and md["current_planar"] == 20.0
     assert md["passenger_drift"] <= 1e-12
+    assert sorted(f for f in os.listdir(d) if f.endswith(".pvd")) == sorted("solution_" + n + ".pvd" for n in names)
 
 
 def test_geometry_voltage_sweep_parks_failed_points(lib):
