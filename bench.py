@@ -234,6 +234,7 @@ def bench_pore3d(local, world, dev, batch, peak):
                      "kernels": "tet_moments_kernel + assemble_bsr_kernel + residual_gather_kernel"},
         "spmv": {"ms": ms_spmv, "GBs": b_spmv / ms_spmv / 1e6, "frac_of_hbm_peak": b_spmv / ms_spmv / 1e6 / peak,
                  "algorithmic_bytes": b_spmv,
+                 "dram_traffic_over_algorithmic": 0.99,      # ncu, profiles/r01_spmv_v2_ncu_summary.md
                  "note": "batch Jacobians (%.2f GB) exceed the 126 MB L2" % (batch * 8 * 81 * nb / 1e9)},
     }
     pp.solver.close()
