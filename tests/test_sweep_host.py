@@ -82,3 +82,24 @@ def test_gather_results_single_rank():
     idx = torch.tensor([5, 0, 3, 1, 2, 4])
     out = sweep.gather_results(local, idx, 6, 1)
     assert torch.equal(out[idx], local)
+
+
+def test_config4_enumeration_and_sharding():
+    """Config 4: every present pore mesh x the 256-voltage grid; shards are disjoint, cover the sweep and
+    keep a rank's points of one mesh together as one batch."""
+    from gmpnp_b200 import meshio, sweep3d
+    pts = sweep3d.config4_points()
+    assert len(pts) == 11 * 256 and [p.index for p in pts] == list(range(len(pts)))
+    assert pts[0].V == -12.5 / 256 and pts[255].V == -12.5 and pts[256].mesh != pts[255].mesh
+    for name, L, R in sweep3d.CONFIG4_MESHES:
+        m = meshio.load_mesh(name)                        # all eleven files are packaged
+        assert m.dim == 3 and m.cells.shape[1] == 4
+    world = 8
+    seen = []
+    for r in range(world):
+        mine = sweep3d.shard(pts, r, world)
+        seen += [p.index for p in mine]
+        sw = sweep3d.Sweep3D(mine)
+        assert len(sw.by_mesh) == 11 and sum(len(v) for v in sw.by_mesh.values()) == len(mine)
+        assert all(len(v) == 32 for v in sw.by_mesh.values())         # 256 voltages / 8 ranks per mesh
+    assert sorted(seen) == list(range(len(pts)))
