@@ -10,6 +10,12 @@ is parsed as a real boolean (the reference's ``type=bool`` turns any string into
 the non-dry staged run defines ``time_step`` / ``total_sim_time`` for the metadata (the reference
 crashes with NameError at 1D:971-972); ``--mode steady`` selects the new steady solve with voltage
 continuation (BASELINE.json north_star) instead of the march.
+
+Staging of the non-dry run (1D:271-290, 641-648): the reference means to switch from dt = 1e-5 s to 1e-3 s at
+t = 0.1 s, but it only rebinds the Python name ``del_t`` to a second ``Constant``; the form ``F`` was built with the
+first ``Constant`` object (1D:458 ff.) and is never rebuilt, so all 10 000 + 10 000 steps are integrated with 1e-5 s
+(physical end time 0.2 s) while the stored time axis pretends 10.1 s.  ``staging="as_executed"`` (default) reproduces
+that; ``--staging intended`` uses the two step sizes.  The time axis written to the files is the reference's in both.
 """
 from __future__ import annotations
 
@@ -32,7 +38,7 @@ def scale(species="H", tau=None, C=None, initial_conc=None, diff_coeff=None, L_n
 def solve_EDL(concentration_elec=0.1, model="MPNP", voltage_multiplier=-1.0, H2_FE=0.2,
               mesh_structure="variable", current_OHP_ss=10.0, L_n=50.0e-6, stabilization="N", H_OHP=None,
               cation="K", params_file="parameters", dry_run=True, *, utilities_dir=None, out_dir=None,
-              mode="march", device=0, n_steps=None, write=True):
+              mode="march", device=0, n_steps=None, write=True, staging="as_executed"):
     import torch
     from . import meshio, params as _params, solver1d
     from ._lib import NewtonOpts
@@ -80,10 +86,12 @@ def solve_EDL(concentration_elec=0.1, model="MPNP", voltage_multiplier=-1.0, H2_
                 ns = min(ns, n_steps - sum(len(p) for p in tau_parts)) if tau_parts else min(ns, n_steps)
             if ns <= 0:
                 break
+            # the step size that is IN THE FORM: the first stage's for every stage as executed (module docstring)
+            dt_form = time_step if staging == "intended" else stages[0][0]
             p_stage = _params.params_1d(concentration_elec=concentration_elec, model=model,
                                         voltage_multiplier=voltage_multiplier, H2_FE=H2_FE,
                                         current_OHP_ss=current_OHP_ss, L_n=L_n, H_OHP=H_OHP, cation=cation,
-                                        params_file=params_file, utilities_dir=utilities_dir, time_step=time_step,
+                                        params_file=params_file, utilities_dir=utilities_dir, time_step=dt_form,
                                         current_H_frac=current_H_frac)
             p_stage.extras["H_OHP"] = H_OHP
             solver.set_params([p_stage])
@@ -229,6 +237,9 @@ def build_parser():
     parser.add_argument("--utilities_dir", default=None, help="folder with the reference's utilities/ files")
     parser.add_argument("--out_dir", default=None, help="output base folder (default ./out)")
     parser.add_argument("--mode", default="march", choices=["march", "steady"])
+    parser.add_argument("--staging", default="as_executed", choices=["as_executed", "intended"],
+                        help="non-dry run: keep dt = 1e-5 s in the form for all 20000 steps as the reference does "
+                             "(its del_t rebinding never reaches the form), or switch to 1e-3 s at t = 0.1 s")
     parser.add_argument("--device", default=0, type=int)
     return parser
 
@@ -240,7 +251,7 @@ def main(argv=None):
                      H2_FE=args.H2_FE, current_OHP_ss=args.current_OHP_ss, L_n=args.L_n,
                      stabilization=args.stabilization, H_OHP=args.H_OHP, cation=args.cation,
                      params_file=args.params_file, dry_run=args.dry_run, utilities_dir=args.utilities_dir,
-                     out_dir=args.out_dir, mode=args.mode, device=args.device)
+                     out_dir=args.out_dir, mode=args.mode, device=args.device, staging=args.staging)
     print(json.dumps({k: meta[k] for k in ("field_OHP", "eps_rel_OHP", "pH_OHP", "potential_OHP", "output_dir")}))
 
 

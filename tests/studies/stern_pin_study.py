@@ -88,12 +88,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20000)
     ap.add_argument("--every", type=int, default=250)
     ap.add_argument("--cation", default="K")
+    ap.add_argument("--dt", type=float, default=1.0e-5, help="time step in s (the reference: 1e-5)")
     ap.add_argument("--out", default=None)
     ap.add_argument("--check", type=int, default=0, help="compare the first N steps with oracle.solver.march_1d")
     a = ap.parse_args()
     m = meshio.load_mesh("1D_variable_50um_mesh_5990")
     x = m.x[:, 0]
-    prm = params.params_1d(voltage_multiplier=a.V, cation=a.cation)
+    prm = params.params_1d(voltage_multiplier=a.V, cation=a.cation, time_step=a.dt)
     bn = BandedNewton(x, prm)
     nv = len(x)
     if a.check:
@@ -115,7 +116,7 @@ def main():
         if n % a.every == 0 or n == a.steps or n in (1, 10, 100):
             f, e = ohp_metrics(x, u.reshape(nv, 7), prm)
             gE, ge = STERN.get(a.V, (float("nan"), float("nan")))
-            out.write(json.dumps({"V": a.V, "step": n, "t_s": n * 1e-5, "field_OHP": f, "eps_rel_OHP": e,
+            out.write(json.dumps({"V": a.V, "step": n, "t_s": n * a.dt, "field_OHP": f, "eps_rel_OHP": e,
                                   "field_rel_dev": f / gE - 1, "eps_rel_dev": e / ge - 1, "newton_total": tot,
                                   "wall_s": round(time.time() - t0, 1)}) + "\n")
             out.flush()

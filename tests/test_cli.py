@@ -10,6 +10,7 @@ def test_1d_cli_flags_and_defaults_match_reference():
     assert (a.concentration_elec, a.model, a.voltage_multiplier, a.mesh_structure) == (0.1, "MPNP", -1.0, "variable")
     assert (a.H2_FE, a.current_OHP_ss, a.L_n, a.stabilization, a.H_OHP) == (0.2, 10.0, 50.0e-6, "N", None)
     assert (a.cation, a.params_file, a.dry_run) == ("K", "parameters", True)
+    assert a.staging == "as_executed" and inspect.signature(edl1d.solve_EDL).parameters["staging"].default == "as_executed"
     b = edl1d.build_parser().parse_args(["--voltage_multiplier=-10.0", "--cation=Cs", "--dry_run", "False", "--H_OHP", "1.1"])
     assert b.voltage_multiplier == -10.0 and b.cation == "Cs" and b.dry_run is False and b.H_OHP == 1.1
     sig = inspect.signature(edl1d.solve_EDL)
