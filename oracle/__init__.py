@@ -7,10 +7,13 @@ NewtonSolver semantics.  Only ``tests/``,
 ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
 legs may import it; nothing under ``gmpnp_b200/`` does.
 
-PARITY UNPINNED: the arithmetic of the reference lives in un-vendored third-party
-packages (fenics-dolfin/ffc/ufl/fiat 2019.1.0, petsc 3.12.3, mumps 5.2.1,
-suitesparse 5.6.0 -- environment.yml:21-27,78,86,110) that can be neither imported
-nor built in this container, and the reference has no tests or golden outputs for
-this path.  The only numbers it holds are the five soft (field_OHP, eps_rel_OHP)
-pairs in 1D/Stern_CO2ER.py:66-68, which this oracle brackets (tests/test_oracle_1d.py).
+PARITY: the arithmetic of the reference lives in un-vendored third-party packages
+(fenics-dolfin/ffc/ufl/fiat 2019.1.0, petsc 3.12.3, mumps 5.2.1, suitesparse 5.6.0 --
+environment.yml:21-27,78,86,110) that can be neither imported nor built in this container, and
+the reference has no tests.  1D PATH PINNED: the only result values it holds, the five
+(field_OHP, eps_rel_OHP) pairs in 1D/Stern_CO2ER.py:66-68, are reproduced by this oracle to 9-10
+digits (state of the default non-dry run at t = 0.2 s; tests/golden/stern_pin_results.json,
+tests/test_oracle_1d.py).  3D PATH UNPINNED (no reference output exists for it): it shares forms.py
+with the 1D path and is checked by identities, Jacobian consistency and an independent second
+restatement (oracle/rxn_diff3d.py) only.
 """

@@ -43,10 +43,10 @@ def ohp_metrics(x, u, prm):
 
 
 class BandedNewton:
-    def __init__(self, x, prm):
+    def __init__(self, x, prm, jac_rule=0):
         nv = len(x)
         cells = np.stack([np.arange(nv - 1), np.arange(1, nv)], axis=1)
-        self.disc = solver.Discretisation(x, cells, 7)
+        self.disc = solver.Discretisation(x, cells, 7, jac_rule=jac_rule)
         self.prm = prm
         self.bd, self.bv = solver.bc_1d(nv, 7, prm.V)
         n = self.disc.ndof
@@ -82,6 +82,33 @@ class BandedNewton:
         return x, k, conv
 
 
+def march_to(V, t_end=0.2, dt=1.0e-5, dt2=4.0e-3, n1=5, grow=1.5, jac_rule=1, cation="K"):
+    """Backward-Euler march of the default configuration from u = 0 to ``t_end``: ``n1`` steps of ``dt`` (the
+    reference's step), then the step grows by ``grow`` per step up to ``dt2`` and lands exactly on ``t_end``.
+    Returns (field_OHP, eps_rel_OHP, steps, Newton iterations)."""
+    m = meshio.load_mesh("1D_variable_50um_mesh_5990")
+    x = m.x[:, 0]
+    nv = len(x)
+    prm = params.params_1d(voltage_multiplier=V, cation=cation, time_step=dt)
+    bn = BandedNewton(x, prm, jac_rule)
+    u = np.zeros(bn.n)
+    un = np.tile(np.array([1.0] * 6 + [0.0]), nv)
+    t, dt_cur, n, tot = 0.0, dt, 0, 0
+    while t_end - t > 1e-15:
+        n += 1
+        if n > n1:
+            dt_cur = min(dt2, dt_cur * grow, t_end - t)
+            bn.prm = prm = params.params_1d(voltage_multiplier=V, cation=cation, time_step=dt_cur)
+        t += dt_cur
+        u, k, conv = bn.newton(u, un, prm.jflux)
+        if not conv:
+            raise RuntimeError(f"Newton failed in step {n}")
+        tot += k
+        un = u.copy()
+    f, e = ohp_metrics(x, u.reshape(nv, 7), prm)
+    return f, e, n, tot
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--V", type=float, default=-2.5)
@@ -89,13 +116,18 @@ def main():
     ap.add_argument("--every", type=int, default=250)
     ap.add_argument("--cation", default="K")
     ap.add_argument("--dt", type=float, default=1.0e-5, help="time step in s (the reference: 1e-5)")
+    ap.add_argument("--dt2", type=float, default=0.0, help="feasibility mode: after --n1 steps of --dt continue with this step")
+    ap.add_argument("--n1", type=int, default=100)
+    ap.add_argument("--grow", type=float, default=1.25, help="feasibility mode: dt grows by this factor per step up to --dt2")
+    ap.add_argument("--t_end", type=float, default=0.2, help="feasibility mode: stop exactly at this physical time")
+    ap.add_argument("--jac_rule", type=int, default=0, help="1: consistent Jacobian (same step solutions, fewer iterations)")
     ap.add_argument("--out", default=None)
     ap.add_argument("--check", type=int, default=0, help="compare the first N steps with oracle.solver.march_1d")
     a = ap.parse_args()
     m = meshio.load_mesh("1D_variable_50um_mesh_5990")
     x = m.x[:, 0]
     prm = params.params_1d(voltage_multiplier=a.V, cation=a.cation, time_step=a.dt)
-    bn = BandedNewton(x, prm)
+    bn = BandedNewton(x, prm, a.jac_rule)
     nv = len(x)
     if a.check:
         hist, its, _ = solver.march_1d(x, prm, a.check)
@@ -104,7 +136,17 @@ def main():
     out = open(a.out, "w") if a.out else sys.stdout
     t0 = time.time()
     tot = 0
+    t_phys, dt_cur = 0.0, a.dt
     for n in range(1, a.steps + 1):
+        if a.dt2 > 0 and n > a.n1:
+            # feasibility mode: grow the step gently to dt2 and land exactly on t_end
+            dt_cur = min(a.dt2, dt_cur * a.grow, a.t_end - t_phys)
+            if dt_cur <= 1e-15:
+                break
+            prm = params.params_1d(voltage_multiplier=a.V, cation=a.cation, time_step=dt_cur)
+            bn.prm = prm
+        t_phys += dt_cur
+        last = a.dt2 > 0 and abs(t_phys - a.t_end) < 1e-12
         u, k, conv = bn.newton(u, un, prm.jflux)
         if not conv:
             raise RuntimeError(f"Newton failed in step {n}")
@@ -113,10 +155,10 @@ def main():
             d = np.abs(u.reshape(nv, 7) - hist[n]).max()
             print(f"step {n}: its {k} (oracle {its[n - 1]}), max |diff| vs oracle.march_1d {d:.2e}", file=sys.stderr)
         un = u.copy()
-        if n % a.every == 0 or n == a.steps or n in (1, 10, 100):
+        if n % a.every == 0 or n == a.steps or n in (1, 10, 100) or last:
             f, e = ohp_metrics(x, u.reshape(nv, 7), prm)
             gE, ge = STERN.get(a.V, (float("nan"), float("nan")))
-            out.write(json.dumps({"V": a.V, "step": n, "t_s": n * a.dt, "field_OHP": f, "eps_rel_OHP": e,
+            out.write(json.dumps({"V": a.V, "step": n, "t_s": t_phys, "field_OHP": f, "eps_rel_OHP": e,
                                   "field_rel_dev": f / gE - 1, "eps_rel_dev": e / ge - 1, "newton_total": tot,
                                   "wall_s": round(time.time() - t0, 1)}) + "\n")
             out.flush()

@@ -127,3 +127,24 @@ def test_h_ohp_ladder_branches():
     assert f(0.001, 1.2, 1.1) == 0.001 * 1.04
     assert f(0.001, 1.6, 1.1) == 0.001 * 1.15
     assert f(0.001, 1.09, 1.1) == 0.001
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("V", [-2.5, -10.0])
+def test_oracle_reproduces_the_reference_stern_table(V):
+    """PINNED AGAINST THE REFERENCE'S OWN NUMBERS.  The (field_OHP, eps_rel_OHP) pairs pasted into
+    1D/Stern_CO2ER.py:66-68 are the output of the default non-dry run of 1D/MPNP_CO2ER_EDL.py, which integrates
+    20 000 steps of 1e-5 s (the `del_t` rebinding at 1D:643-646 never reaches the form), i.e. the state at t = 0.2 s.
+    The oracle's backward-Euler march from u = 0 to t = 0.2 s reproduces them: to 1e-7 with steps of 1e-4 s, to
+    (3e-8, extrapolated) with the reference's own step (tests/golden/stern_pin_results.json, generated by
+    tests/studies/stern_pin_study.py over ~2 h of CPU); here a 67-step march, good to 5e-5 (first-order in dt)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("stern_pin_study",
+                                                  os.path.join(os.path.dirname(__file__), "studies", "stern_pin_study.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    f, e, steps, its = mod.march_to(V)
+    E, eps = STERN[V]
+    assert abs(f / E - 1) < 5e-5, (f, E)
+    assert abs(e / eps - 1) < 1e-5, (e, eps)
+    assert steps < 100
