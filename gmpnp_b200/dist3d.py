@@ -143,11 +143,8 @@ class PartitionedPore:
             agg = np.ascontiguousarray(agg, dtype=np.int32)
             check(s.lib.gmpnp_set_aggregates_3d(s._h, agg.ctypes.data_as(C.POINTER(C.c_int))), s._h)
             if self.intended_bcs:
-                g2l = -np.ones(mesh.x.shape[0], dtype=np.int64)
-                g2l[p.glob] = np.arange(p.n_local)
-                lf = g2l[np.asarray(exit_f, dtype=np.int64).reshape(-1, 3)]
-                keep = (lf >= 0).all(axis=1) & ((lf >= 0) & (lf < p.n_own)).any(axis=1)
-                s.set_facet_terms(wall_w[p.glob], lf[keep].astype(np.int32), np.asarray(exit_a)[keep],
+                lf, sel_f = _part.local_facets(p, exit_f, mesh.x.shape[0])
+                s.set_facet_terms(wall_w[p.glob], lf, np.asarray(exit_a)[sel_f],
                                   prm.extras["J_wall"][None, :], prm.extras["k_exit"][None, :])
             self.solvers.append(s)
             self.dir_sel.append(sel)

@@ -133,6 +133,18 @@ def local_dirichlet(part: MeshPart, dofs: np.ndarray, ncomp: int = 9):
     return ld[order].astype(np.int32), sel[order]
 
 
+def local_facets(part: MeshPart, facets: np.ndarray, n_global: int):
+    """Boundary facets (global vertex ids, [nf, 3]) a part must integrate: those with at least one OWNED vertex --
+    the tet behind such a facet touches an owned vertex, so it is local and all three vertices exist locally.  Every
+    owned row then receives every facet that touches it; ghost rows stay incomplete and are never used.
+    Returns (local vertex ids [k, 3] int32, indices into ``facets``)."""
+    g2l = -np.ones(n_global, dtype=np.int64)
+    g2l[part.glob] = np.arange(part.n_local)
+    lf = g2l[np.asarray(facets, dtype=np.int64).reshape(-1, 3)]
+    keep = (lf >= 0).all(axis=1) & ((lf >= 0) & (lf < part.n_own)).any(axis=1)
+    return lf[keep].astype(np.int32), np.nonzero(keep)[0]
+
+
 def scatter_to_part(part: MeshPart, xg: np.ndarray) -> np.ndarray:
     """Global nodal array [nv, ...] -> local array [n_local, ...] (owned and ghost slots filled)."""
     return np.ascontiguousarray(xg[part.glob])

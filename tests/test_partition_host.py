@@ -99,3 +99,24 @@ def test_halo_exchange_and_allreduce_gloo_world2():
         assert ok_halo, rank
         assert abs(tot[0] - ref) <= 1e-12 * ref and tot[1] == nv
         assert hb == hb_expected > 0
+
+
+def test_local_facets_give_every_owned_vertex_all_its_boundary_facets():
+    """Intended boundary integrals in the partitioned mode: a part integrates the exit facets that touch one of its
+    OWNED vertices; all their vertices are local, and per owned vertex the facet set equals the global one."""
+    from gmpnp_b200 import marking, meshio, partition
+    mesh = meshio.load_mesh("L_10_R_5")
+    _, ef, ea = marking.facet_terms(mesh, 10e-9, 5e-9)
+    nv = mesh.x.shape[0]
+    glob_cnt = np.bincount(ef.ravel(), minlength=nv)
+    for world in (2, 5):
+        parts = partition.partition_z(mesh, world)
+        covered = np.zeros(len(ef), dtype=int)
+        for p in parts:
+            lf, sel = partition.local_facets(p, ef, nv)
+            assert lf.shape[1] == 3 and (len(lf) == 0 or (lf.min() >= 0 and lf.max() < p.n_local))
+            assert np.array_equal(p.glob[lf], ef[sel])                      # same facets, local numbering
+            covered[sel] += 1
+            cnt = np.bincount(lf.ravel(), minlength=p.n_local)[: p.n_own]
+            assert np.array_equal(cnt, glob_cnt[p.glob[: p.n_own]])         # owned rows see all their facets
+        assert covered.min() >= 1                                            # the exit disc sits in the last slab(s)
