@@ -135,8 +135,8 @@ def test_oracle_reproduces_the_reference_stern_table(V):
     """PINNED AGAINST THE REFERENCE'S OWN NUMBERS.  The (field_OHP, eps_rel_OHP) pairs pasted into
     1D/Stern_CO2ER.py:66-68 are the output of the default non-dry run of 1D/MPNP_CO2ER_EDL.py, which integrates
     20 000 steps of 1e-5 s (the `del_t` rebinding at 1D:643-646 never reaches the form), i.e. the state at t = 0.2 s.
-    The oracle's backward-Euler march from u = 0 to t = 0.2 s reproduces them: to 1e-7 with steps of 1e-4 s, to
-    (3e-8, extrapolated) with the reference's own step (tests/golden/stern_pin_results.json, generated by
+    The oracle's backward-Euler march from u = 0 to t = 0.2 s reproduces them: to 3e-13 by the literal 20 000-step
+    replay at V = -2.5, to 1e-7 with steps of 1e-4 s and to 3e-10 extrapolated to the reference's own step at all five voltages (tests/golden/stern_pin_results.json, generated by
     tests/studies/stern_pin_study.py over ~2 h of CPU); here a 67-step march, good to 5e-5 (first-order in dt)."""
     import importlib.util
     spec = importlib.util.spec_from_file_location("stern_pin_study",
