@@ -1,23 +1,36 @@
 #!/usr/bin/env python
 """Benchmark of the GMPNP hot path: steady solves/sec on the 1D parameter sweep (BASELINE.json
-config 2: {K,Cs} x 256 voltages x {0.1,0.5,1.0} M x 5 meshes = 7680 steady problems per GPU).
+config 2: {K,Cs} x 256 voltages x {0.1,0.5,1.0} M x 5 meshes = 7680 steady problems).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 A "step" = one pass of the hot path over the whole batch: every sweep point goes from the bulk
 state to its converged steady solution (voltage continuation + Newton, all inside the CUDA
-kernels).  Prints ONE JSON line (see the task contract): `value` = solves/s with inputs resident
-in HBM, `e2e` = the same through the public host API with host buffers (H2D of parameters and
-continuation paths, D2H of every solution profile inside the timed region), `roofline` for the
-fused assemble+eliminate kernel, `cpu_baseline` = the oracle on the box's host cores.
+kernels; points that end at the round-off floor are polished with the pivoted elimination and
+failed points retried INSIDE the step).  Prints ONE JSON line (see the task contract):
+`value` = solves/s with inputs resident in HBM, `e2e` = the same through the public host API with
+host buffers (H2D of parameters and continuation paths, D2H of every solution profile and the
+gather of the per-point summaries inside the timed region), `roofline` for the fused
+assemble+eliminate kernel, `cpu_baseline` = the oracle on the box's host cores and `parity` =
+the GPU solutions of the sampled sweep points against the oracle's (the bench fails if they
+differ by more than 1e-8).  Headline = weak scaling (every rank owns a full 7680-point sweep);
+for N > 1 the same line carries `strong` (the 7680 points of config 2 sharded over the N ranks,
+per-point summaries gathered over NCCL).
 """
-import argparse
-import json
 import os
-import subprocess
-import sys
-import threading
-import time
+
+# before NumPy/SciPy are imported anywhere (this process and the spawned CPU workers inherit it): the CPU arm
+# runs one single-threaded oracle solve per host core
+os.environ.setdefault("OMP_NUM_THREADS", "1")
+os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+os.environ.setdefault("MKL_NUM_THREADS", "1")
+
+import argparse  # noqa: E402
+import json  # noqa: E402
+import subprocess  # noqa: E402
+import sys  # noqa: E402
+import threading  # noqa: E402
+import time  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -25,6 +38,7 @@ sys.path.insert(0, ROOT)
 METRIC = "GMPNP steady solves/sec (1D sweep)"
 UNIT = "solves/s"
 WORKLOAD = "config2: 1D GMPNP sweep {K,Cs} x 256 V x {0.1,0.5,1.0} M KHCO3 x 5 meshes = 7680 steady solves per GPU"
+PARITY_TOL = 1.0e-8        # north_star: relative L2 <= 1e-8 on concentrations and potential
 
 
 def parse():
@@ -34,71 +48,139 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--voltages", type=int, default=256, help="voltage points per chain (256 = config 2)")
-    ap.add_argument("--cpu-sample", type=int, default=16, help="sweep points timed on the CPU baseline")
+    ap.add_argument("--cpu-sample", type=int, default=2,
+                    help="b200 arm: sweep points PER CHAIN (30 chains = cation x concentration x mesh) solved by the "
+                         "CPU oracle for cpu_baseline and the parity block")
+    ap.add_argument("--ref-sample", type=int, default=16,
+                    help="reference arm: sweep points per step (a different stratified slice every step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pore3d-batch", type=int, default=128, help="3D pore problems per GPU in the 3D part (0: skip)")
+    ap.add_argument("--no-config1", action="store_true", help="skip the config-1 latency measurement")
     ap.add_argument("--pivot", type=int, default=0, help="partial pivoting inside the 7x7 blocks (0: none; "
-                    "non-converged points are retried with pivoting, see Sweep1D)")
+                    "stalled points are polished / failed points retried with pivoting, see Sweep1D)")
     ap.add_argument("--dv", type=float, default=0.75, help="largest voltage increment of the continuation [V_T]")
     ap.add_argument("--xtol-path", type=float, default=1.0,
                     help="increment tolerance of the intermediate continuation stages (1.0 = one Newton corrector "
                          "per voltage increment); the final stage always converges to xtol = 1e-12")
+    ap.add_argument("--scaling", default="both", choices=["weak", "strong", "both"],
+                    help="N > 1: which arms to run (the headline is always the weak one)")
     return ap.parse_args()
+
+
+def base_config(args):
+    """Workload description shared verbatim by both arms (b200 and reference)."""
+    return {"workload": WORKLOAD if args.voltages == 256 else f"reduced sweep ({args.voltages} V/chain)",
+            "continuation": f"dV<={args.dv:g} V_T, one Newton corrector per increment (xtol_path {args.xtol_path:g}), "
+                            "xtol 1e-12 at the target voltage, consistent Jacobian (jac_rule 1)",
+            "points_total_config2": 30 * args.voltages}
 
 
 # --------------------------------------------------------------------------------------------
 # CPU arm: the oracle (port of the reference's algorithm class: P1 assembly + sparse LU + Newton)
 # --------------------------------------------------------------------------------------------
-def _cpu_solve_point(args):
-    cation, conc, L_n, V, dv, xtol_path = args
+_WORKER = {}
+
+
+def _worker_init():
+    """Runs once per pool worker, outside every timed region: imports (NumPy/SciPy only, no torch) and caches."""
+    import numpy as np  # noqa: F401
+    import scipy.sparse.linalg  # noqa: F401
+    from gmpnp_b200 import meshio, params  # noqa: F401
+    from gmpnp_b200 import sweep_points  # noqa: F401
+    from oracle import solver  # noqa: F401
+    assert "torch" not in sys.modules
+    _WORKER["mesh"] = {}
+
+
+def _cpu_solve_point(task):
+    cation, conc, L_n, V, dv, xtol_path, want_u = task
     import numpy as np
     from gmpnp_b200 import meshio, params
-    from gmpnp_b200.sweep import voltage_paths
+    from gmpnp_b200.sweep_points import voltage_paths
     from oracle import solver as osolver
-    os.environ["OMP_NUM_THREADS"] = "1"
-    mesh = meshio.load_mesh(params.mesh_name_1d(L_n))
+    cache = _WORKER.setdefault("mesh", {})
+    if L_n not in cache:
+        cache[L_n] = meshio.load_mesh(params.mesh_name_1d(L_n)).x[:, 0].copy()
+    x = cache[L_n]
     prm = params.params_1d(concentration_elec=conc, cation=cation, L_n=L_n, voltage_multiplier=V)
     path = voltage_paths(np.array([V]), dv)[0]
     path = path[~np.isnan(path)]
+    info = {}
     t = time.perf_counter()
     try:
-        u, its = osolver.steady_1d(mesh.x[:, 0], prm, path, xtol=1e-12, xtol_path=xtol_path, jac_rule=1)
+        u, its = osolver.steady_1d(x, prm, path, xtol=1e-12, xtol_path=xtol_path, jac_rule=1, info=info)
         ok = True
     except RuntimeError:
-        its, ok = [], False
-    return time.perf_counter() - t, sum(its), ok
+        u, its, ok = None, [], False
+    dt = time.perf_counter() - t
+    return dict(t=dt, its=[int(k) for k in its], ok=ok, u=(u if (want_u and ok) else None),
+                assembly=info.get("assembly", 0.0), lu=info.get("lu", 0.0), n=len(x))
 
 
-def cpu_sample_points(n_sample, n_voltages, dv=0.75, xtol_path=1.0):
+def stratified_points(per_chain, n_voltages, seed=0):
+    """`per_chain` sweep points of every (mesh, concentration, cation) chain, voltages drawn without replacement."""
     import numpy as np
-    from gmpnp_b200.sweep import config2_points
+    from gmpnp_b200.sweep_points import config2_points
     pts = config2_points(n_voltages)
-    rng = np.random.default_rng(0)
-    sel = rng.choice(len(pts), size=min(n_sample, len(pts)), replace=False)
-    return [(pts[i].cation, pts[i].conc, pts[i].L_n, pts[i].V, dv, xtol_path) for i in sorted(sel)]
+    chains = {}
+    for p in pts:
+        chains.setdefault((p.L_n, p.conc, p.cation), []).append(p)
+    rng = np.random.default_rng(seed)
+    out = []
+    for key in sorted(chains):
+        c = chains[key]
+        for j in rng.choice(len(c), size=min(per_chain, len(c)), replace=False):
+            out.append(c[int(j)])
+    return out
 
 
-def run_cpu(n_sample, n_voltages, cores=None, dv=0.75, xtol_path=1.0):
-    import multiprocessing as mp
-    cores = cores or (os.cpu_count() or 1)
-    cores = max(1, min(cores, n_sample))
-    work = cpu_sample_points(n_sample, n_voltages, dv, xtol_path)
-    t = time.perf_counter()
-    with mp.get_context("spawn").Pool(cores) as pool:
-        res = pool.map(_cpu_solve_point, work, chunksize=1)
-    wall = time.perf_counter() - t
-    n_ok = sum(1 for r in res if r[2])
-    return dict(value=len(work) / wall, unit=UNIT, cores=cores, kind="port",
-                sample=f"{len(work)} of the {7680 if n_voltages == 256 else 30 * n_voltages} sweep points (seed 0), "
-                       f"oracle steady_1d (NumPy assembly + SuperLU, same continuation and Jacobian rule as the GPU arm), "
-                       f"{n_ok} converged, wall {wall:.1f} s",
-                newton_iterations=int(sum(r[1] for r in res)))
+class CpuPool:
+    """One persistent process pool for the CPU arm (created and warmed outside the timed regions)."""
+
+    def __init__(self, cores=None):
+        import multiprocessing as mp
+        self.cores = max(1, cores or (os.cpu_count() or 1))
+        self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_worker_init)
+        # touch every worker once (imports done, meshes cached lazily)
+        self.pool.map(_noop, range(4 * self.cores), chunksize=1)
+
+    def solve(self, points, dv, xtol_path, want_u=False):
+        work = [(p.cation, p.conc, p.L_n, p.V, dv, xtol_path, want_u) for p in points]
+        # longest first (LPT) so the tail of the sample does not idle the cores
+        order = sorted(range(len(work)), key=lambda i: -abs(work[i][3]) * (1 + 1e6 * work[i][2]))
+        t = time.perf_counter()
+        res = self.pool.map(_cpu_solve_point, [work[i] for i in order], chunksize=1)
+        wall = time.perf_counter() - t
+        out = [None] * len(work)
+        for i, r in zip(order, res):
+            out[i] = r
+        return out, wall
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def _noop(i):
+    return i
+
+
+def cpu_summary(res, wall, cores, n_points, what):
+    n_ok = sum(1 for r in res if r["ok"])
+    its = sum(sum(r["its"]) for r in res)
+    rows = sum(sum(r["its"]) * r["n"] for r in res)
+    asm, lu = sum(r["assembly"] for r in res), sum(r["lu"] for r in res)
+    return dict(value=n_points / wall, unit=UNIT, cores=cores, kind="port",
+                sample=f"{what}; oracle steady_1d (NumPy assembly + SuperLU, same continuation and Jacobian rule as the "
+                       f"GPU arm), one single-threaded solve per core, persistent pool, {n_ok} converged, wall {wall:.1f} s",
+                newton_iterations=int(its),
+                per_newton_iteration_ms={"assembly": 1e3 * asm / max(1, its), "sparse_lu": 1e3 * lu / max(1, its),
+                                         "mean_nodes": rows / max(1, its)})
 
 
 def _cpu_newton_iteration_3d(_):
     """One damped-Newton iteration of config 3 on the CPU oracle: P1 assembly of F and J (NumPy) + sparse LU
     (SuperLU; the reference uses MUMPS, 3D:792) + solve."""
-    os.environ["OMP_NUM_THREADS"] = "1"
     import numpy as np
     import scipy.sparse.linalg as spla
     from gmpnp_b200 import marking, meshio, params
@@ -114,44 +196,65 @@ def _cpu_newton_iteration_3d(_):
     t = time.perf_counter()
     b = osolver.apply_bc_residual(disc.residual(u, un, p3), u, dofs.astype(np.int64), vals)
     A = osolver.apply_bc_matrix(disc.jacobian(u, p3), dofs.astype(np.int64))
+    t1 = time.perf_counter()
     dx = spla.splu(A).solve(b)
-    return time.perf_counter() - t, float(np.abs(dx).max())
+    t2 = time.perf_counter()
+    return t2 - t, t1 - t, t2 - t1, float(np.abs(dx).max())
 
 
-def run_cpu_3d(newton_per_solve, cores=None):
+def run_cpu_3d(pool, newton_per_solve):
     """Bounded CPU sample of the 3D workload: ONE Newton iteration per process on up to 8 host cores at once;
     steady solves/s is extrapolated with the Newton count per steady solve measured on the GPU arm."""
-    import multiprocessing as mp
-    cores = max(1, min(cores or (os.cpu_count() or 1), 8))
+    cores = max(1, min(pool.cores, 8))
     t = time.perf_counter()
-    with mp.get_context("spawn").Pool(cores) as pool:
-        res = pool.map(_cpu_newton_iteration_3d, range(cores), chunksize=1)
+    res = pool.pool.map(_cpu_newton_iteration_3d, range(cores), chunksize=1)
     wall = time.perf_counter() - t
     per_it = sum(r[0] for r in res) / len(res)
     return dict(value=cores / (per_it * newton_per_solve), unit="steady solves/s (extrapolated)", cores=cores, kind="port",
                 sample=f"one damped-Newton iteration of config 3 (NumPy assembly + SuperLU of 33111 DOFs) per core on {cores} "
-                       f"cores at once: {per_it:.1f} s per iteration, wall {wall:.1f} s; x {newton_per_solve} iterations per steady solve")
+                       f"cores at once: {per_it:.1f} s per iteration (assembly {sum(r[1] for r in res) / len(res):.1f} s, "
+                       f"LU {sum(r[2] for r in res) / len(res):.1f} s), wall {wall:.1f} s; x {newton_per_solve} iterations "
+                       "per steady solve")
+
+
+def _cpu_config1(n_steps):
+    from gmpnp_b200 import meshio, params
+    from oracle import solver as osolver
+    x = meshio.load_mesh("1D_variable_50um_mesh_5990").x[:, 0]
+    prm = params.params_1d()
+    t = time.perf_counter()
+    _hist, its, _ = osolver.march_1d(x, prm, n_steps)
+    return time.perf_counter() - t, [int(k) for k in its]
 
 
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals = []
-    for _ in range(args.warmup if args.warmup < 1 else 1):
-        run_cpu(min(args.cpu_sample, os.cpu_count() or 1), args.voltages, dv=args.dv, xtol_path=args.xtol_path)
-    info = None
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        info = run_cpu(args.cpu_sample, args.voltages, dv=args.dv, xtol_path=args.xtol_path)
-        vals.append(info["value"])
-    T = (time.perf_counter() - t0) / max(1, args.steps)
-    v = sum(vals) / len(vals)
+    pool = CpuPool()
+    per_chain = max(1, (args.ref_sample * max(1, args.steps + 1) + 29) // 30)
+    pts = stratified_points(per_chain, args.voltages, seed=1)
+    import numpy as np
+    np.random.default_rng(2).shuffle(pts)
+    step_pts = [pts[i * args.ref_sample:(i + 1) * args.ref_sample] for i in range(args.steps + 1)]
+    if min(args.warmup, 1):
+        pool.solve(step_pts[args.steps], args.dv, args.xtol_path)       # warm-up step (meshes cached in the workers)
+    # the K steps' samples are independent sweep points (the reference: one process per point, README.md:37), so they
+    # stream through the pool without a barrier between steps; ms_per_step = total wall / K
+    timed = [p for k in range(args.steps) for p in step_pts[k]]
+    n_pts = len(timed)
+    res_all, T = pool.solve(timed, args.dv, args.xtol_path)
+    pool.close()
+    v = n_pts / T
+    info = cpu_summary(res_all, T, pool.cores, n_pts,
+                       f"{n_pts} of the {30 * args.voltages} sweep points: every step a different slice of "
+                       f"{args.ref_sample} points, stratified over the 30 (mesh, concentration, cation) chains (seed 1)")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": T * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "CPU oracle port (FEniCS is not installable here); each step "
-                       "= a bounded sample of the sweep on all host cores"},
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": T / max(1, args.steps) * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": base_config(args),
+            "note": "CPU oracle port (FEniCS is not installable here: DESIGN.md section 4); each step = a bounded "
+                    "sample of the sweep on all host cores",
             "cpu_baseline": dict(info, value=v),
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -207,7 +310,6 @@ def bench_pore3d(local, world, dev, batch, peak):
     b_asm = batch * (8 * 81 * nb + 8 * 9 * Vn + 2 * 8 * 9 * Vn + 8 * 3 * Vn + 4 * 4 * T + 4 * 16 * T)
     b_spmv = batch * (8 * 81 * nb + 4 * nb + 4 * (Vn + 1) + 2 * 8 * 9 * Vn)
     del F, J, x
-    l0 = s.launch_count()
     o3 = NewtonOpts.sweep_3d()
     pp.steady(opts=o3, tol=1e-8, max_steps=3)             # warm-up (allocations of the Krylov basis)
     sync()
@@ -221,23 +323,74 @@ def bench_pore3d(local, world, dev, batch, peak):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_steady = float(t[0])
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp))
+    n_conv = int(batch if out.get("converged") is None else int(np.sum(out["converged"])))
     res = {
         "workload": f"config3 batch: L_50_R_5 (V=3679, T=17297, 33111 DOFs), {batch} wall voltages in [-0.5,-1.25] V_T per GPU, "
                     "pseudo-time march to steady state (increment <= 1e-8); damped Newton (relaxation 0.9, residual "
                     "criterion 1e-4 as 3D:789-798), GMRES(40) to 1e-8 + block-Jacobi + z-slab coarse space",
-        "steady_solves_per_s": world * batch / (ms_steady * 1e-3), "ms_per_batch": ms_steady,
+        "steady_solves_per_s": world * n_conv / (ms_steady * 1e-3), "ms_per_batch": ms_steady,
+        "converged": n_conv, "problems": batch,
         "pseudo_time_steps": int(out["steps"]), "newton_iterations_per_problem": int(out["iters"].sum(axis=0).max()),
         "gpu_launches": int(s.launch_count() - l1),
         "assemble": {"ms": ms_asm, "GBs": b_asm / ms_asm / 1e6, "frac_of_hbm_peak": b_asm / ms_asm / 1e6 / peak,
                      "algorithmic_bytes": b_asm,
-                     "dram_traffic_over_algorithmic": 1.18,      # ncu, profiles/r01_pore3d_ncu_summary.md
+                     "dram_traffic_over_algorithmic_ncu": traffic.get("assemble3d_dram_bytes_over_algorithmic_bytes"),
                      "kernels": "tet_moments_kernel + assemble_bsr_kernel + residual_gather_kernel"},
         "spmv": {"ms": ms_spmv, "GBs": b_spmv / ms_spmv / 1e6, "frac_of_hbm_peak": b_spmv / ms_spmv / 1e6 / peak,
                  "algorithmic_bytes": b_spmv,
-                 "dram_traffic_over_algorithmic": 0.99,      # ncu, profiles/r01_spmv_v2_ncu_summary.md
+                 "dram_traffic_over_algorithmic_ncu": traffic.get("spmv_dram_bytes_over_algorithmic_bytes"),
                  "note": "batch Jacobians (%.2f GB) exceed the 126 MB L2" % (batch * 8 * 81 * nb / 1e9)},
     }
     pp.solver.close()
+    return res
+
+
+def bench_config1(dev):
+    """BASELINE config 1 as a latency number: the reference's default run (1D:256-268, 633-796: 100 backward-Euler
+    steps of 1e-5 s, 50 um mesh, V = -1) of ONE problem through gmpnp_march_1d -- device time and end to end
+    (host parameter record in, final state + per-step Newton counts out)."""
+    import torch
+    from gmpnp_b200 import meshio, params, solver1d
+    x = meshio.load_mesh("1D_variable_50um_mesh_5990").x[:, 0]
+    prm = params.params_1d()
+    s = solver1d.Solver1D(x, batch=1, device=dev.index)
+    s.set_params([prm])
+    h_u = torch.empty(1, s.n, 7, dtype=torch.float64).pin_memory()
+
+    def run(e2e):
+        if e2e:
+            s.set_params([prm])
+        u = torch.zeros(1, s.n, 7, dtype=torch.float64, device=dev)
+        un = solver1d.bulk_state(1, s.n, dev)
+        out = s.march(u, un, 100)
+        if e2e:
+            h_u.copy_(u, non_blocking=True)
+            its = out["iters"].cpu()
+            torch.cuda.synchronize()
+            return its
+        return out["iters"]
+
+    run(False)
+    torch.cuda.synchronize()
+    res = {}
+    for name, e2e in (("device_ms", False), ("e2e_ms", True)):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        its = run(e2e)
+        e1.record()
+        torch.cuda.synchronize()
+        res[name] = e0.elapsed_time(e1)
+    its = its[0].tolist()
+    s.close()
+    res.update({"workload": "config1: 1D_variable_50um_mesh_5990, 0.1 M KHCO3, K+, V=-1, 100 steps of 1e-5 s "
+                            "(the reference's default dry run), one problem, reference Newton semantics (FFC rule pair, "
+                            "residual criterion 1e-4, pivoted elimination)",
+                "newton_iterations": int(sum(its)), "newton_per_step_head": its[:12],
+                "us_per_newton_iteration": 1e3 * res["device_ms"] / max(1, sum(its))})
     return res
 
 
@@ -273,155 +426,276 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm), "power_w_max": max(float(s[2]) for s in self.samples)}
 
 
+class SweepArm:
+    """One timed arm of the bench: a Sweep1D over `pts` on this rank, the resident region and the e2e region."""
+
+    def __init__(self, pts, n_global, args, local, world, dev):
+        import torch
+        from gmpnp_b200 import sweep
+        from gmpnp_b200.solver1d import NC
+        self.torch, self.sweep, self.world, self.dev, self.args = torch, sweep, world, dev, args
+        self.n_global = n_global
+        self.sw = sweep.Sweep1D(pts, device=local, dv_max=args.dv, xtol_path=args.xtol_path, pivot=args.pivot)
+        sw = self.sw
+        self.h_params = [torch.as_tensor(g["packed"]).pin_memory() for g in sw.groups]
+        self.h_paths = [torch.as_tensor(g["path"]).pin_memory() for g in sw.groups]
+        self.h_out = [torch.empty(g["solver"].batch, g["solver"].n, NC, dtype=torch.float64).pin_memory()
+                      for g in sw.groups]
+        self.h_summary = torch.empty(n_global, sweep.N_SUMMARY, dtype=torch.float64).pin_memory()
+        self.h2d = sum(t.numel() * 8 for t in self.h_params) + sum(t.numel() * 8 for t in self.h_paths)
+        self.d2h = sum(t.numel() * 8 for t in self.h_out) + self.h_summary.numel() * 8
+        sw.upload()
+
+    def launches(self):
+        return sum(g["solver"].launch_count() for g in self.sw.groups) + self.sw.extra_launches
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def resident_step(self):
+        outs = self.sw.solve_resident()
+        self.fin = self.sw.finish(outs)                 # polish stalled points / retry failed ones (syncs the step)
+        return outs
+
+    def e2e_step(self):
+        sw, torch = self.sw, self.torch
+        for g, hp, hv in zip(sw.groups, self.h_params, self.h_paths):
+            g["solver"].set_params(hp.numpy())                  # H2D of the parameter records
+            g["d_path"].copy_(hv, non_blocking=True)            # H2D of the continuation paths
+        outs = sw.solve_resident(host_out=self.h_out)           # D2H of every solution profile, per mesh stream
+        fin = sw.finish(outs)
+        if fin["polished"] or fin["retried"]:
+            for k, g in enumerate(sw.groups):                   # profiles of the points touched after the first copy
+                self.h_out[k].copy_(g["u"], non_blocking=True)
+        summ, idx = sw.results_device(outs)                     # per-point summaries (status, its, OHP values, field)
+        table = self.sweep.gather_results(summ, idx, self.n_global, self.world)     # the one collective (NCCL)
+        self.h_summary.copy_(table, non_blocking=True)
+        torch.cuda.synchronize()
+        return outs
+
+    def run(self, sampler_index=None):
+        torch, args = self.torch, self.args
+        for _ in range(args.warmup):
+            outs = self.resident_step()
+        self.barrier()
+        l1 = self.launches()
+        sampler = None
+        if sampler_index is not None:
+            sampler = ClockSampler(sampler_index)
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            outs = self.resident_step()
+        ev1.record()
+        self.barrier()
+        if sampler is not None:
+            sampler.stop_flag = True
+        ms = ev0.elapsed_time(ev1) / args.steps
+        l2 = self.launches()
+        summary = self.sw.summary(outs)
+        n_its, alg_bytes = self.sw.newton_iterations(outs)
+        self.e2e_step()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            self.e2e_step()
+        e1.record()
+        self.barrier()
+        ms_e2e = e0.elapsed_time(e1) / args.steps
+        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=self.dev)
+        cnt = torch.tensor([self.sw.n_points, summary["converged"], summary["stagnated_at_floor"], summary["failed"],
+                            n_its, alg_bytes, self.fin["polished"], self.fin["retried"], self.h2d, self.d2h],
+                           dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        ms, ms_e2e = [float(v) for v in t.tolist()]
+        c = [float(v) for v in cnt.tolist()]
+        return dict(ms=ms, ms_e2e=ms_e2e, n_points=int(c[0]), converged=int(c[1]), stagnated=int(c[2]), failed=int(c[3]),
+                    newton_iterations=int(c[4]), alg_bytes=c[5], polished=int(c[6]), retried=int(c[7]),
+                    h2d=int(c[8]), d2h=int(c[9]), launches=int(l2 - l1), outs=outs, summary=summary,
+                    clocks=sampler.summary() if sampler is not None else None)
+
+
+def parity_block(gpu_u, cpu_res, pts, gpu_its):
+    """GPU solutions of the sampled sweep points (resident arm, after `finish`) against the oracle's."""
+    import numpy as np
+    worst = np.zeros(7)
+    worst_pt = None
+    n_cmp, dits = 0, []
+    for p, r in zip(pts, cpu_res):
+        if not r["ok"] or p.index not in gpu_u:
+            continue
+        a, b = gpu_u[p.index], r["u"]
+        rel = np.array([np.linalg.norm(a[:, c] - b[:, c]) / max(np.linalg.norm(b[:, c]), 1e-300) for c in range(7)])
+        if rel.max() > worst.max():
+            worst_pt = {"cation": p.cation, "conc": p.conc, "L_n": p.L_n, "V": p.V}
+        worst = np.maximum(worst, rel)
+        dits.append(int(gpu_its[p.index]) - int(sum(r["its"])))
+        n_cmp += 1
+    names = ["H", "OH", "HCO3", "CO32", "CO2", "cat", "p"]
+    return {"points": n_cmp, "tolerance": PARITY_TOL,
+            "max_rel_l2_per_field": {n: float(v) for n, v in zip(names, worst)},
+            "newton_count_diff_max_abs": int(max(abs(d) for d in dits)) if dits else None,
+            "worst_point": worst_pt, "ok": bool(n_cmp > 0 and worst.max() <= PARITY_TOL),
+            "setting": "the benchmarked one: pivot-free elimination, consistent Jacobian, Euler-Newton path, xtol 1e-12; "
+                       "stratified over cation x concentration x mesh"}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         return reference_arm(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    want_cpu = (world == 1 and not args.no_cpu_baseline)
+    pool = CpuPool() if (rank == 0 and want_cpu) else None       # spawned before torch/CUDA are initialised
+
     import numpy as np
     import torch
     import torch.distributed as dist
     from gmpnp_b200 import sweep
-    from gmpnp_b200.solver1d import NC
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # weak scaling: every rank owns one full config-2 sweep (independent sweep points, no collective
-    # on the data path; one gather of the per-point summaries at the end)
     pts = sweep.config2_points(args.voltages)
-    sw = sweep.Sweep1D(pts, device=local, dv_max=args.dv, xtol_path=args.xtol_path, pivot=args.pivot)
-    n_local = sw.n_points
+    n_cfg = len(pts)
+    # ---- weak arm (headline): every rank owns one full config-2 sweep; global point index = rank * n_cfg + i ------
+    my_pts = [sweep.SweepPoint(p.cation, p.conc, p.L_n, p.V, rank * n_cfg + p.index) for p in pts]
+    weak = SweepArm(my_pts, world * n_cfg, args, local, world, dev)
+    W = weak.run(sampler_index=local)
 
-    # pinned host staging for the e2e arm
-    h_params = [torch.as_tensor(g["packed"]).pin_memory() for g in sw.groups]
-    h_paths = [torch.as_tensor(g["path"]).pin_memory() for g in sw.groups]
-    h_out = [torch.empty(g["solver"].batch, g["solver"].n, NC, dtype=torch.float64).pin_memory() for g in sw.groups]
-    h2d = sum(t.numel() * 8 for t in h_params) + sum(t.numel() * 8 for t in h_paths)
-    d2h = sum(t.numel() * 8 for t in h_out)
+    # parity sample: GPU solutions of the stratified points, taken from the resident arm's state
+    sample = stratified_points(args.cpu_sample, args.voltages, seed=0) if want_cpu else []
+    gpu_u, gpu_its = {}, {}
+    if sample:
+        want = {p.index for p in sample}
+        for g, out in zip(weak.sw.groups, weak.sw.last):
+            its = out["iters"].sum(dim=1).cpu().numpy()
+            for pos, pi in enumerate(g["idx"]):
+                gi = weak.sw.points[pi].index - rank * n_cfg
+                if gi in want:
+                    gpu_u[gi] = g["u"][pos].cpu().numpy()
+                    gpu_its[gi] = its[pos]
+    weak.sw.close()
+    del weak.h_out
+    torch.cuda.empty_cache()
 
-    sw.upload()
-    launches0 = sum(g["solver"].launch_count() for g in sw.groups)
-    # ---- resident arm ---------------------------------------------------------------------
-    for _ in range(args.warmup):
-        outs = sw.solve_resident()
-    barrier()
-    launches1 = sum(g["solver"].launch_count() for g in sw.groups)
-    sampler = ClockSampler(local)
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        outs = sw.solve_resident()
-    ev1.record()
-    barrier()
-    sampler.stop_flag = True
-    ms = ev0.elapsed_time(ev1) / args.steps
-    launches2 = sum(g["solver"].launch_count() for g in sw.groups)
-    n_its, alg_bytes = sw.newton_iterations(outs)
-    status = np.concatenate([o["status"].cpu().numpy() for o in outs])
-    n_conv = int((status == 0).sum())
-
-    # ---- e2e arm: host buffers in, host buffers out, through the public API ---------------
-    def e2e_step():
-        for g, hp, hv in zip(sw.groups, h_params, h_paths):
-            g["solver"].set_params(hp.numpy())                  # H2D of the parameter records
-            g["d_path"].copy_(hv, non_blocking=True)            # H2D of the continuation paths
-        o = sw.solve_resident(host_out=h_out)                   # D2H of every solution profile, per mesh stream
-        torch.cuda.synchronize()
-        return o
-
-    e2e_step()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        e2e_step()
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1) / args.steps
-
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        cnt = torch.tensor([n_local, n_conv, n_its, alg_bytes], dtype=torch.float64, device=dev)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        n_total, n_conv_total, n_its_total, bytes_total = [float(v) for v in cnt.tolist()]
-    else:
-        n_total, n_conv_total, n_its_total, bytes_total = n_local, n_conv, n_its, alg_bytes
-    ms, ms_e2e = [float(v) for v in t.tolist()]
+    # ---- strong arm (N > 1): the 7680 points of config 2 sharded over the ranks, summaries gathered over NCCL ---------
+    S = None
+    if world > 1 and args.scaling in ("strong", "both"):
+        strong = SweepArm(sweep.shard(pts, rank, world), n_cfg, args, local, world, dev)
+        S = strong.run()
+        strong.sw.close()
+        del strong.h_out
+        torch.cuda.empty_cache()
 
     peaks = {}
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         peaks = json.load(open(pk))
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    pore3d = None
-    if args.pore3d_batch > 0:
-        sw.close()
-        del h_out
-        torch.cuda.empty_cache()
-        pore3d = bench_pore3d(local, world, dev, args.pore3d_batch, peak)
+    pore3d = bench_pore3d(local, world, dev, args.pore3d_batch, peak) if args.pore3d_batch > 0 else None
+    config1 = bench_config1(dev) if (rank == 0 and not args.no_config1) else None
+
+    rc = 0
     if rank == 0:
-        achieved = (bytes_total / world) / (ms * 1e-3) / 1e9       # per-GPU GB/s of the kernel
+        ms, ms_e2e = W["ms"], W["ms_e2e"]
+        n_ok = W["converged"]                                     # strictly converged points only
+        achieved = (W["alg_bytes"] / world) / (ms * 1e-3) / 1e9    # per-GPU GB/s of the kernel
         prof = os.path.join(ROOT, "profiles", "traffic.json")
-        # DRAM traffic of the kernel: ncu's dram__bytes_read+write over the algorithmic bytes of the captured launch,
-        # applied to this step's algorithmic bytes (the capture is one of the five launches of a step)
         ratio = json.load(open(prof)).get("newton1d_dram_bytes_over_algorithmic_bytes") if os.path.exists(prof) else None
-        traffic = None if ratio is None else ratio * bytes_total / world
+        cfg = base_config(args)
         line = {
-            "metric": METRIC, "value": n_total / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "metric": METRIC, "value": n_ok / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD if args.voltages == 256 else f"reduced sweep ({args.voltages} V/chain)",
-                       "points_per_gpu": n_local, "converged": int(n_conv_total),
-                       "newton_iterations_per_step": int(n_its_total),
-                       "continuation": f"dV<={args.dv:g} V_T, xtol 1e-12 (final) / {args.xtol_path:g} (path), consistent Jacobian, "
-                                       f"in-block pivoting {'on' if args.pivot else 'off (equilibrated rows; failures retried with pivoting)'}",
-                       "cache": "working set (elimination workspace 10.7 GB/GPU) >> 126 MB L2, no flush needed",
-                       "parallelism": f"sweep points sharded, {world} GPU(s), no data-path collective"},
-            "e2e": {"value": n_total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": int(launches2 - launches1),
+            "config": cfg,
+            "run": {"points_per_gpu": n_cfg, "points": W["n_points"], "converged": W["converged"],
+                    "stagnated_at_floor_after_polish": W["stagnated"], "failed": W["failed"],
+                    "polished_with_pivoting_per_step": W["polished"], "retried_per_step": W["retried"],
+                    "max_final_dx_converged": W["summary"]["max_final_dx_converged"],
+                    "newton_iterations_per_step": W["newton_iterations"],
+                    "in_block_pivoting": "on" if args.pivot else "off (equilibrated rows); points that stall at the "
+                                         "round-off floor (status 4) are polished with the pivoted elimination and failed "
+                                         "points retried inside the timed step",
+                    "cache": "working set (elimination workspace 10.7 GB/GPU) >> 126 MB L2, no flush needed",
+                    "parallelism": f"weak: one full sweep per GPU, {world} GPU(s), no data-path collective; "
+                                   "one all_gather of the per-point summaries in the e2e region"},
+            "e2e": {"value": n_ok / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": W["h2d"],
+                    "d2h_bytes_per_step": W["d2h"]},
+            "gpu_launches": W["launches"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic,
+                         "frac": achieved / peak,
+                         "traffic": None if ratio is None else ratio * W["alg_bytes"] / world,
+                         "traffic_source": "ncu dram__bytes_read+write over algorithmic bytes of ONE captured launch "
+                                           f"(ratio {ratio}, profiles/traffic.json) x this step's algorithmic bytes -- "
+                                           "not a measurement of this run",
                          "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                          "kernel": "edl1d::newton1d_kernel (5 concurrent launches = one step)",
-                         "algorithmic_bytes_per_step": bytes_total / world},
-            "clocks": sampler.summary(),
+                         "algorithmic_bytes_per_step": W["alg_bytes"] / world},
+            "clocks": W["clocks"],
         }
-        # fp64: executed flops of the hot kernel (thread-level DFMA x2 + DMUL + DADD per block row and Newton iteration,
-        # counted by ncu on the v10 kernel: profiles/r01_newton1d_v10_ncu_summary.md) against the measured DFMA peak
+        if S is not None:
+            line["strong"] = {
+                "workload": f"config 2 as stated: {n_cfg} points sharded over {world} GPUs (sweep.shard), per-point "
+                            "summaries gathered with one NCCL all_gather inside the e2e region",
+                "value": S["converged"] / (S["ms"] * 1e-3), "ms_per_step": S["ms"],
+                "e2e": {"value": S["converged"] / (S["ms_e2e"] * 1e-3), "ms_per_step": S["ms_e2e"],
+                        "h2d_bytes_per_step": S["h2d"], "d2h_bytes_per_step": S["d2h"]},
+                "points": S["n_points"], "converged": S["converged"], "stagnated_at_floor_after_polish": S["stagnated"],
+                "failed": S["failed"], "gpu_launches": S["launches"],
+                "roofline_frac_per_gpu": (S["alg_bytes"] / world) / (S["ms"] * 1e-3) / 1e9 / peak}
+        # fp64: executed flops of the hot kernel per block row and Newton iteration (thread-level DFMA x2 + DMUL + DADD,
+        # counted by ncu: profiles/traffic.json) against the measured DFMA peak
         import ctypes as C
         from gmpnp_b200 import _lib
         pk64 = C.c_double(0.0)
         _lib.check(_lib.load().gmpnp_fp64_peak(local, C.byref(pk64)))
-        flops_row = 6233.0
-        ach64 = flops_row * (bytes_total / world / 1072.0) / (ms * 1e-3) / 1e12
+        flops_row = float(json.load(open(prof)).get("newton1d_fp64_flops_per_block_row", 6233.0)) if os.path.exists(prof) else 6233.0
+        ach64 = flops_row * (W["alg_bytes"] / world / 1072.0) / (ms * 1e-3) / 1e12
         line["fp64"] = {"peak_tflops_measured": pk64.value, "achieved_tflops_executed": ach64,
                         "frac": ach64 / pk64.value if pk64.value > 0 else None,
                         "flops_per_block_row_iteration": flops_row,
                         "note": "executed (not minimal) fp64 flops incl. the per-lane redundancy of the quadrature"}
+        if config1 is not None:
+            line["config1"] = config1
         if pore3d is not None:
-            if world == 1 and not args.no_cpu_baseline:
-                pore3d["cpu_baseline"] = run_cpu_3d(pore3d["newton_iterations_per_problem"])
             line["pore3d"] = pore3d
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = run_cpu(args.cpu_sample, args.voltages, dv=args.dv, xtol_path=args.xtol_path)
+        if pool is not None:
+            res, wall = pool.solve(sample, args.dv, args.xtol_path, want_u=True)
+            line["cpu_baseline"] = cpu_summary(res, wall, pool.cores, len(sample),
+                                               f"{len(sample)} of the {n_cfg} sweep points, {args.cpu_sample} per (mesh, "
+                                               "concentration, cation) chain, random voltages (seed 0)")
+            line["parity"] = parity_block(gpu_u, res, sample, gpu_its)
+            if not line["parity"]["ok"]:
+                rc = 3
+            if config1 is not None:
+                t_c1, its_c1 = pool.pool.apply(_cpu_config1, (10,))
+                config1["cpu_oracle"] = {"steps": 10, "newton_iterations": int(sum(its_c1)), "wall_s": t_c1,
+                                         "ms_per_newton_iteration": 1e3 * t_c1 / max(1, sum(its_c1)),
+                                         "note": "first 10 of the 100 steps on one host core (NumPy assembly + SuperLU)"}
+                config1["newton_counts_equal_oracle_first_10_steps"] = bool(its_c1 == config1["newton_per_step_head"][:10])
+            if pore3d is not None:
+                pore3d["cpu_baseline"] = run_cpu_3d(pool, pore3d["newton_iterations_per_problem"])
+            pool.close()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if rc:
+        sys.exit(rc)
 
 
 if __name__ == "__main__":

@@ -83,12 +83,12 @@ int gmpnp_march_1d(gmpnp_handle* h, double* d_u, double* d_un, int n_steps, cons
 
 int gmpnp_steady_continuation_1d(gmpnp_handle* h, double* d_u, const double* d_Vpath, int n_V,
                                  const gmpnp_newton_opts* opts, int* d_iters, int* d_stage, int* d_status,
-                                 void* stream) {
+                                 double* d_dx, void* stream) {
     int rc = check_1d(h); if (rc) return rc;
     if (!d_u || !d_Vpath || !opts || n_V < 1) return GMPNP_ERR_ARG;
     GMPNP_CUDA_TRY(h, cudaSetDevice(h->device));
     return edl1d_launch_newton(h, 2, d_u, nullptr, nullptr, opts, n_V, d_Vpath, nullptr, d_iters, nullptr, nullptr,
-                               nullptr, d_stage, d_status, (cudaStream_t)stream);
+                               d_dx, d_stage, d_status, (cudaStream_t)stream);
 }
 
 int gmpnp_field_1d(gmpnp_handle* h, const double* d_u, double* d_field, void* stream) {

@@ -590,7 +590,7 @@ __device__ void backward_sweep(const Group& g, int first, int dir, int rows, int
     __syncwarp();
 }
 
-struct NewtonOut { int iters; double r0, r; int status; };
+struct NewtonOut { int iters; double r0, r; int status; double dx; };
 
 // Factorisation sweep of both halves + merge.  Both halves eliminate m = n/2 rows (top: 0..m-1 downwards, bottom:
 // n-1 .. n-m upwards), so the two groups of a pair -- and with the warp-uniform drivers below all four groups of a
@@ -724,7 +724,8 @@ __device__ NewtonOut newton_solve(const Group& g, const LaneConst& L, const doub
     int k = 0;
     bool conv = (o.criterion == 0) ? (r < o.atol) : false;
     bool bad = !isfinite(r) || singular;
-    double dx_prev = INFINITY;
+    bool stag = false;
+    double dx_prev = INFINITY, dx_rel = INFINITY;
     bool active = enabled && !conv && !bad && k < o.maxit;
     while (__any_sync(0xffffffffu, active)) {
         double dxmax, umax;
@@ -735,12 +736,14 @@ __device__ NewtonOut newton_solve(const Group& g, const LaneConst& L, const doub
             if (o.criterion == 1) {
                 const double scale = fmax(1.0, umax);
                 conv = dxmax <= o.xtol * scale;
-                // round-off floor (consistent Jacobian only, where convergence is quadratic): an increment that is
-                // already small but no longer contracts sits at cond(J)*eps, above xtol -- accept it
-                if (!conv && NQJ == 2 && k >= 3 && dxmax <= 1.0e-6 * scale && dxmax >= 0.25 * dx_prev) conv = true;
+                // opt-in round-off floor (gmpnp.h, xtol_floor): an increment that is small but no longer contracts
+                // sits at cond(J)*eps of the linear solve, above xtol -- reported as GMPNP_STAGNATED, never as converged
+                if (!conv && o.xtol_floor > 0.0 && k >= 3 && dxmax <= o.xtol_floor * scale && dxmax >= 0.25 * dx_prev)
+                    stag = true;
                 dx_prev = dxmax;
+                dx_rel = dxmax / scale;
                 if (!isfinite(dxmax)) bad = true;
-                if (conv || bad) still = false;           // dolfin-like: no re-assembly after an increment stop
+                if (conv || bad || stag) still = false;   // dolfin-like: no re-assembly after an increment stop
             }
         }
         if (!__any_sync(0xffffffffu, still)) break;   // nobody needs the re-assembly (increment stop / failure)
@@ -756,7 +759,8 @@ __device__ NewtonOut newton_solve(const Group& g, const LaneConst& L, const doub
     }
     out.iters = k;
     out.r = r;
-    out.status = bad ? GMPNP_NOT_FINITE : (conv ? GMPNP_CONVERGED : GMPNP_MAXIT);
+    out.dx = dx_rel;
+    out.status = bad ? GMPNP_NOT_FINITE : (conv ? GMPNP_CONVERGED : (stag ? GMPNP_STAGNATED : GMPNP_MAXIT));
     return out;
 }
 
@@ -895,8 +899,11 @@ newton1d_kernel(int mode, int batch, int n, const double* __restrict__ x, const 
             if (alive) {
                 if (writer && iters) iters[(long)prob * n_stage + s] = o.iters;
                 if (writer && rout) rout[prob] = o.r;
-                if (o.status != GMPNP_CONVERGED) { st = o.status; alive = false; }
-                else ++done;
+                if (writer && hfrac_out) hfrac_out[prob] = o.dx;          // d_dx of the C-ABI
+                // a stalled increment ends the iteration of this stage but not the path; the status of the LAST
+                // stage is what the caller sees
+                if (o.status == GMPNP_CONVERGED || o.status == GMPNP_STAGNATED) { ++done; st = o.status; }
+                else { st = o.status; alive = false; }
             }
         }
         if (writer) {

@@ -135,9 +135,10 @@ class Solver1D:
         it = torch.zeros(self.batch, nV, dtype=torch.int32, device=self.device)
         st = torch.zeros(self.batch, dtype=torch.int32, device=self.device)
         sg = torch.zeros(self.batch, dtype=torch.int32, device=self.device)
+        dx = torch.zeros(self.batch, dtype=torch.float64, device=self.device)
         check(self.lib.gmpnp_steady_continuation_1d(self._h, ptr(u), ptr(Vpath), nV, C.byref(opts), ptr(it), ptr(sg),
-                                                    ptr(st), self._stream()), self._h)
-        return dict(iters=it, status=st, stages=sg)
+                                                    ptr(st), ptr(dx), self._stream()), self._h)
+        return dict(iters=it, status=st, stages=sg, dx=dx)
 
     def field(self, u):
         self._chk(u, (self.batch, self.n, NC))

@@ -8,9 +8,6 @@ shards across GPUs by point with no data-path collective (results are gathered a
 """
 from __future__ import annotations
 
-import math
-from dataclasses import dataclass
-
 import numpy as np
 import torch
 
@@ -18,38 +15,11 @@ from . import meshio, params as _params
 from ._lib import NewtonOpts
 from .solver1d import Solver1D, bulk_state, pack_1d, NC
 
-CONFIG2_CATIONS = ("K", "Cs")
-CONFIG2_CONCS = (0.1, 0.5, 1.0)
-CONFIG2_LN = (1e-6, 5e-6, 10e-6, 50e-6, 200e-6)
-CONFIG2_NV = 256
-CONFIG2_VMAX = -12.5
+from .sweep_points import (CONFIG2_CATIONS, CONFIG2_CONCS, CONFIG2_LN, CONFIG2_NV, CONFIG2_VMAX,  # noqa: F401
+                           SweepPoint, config2_points, shard, voltage_paths)
 
 
-@dataclass
-class SweepPoint:
-    cation: str
-    conc: float
-    L_n: float
-    V: float
-    index: int = 0
-
-
-def config2_points(n_voltages: int = CONFIG2_NV, meshes=CONFIG2_LN, concs=CONFIG2_CONCS,
-                   cations=CONFIG2_CATIONS, vmax: float = CONFIG2_VMAX):
-    """{K, Cs} x n_voltages (V_k = vmax (k+1)/n) x {0.1, 0.5, 1.0} M x 5 meshes (SURVEY 8d cfg 2)."""
-    pts = []
-    for L_n in meshes:
-        for k in range(n_voltages):
-            V = vmax * (k + 1) / n_voltages
-            for conc in concs:
-                for cat in cations:
-                    pts.append(SweepPoint(cat, conc, L_n, V, len(pts)))
-    return pts
-
-
-def shard(points, rank: int, world: int):
-    """Static shard by sweep point: every rank gets the same mix of meshes and voltages."""
-    return points[rank::world]
+N_SUMMARY = 10      # per-point summary row: status, Newton iterations, u(OHP)[7], projected field at the OHP
 
 
 def gather_results(local: "torch.Tensor", local_index: "torch.Tensor", n_total: int, world: int):
@@ -75,32 +45,26 @@ def gather_results(local: "torch.Tensor", local_index: "torch.Tensor", n_total: 
     return out
 
 
-def voltage_paths(Vs: np.ndarray, dv_max: float) -> np.ndarray:
-    """Ragged continuation paths, NaN-terminated: point b walks 0 -> V_b in ceil(|V_b|/dv_max) equal steps."""
-    Vs = np.asarray(Vs, dtype=np.float64)
-    nst = np.maximum(1, np.ceil(np.abs(Vs) / dv_max - 1e-12).astype(int))
-    nV = int(nst.max())
-    path = np.full((len(Vs), nV), np.nan)
-    for b, (V, n) in enumerate(zip(Vs, nst)):
-        path[b, :n] = V * np.arange(1, n + 1) / n
-    return path
-
-
 class Sweep1D:
     """All sweep points of one rank, grouped by mesh into one :class:`Solver1D` each."""
 
     def __init__(self, points, device: int = 0, utilities_dir=None, dv_max: float = 0.5,
                  xtol: float = 1e-12, xtol_path: float = 1e-1, maxit: int = 50, jac_rule: int = 1,
-                 pivot: int = 0):
+                 pivot: int = 0, xtol_floor: float = 1e-6):
         """``pivot``: partial pivoting inside the 7x7 blocks of the block-Thomas elimination.  The sweep default is
         0: with the Poisson row equilibrated the in-block pivot is the diagonal in 99.95 % of the steps, and a
         Newton iteration that converges (increment criterion, residual evaluated independently of the linear
         solve) is correct whatever the pivoting of its linear solves; points that do NOT converge are re-run
-        with pivoting and halved voltage increments by :meth:`retry_failed`."""
+        with pivoting and halved voltage increments by :meth:`retry_failed`.
+
+        ``xtol_floor`` (gmpnp.h): with the pivot-free elimination the last increments of a few points stall at the
+        round-off floor of the linear solve, above ``xtol``.  Those points end with status 4 (GMPNP_STAGNATED), never
+        with 0; :meth:`summary` counts them and reports their largest final relative increment, and
+        :meth:`retry_failed` (``include_stagnated=True``) polishes them with the pivoted elimination."""
         self.points = list(points)
         self.device = torch.device("cuda", int(device))
         self.dv_max, self.xtol, self.xtol_path, self.maxit = dv_max, xtol, xtol_path, maxit
-        self.jac_rule, self.pivot = jac_rule, pivot
+        self.jac_rule, self.pivot, self.xtol_floor = jac_rule, pivot, xtol_floor
         self.groups = []
         by_mesh = {}
         for i, p in enumerate(self.points):
@@ -128,9 +92,11 @@ class Sweep1D:
             self.groups.append(dict(L_n=L_n, idx=np.array(idx), solver=solver, packed=packed, path=path,
                                     stream=torch.cuda.Stream(self.device)))
         self.n_points = len(self.points)
+        self.extra_launches = 0       # kernels launched by sub-solvers (polish / retry), not counted by the groups
 
     def opts(self, pivot=None):
-        o = NewtonOpts.steady(xtol=self.xtol, maxit=self.maxit, xtol_path=self.xtol_path, jac_rule=self.jac_rule)
+        o = NewtonOpts.steady(xtol=self.xtol, maxit=self.maxit, xtol_path=self.xtol_path, jac_rule=self.jac_rule,
+                              xtol_floor=self.xtol_floor)
         o.pivot = self.pivot if pivot is None else pivot
         return o
 
@@ -140,6 +106,8 @@ class Sweep1D:
             g["solver"].set_params(g["packed"])
             g["d_path"] = torch.as_tensor(g["path"], device=self.device)
             g["u"] = torch.empty(g["solver"].batch, g["solver"].n, NC, dtype=torch.float64, device=self.device)
+            g["d_idx"] = torch.as_tensor(g["idx"], dtype=torch.long, device=self.device)
+        self.d_gindex = torch.as_tensor([p.index for p in self.points], dtype=torch.long, device=self.device)
 
     def solve_resident(self, host_out=None):
         """One pass of the hot path over the whole batch: every point from the bulk state to its
@@ -164,13 +132,73 @@ class Sweep1D:
         self.last = outs
         return outs
 
+    def summary(self, outs):
+        """Counts per status over the sweep and the largest final relative increment per status class."""
+        st = np.concatenate([o["status"].cpu().numpy() for o in outs])
+        dx = np.concatenate([o["dx"].cpu().numpy() for o in outs])
+        res = {"converged": int((st == 0).sum()), "stagnated_at_floor": int((st == 4).sum()),
+               "failed": int(((st != 0) & (st != 4)).sum())}
+        res["max_final_dx_converged"] = float(dx[st == 0].max()) if (st == 0).any() else None
+        res["max_final_dx_stagnated"] = float(dx[st == 4].max()) if (st == 4).any() else None
+        return res
+
+    def finish(self, outs):
+        """End of a sweep pass: points that stalled at the round-off floor are polished with the pivoted elimination,
+        failed points are retried with halved increments.  One device->host read of two counters when there is
+        nothing to do."""
+        st = torch.cat([o["status"] for o in outs])
+        n4, nbad = torch.stack([(st == 4).sum(), ((st != 0) & (st != 4)).sum()]).tolist()
+        polished = self.polish_stagnated(outs) if n4 else 0
+        retried = self.retry_failed(outs) if nbad else 0
+        return dict(polished=int(polished), retried=int(retried))
+
+    def results_device(self, outs):
+        """Per-point summary rows on the device, [n_points, N_SUMMARY] in the order of ``self.points``, and the
+        global sweep-point index of every row: the payload of the sharded sweep's one collective."""
+        rows = torch.empty(self.n_points, N_SUMMARY, dtype=torch.float64, device=self.device)
+        for g, out in zip(self.groups, outs):
+            f = g["solver"].field(g["u"])[:, 0]
+            blk = torch.cat([out["status"].to(torch.float64)[:, None],
+                             out["iters"].sum(dim=1).to(torch.float64)[:, None], g["u"][:, 0, :], f[:, None]], dim=1)
+            rows[g["d_idx"]] = blk
+        return rows, self.d_gindex
+
+    def polish_stagnated(self, outs):
+        """Points that stalled at the round-off floor of the pivot-free elimination (status 4) take a few more Newton
+        iterations with in-block pivoting from their current state, at their target voltage; their status becomes 0
+        if the strict criterion is then met.  Returns the number of points polished."""
+        n = 0
+        for g, out in zip(self.groups, outs):
+            status = out["status"].cpu().numpy()
+            idx = np.nonzero(status == 4)[0]
+            if not len(idx):
+                continue
+            n += len(idx)
+            Vs = np.array([self.points[g["idx"][b]].V for b in idx])
+            sub = Solver1D(g["solver"].x, batch=len(idx), device=self.device.index)
+            sub.set_params(g["packed"][idx])
+            sel = torch.as_tensor(idx, device=self.device)
+            u = g["u"][sel].contiguous()
+            o = self.opts(pivot=1)
+            o.xtol_floor = 0.0
+            o.maxit = 8
+            res = sub.steady(u, Vs[:, None], o)
+            ok = res["status"] == 0
+            g["u"][sel[ok]] = u[ok]
+            out["status"][sel[ok]] = 0
+            out["dx"][sel[ok]] = res["dx"][ok]
+            out["iters"][sel, -1] += res["iters"][:, 0]
+            self.extra_launches += sub.launch_count()
+            sub.close()
+        return n
+
     def retry_failed(self, outs, max_rounds: int = 3):
-        """Points whose Newton failed (status != 0) are re-run from bulk with a halved voltage step
+        """Points whose Newton failed (status not 0 and not 4) are re-run from bulk with a halved voltage step
         (failure handling: per-problem status, never abort the batch)."""
         n_retry = 0
         for g, out in zip(self.groups, outs):
             status = out["status"].cpu().numpy()
-            bad = np.nonzero(status != 0)[0]
+            bad = np.nonzero((status != 0) & (status != 4))[0]
             dv = self.dv_max
             rounds = 0
             while len(bad) and rounds < max_rounds:
@@ -187,6 +215,7 @@ class Sweep1D:
                 g["u"][torch.as_tensor(bad[ok], device=self.device)] = u[torch.as_tensor(np.nonzero(ok)[0], device=self.device)]
                 out["status"][torch.as_tensor(bad[ok], device=self.device)] = 0
                 bad = bad[~ok]
+                self.extra_launches += sub.launch_count()
                 sub.close()
         return n_retry
 

@@ -58,7 +58,8 @@ typedef struct gmpnp_newton_opts {
     double rtol;        /* relative_tolerance  (1e-4 at 1D:361, 3D:794)                    */
     double atol;        /* absolute_tolerance  (1e-4 at 1D:362, 3D:795)                    */
     double relax;       /* relaxation_parameter (1.0 in 1D, 0.9 at 3D:796)                 */
-    double xtol;        /* increment criterion: ||dx||_inf <= xtol*max(1,||x||_inf)        */
+    double xtol;        /* increment criterion: ||dx||_inf <= xtol*max(1,||x||_inf); nothing else
+                           counts as GMPNP_CONVERGED under criterion 1                        */
     int    maxit;       /* maximum_iterations  (50)                                        */
     int    criterion;   /* 0 = residual (reference), 1 = increment (steady mode)           */
     int    pivot;       /* 1 = partial pivoting inside the 7x7 blocks (default), 0 = none  */
@@ -72,6 +73,12 @@ typedef struct gmpnp_newton_opts {
                            rule (exact derivative of the discrete F: quadratic convergence; same
                            converged solution, which depends on F's rule only)              */
     int    reserved;
+    double xtol_floor;  /* increment criterion only, 0 = off (the default: strict contract above).  > 0: an
+                           increment that has stopped contracting (||dx|| >= 0.25 ||dx_prev||, after >= 3
+                           iterations) with xtol*s < ||dx||_inf <= xtol_floor*s, s = max(1,||x||_inf), ends the
+                           iteration with status GMPNP_STAGNATED (round-off floor of the linear solve, e.g. of
+                           the pivot-free elimination); the iterate is kept and the final relative increment is
+                           returned (d_dx), so the caller decides: accept, or re-run with pivoting.           */
 } gmpnp_newton_opts;
 
 /* per-problem status codes written to status[] */
@@ -79,6 +86,7 @@ typedef struct gmpnp_newton_opts {
 #define GMPNP_MAXIT            1   /* dolfin would raise RuntimeError here                   */
 #define GMPNP_NOT_FINITE       2   /* NaN/Inf in residual or singular pivot                  */
 #define GMPNP_LINEAR_FAILED    3   /* 3D: GMRES did not reach lin_rtol                       */
+#define GMPNP_STAGNATED        4   /* increment stalled between xtol and xtol_floor (see opts) */
 
 /* API error codes */
 #define GMPNP_OK               0
@@ -131,10 +139,12 @@ int gmpnp_march_1d(gmpnp_handle* h, double* d_u, double* d_un, int n_steps,
 /* Steady equations (kappa forced to 0) with voltage continuation: for s < n_V the OHP
  * potential is d_Vpath[problem][s] and Newton restarts from the previous stage's solution.
  * A NaN entry ends that problem's path early (ragged paths in one batch).
- * d_iters (optional) [batch][n_V]; d_stage (optional) [batch] = number of stages completed. */
+ * d_iters (optional) [batch][n_V]; d_stage (optional) [batch] = number of stages completed;
+ * d_dx (optional) [batch] = ||dx||_inf / max(1,||u||_inf) of the last Newton update of the last stage
+ * (what the increment criterion saw).  GMPNP_STAGNATED at an intermediate stage does not end a path. */
 int gmpnp_steady_continuation_1d(gmpnp_handle* h, double* d_u, const double* d_Vpath, int n_V,
                                  const gmpnp_newton_opts* opts, int* d_iters, int* d_stage,
-                                 int* d_status, void* stream);
+                                 int* d_status, double* d_dx, void* stream);
 
 /* L2 projection of -d(phi)/dx onto P1 (dolfin project(-grad(u_p), W), 1D:802-803) for
  * every problem: d_field[batch][n].                                                       */

@@ -114,32 +114,59 @@ def bc_1d(nv, ncomp, V):
 
 
 def newton(disc, prm, u, un, bc_dofs, bc_vals, point_flux=None, rtol=1e-4, atol=1e-4, maxit=50,
-           relax=1.0, criterion="residual", xtol=1e-12, history=None):
+           relax=1.0, criterion="residual", xtol=1e-12, history=None, xtol_floor=0.0, info=None):
     """dolfin NewtonSolver.  Returns (u, iterations, converged, r0, r).
 
     criterion 'residual': stop when ||b||/||b0|| < rtol or ||b|| < atol (reference).
-    criterion 'increment': stop when ||dx||_inf <= xtol * max(1, ||x||_inf)  (steady mode)."""
+    criterion 'increment': stop when ||dx||_inf <= xtol * max(1, ||x||_inf)  (steady mode).
+    ``xtol_floor`` > 0 mirrors the opt-in rule of include/gmpnp.h (gmpnp_newton_opts.xtol_floor): an increment that
+    stopped contracting between xtol and xtol_floor ends the iteration with ``info['stagnated'] = True`` and
+    converged = False.  ``info`` (dict, optional) also receives 'dx_rel' (last relative increment) and the wall time
+    spent in 'assembly' (residual + Jacobian) and 'lu' (sparse LU factorisation + solve)."""
+    import time as _time
     x = u.copy()
+    t0 = _time.perf_counter()
     b = apply_bc_residual(disc.residual(x, un, prm, point_flux), x, bc_dofs, bc_vals)
+    t_asm, t_lu = _time.perf_counter() - t0, 0.0
     r0 = float(np.linalg.norm(b))
     r = r0
     k = 0
     conv = (r < atol) if criterion == "residual" else False
+    stagnated = False
+    dx_prev, dx_rel = np.inf, np.inf
     while not conv and k < maxit:
+        t0 = _time.perf_counter()
         A = apply_bc_matrix(disc.jacobian(x, prm), bc_dofs)
+        t1 = _time.perf_counter()
         dx = spla.splu(A).solve(b)
+        t2 = _time.perf_counter()
         x = x - relax * dx
         k += 1
         b = apply_bc_residual(disc.residual(x, un, prm, point_flux), x, bc_dofs, bc_vals)
+        t3 = _time.perf_counter()
+        t_asm += (t1 - t0) + (t3 - t2)
+        t_lu += t2 - t1
         r = float(np.linalg.norm(b))
+        dxmax = float(np.abs(dx).max())
         if history is not None:
-            history.append((k, r, float(np.abs(dx).max())))
+            history.append((k, r, dxmax))
         if criterion == "residual":
             conv = (r / r0 < rtol) or (r < atol)
         else:
-            conv = float(np.abs(dx).max()) <= xtol * max(1.0, float(np.abs(x).max()))
+            scale = max(1.0, float(np.abs(x).max()))
+            conv = dxmax <= xtol * scale
+            if not conv and xtol_floor > 0 and k >= 3 and dxmax <= xtol_floor * scale and dxmax >= 0.25 * dx_prev:
+                stagnated = True
+            dx_prev, dx_rel = dxmax, dxmax / scale
+            if stagnated:
+                break
         if not np.isfinite(r):
             break
+    if info is not None:
+        info["stagnated"] = stagnated
+        info["dx_rel"] = dx_rel
+        info["assembly"] = info.get("assembly", 0.0) + t_asm
+        info["lu"] = info.get("lu", 0.0) + t_lu
     return x, k, conv, r0, r
 
 
@@ -188,7 +215,7 @@ def march_1d(x, prm, n_steps, H_OHP=None, rtol=1e-4, atol=1e-4, maxit=50):
     return np.array(hist), its, frac
 
 
-def steady_1d(x, prm, V_path, u0=None, xtol=1e-12, maxit=50, xtol_path=0.0, jac_rule=0):
+def steady_1d(x, prm, V_path, u0=None, xtol=1e-12, maxit=50, xtol_path=0.0, jac_rule=0, info=None):
     """Steady equations (kappa = 0) with voltage continuation along ``V_path``.
     Starts from the bulk state unless ``u0`` is given.  Returns (u[nv, ncomp] at the last V,
     list of Newton counts)."""
@@ -206,7 +233,7 @@ def steady_1d(x, prm, V_path, u0=None, xtol=1e-12, maxit=50, xtol_path=0.0, jac_
         bc_dofs, bc_vals = bc_1d(nv, ncomp, float(V))
         tol = xtol if (s_ + 1 == len(V_path) or not xtol_path > 0) else xtol_path
         u, k, conv, r0, r = newton(disc, pv, u, u, bc_dofs, bc_vals, point_flux=pv.jflux,
-                                   criterion="increment", xtol=tol, maxit=maxit)
+                                   criterion="increment", xtol=tol, maxit=maxit, info=info)
         if not conv:
             raise RuntimeError(f"steady Newton failed at V={V} after {k} its (r={r})")
         its.append(k)

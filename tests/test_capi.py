@@ -27,7 +27,8 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 def test_struct_layout_matches_header():
     from gmpnp_b200 import _lib, params
     o = _lib.NewtonOpts.reference_3d()
-    assert ctypes.sizeof(o) == 4 * 8 + 5 * 4 + 4 + 2 * 8 + 2 * 4     # 4 doubles, 5 ints (+pad), 2 doubles, 2 ints
+    assert ctypes.sizeof(o) == 4 * 8 + 5 * 4 + 4 + 2 * 8 + 2 * 4 + 8   # 4 doubles, 5 ints (+pad), 2 doubles, 2 ints, 1 double
+    assert _lib.NewtonOpts.xtol_floor.offset == 80 and o.xtol_floor == 0.0
     assert (o.rtol, o.atol, o.relax, o.maxit) == (1e-4, 1e-4, 0.9, 50)
     src = open(os.path.join(ROOT, "include", "gmpnp.h")).read()
     defs = dict(re.findall(r"#define\s+GMPNP_P_(\w+)\s+(\d+)", src))

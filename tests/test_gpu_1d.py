@@ -171,6 +171,78 @@ def test_config1_march_first_steps(lib):
         assert rel_l2(got[:, c], g["last"][:, c]) < 1e-8
 
 
+def test_config1_full_default_run_100_steps(lib):
+    """BASELINE config 1 in full: the reference's default dry run (1D:256-268: 100 steps of 1e-5 s) through
+    gmpnp_march_1d: the Newton count of every step ([7] + [3]*9 + [2]*90 = 214 iterations) and the state after step
+    100 against the oracle's golden vector (tests/golden/make_golden_config1.py)."""
+    from gmpnp_b200 import meshio, params, solver1d
+    g = np.load(os.path.join(GOLDEN, "march_50um_100.npz"))
+    m = meshio.load_mesh("1D_variable_50um_mesh_5990")
+    prm = params.params_1d()
+    s = solver1d.Solver1D(m.x[:, 0], batch=1)
+    s.set_params([prm])
+    u = torch.zeros(1, s.n, 7, dtype=torch.float64, device=_dev())
+    un = solver1d.bulk_state(1, s.n, _dev())
+    out = s.march(u, un, 100)
+    torch.cuda.synchronize()
+    assert out["status"].tolist() == [0]
+    its = out["iters"][0].tolist()
+    assert its == g["its"].tolist() == [7] + [3] * 9 + [2] * 90
+    got = u[0].cpu().numpy()
+    for c in range(7):
+        assert rel_l2(got[:, c], g["last"][:, c]) < 1e-8, c
+    assert np.abs(got[0] - g["ohp"][2]).max() <= 1e-9 * np.abs(g["ohp"][2]).max()
+
+
+@pytest.mark.parametrize("cation,conc,L_n,V", [("Cs", 1.0, 200e-6, -12.5 * 200 / 256), ("K", 0.5, 5e-6, -12.5),
+                                              ("Cs", 0.5, 1e-6, -12.5 * 77 / 256), ("K", 1.0, 10e-6, -12.5 * 140 / 256)])
+def test_benchmarked_setting_matches_oracle(lib, cation, conc, L_n, V):
+    """The bench's own setting (Sweep1D defaults of bench.py: pivot-free elimination, consistent Jacobian, Euler-Newton
+    path with dV <= 0.75 and one corrector per increment, xtol 1e-12, stalled points polished) against the oracle
+    solving the same sweep point with the same continuation: rel-L2 per field <= 1e-8, Newton counts within 1."""
+    from gmpnp_b200 import meshio, params, sweep
+    from oracle import solver as osolver
+    pt = sweep.SweepPoint(cation, conc, L_n, V, 0)
+    sw = sweep.Sweep1D([pt], device=0, dv_max=0.75, xtol_path=1.0, pivot=0)
+    sw.upload()
+    outs = sw.solve_resident()
+    sw.finish(outs)
+    torch.cuda.synchronize()
+    assert outs[0]["status"].tolist() == [0], (outs[0]["status"].tolist(), outs[0]["dx"].tolist())
+    got = sw.groups[0]["u"][0].cpu().numpy()
+    x = meshio.load_mesh(params.mesh_name_1d(L_n)).x[:, 0]
+    prm = params.params_1d(concentration_elec=conc, cation=cation, L_n=L_n, voltage_multiplier=V)
+    path = sweep.voltage_paths(np.array([V]), 0.75)[0]
+    uo, its = osolver.steady_1d(x, prm, path[~np.isnan(path)], xtol=1e-12, xtol_path=1.0, jac_rule=1)
+    for c in range(7):
+        assert rel_l2(got[:, c], uo[:, c]) < 1e-8, (c, rel_l2(got[:, c], uo[:, c]))
+    assert abs(int(outs[0]["iters"].sum()) - sum(its)) <= 1, (outs[0]["iters"].tolist(), its)
+    sw.close()
+
+
+def test_stalled_increment_is_reported_not_accepted(lib):
+    """gmpnp.h: under the increment criterion status 0 means ||dx|| <= xtol * max(1,||x||) and nothing else.  With an
+    unreachable xtol the iteration ends with GMPNP_STAGNATED (4) when xtol_floor allows it, with GMPNP_MAXIT (1)
+    when it does not, and d_dx returns what the criterion saw."""
+    from gmpnp_b200 import meshio, params, solver1d
+    from gmpnp_b200._lib import NewtonOpts
+    m = meshio.load_mesh("1D_variable_1um_mesh_1090")
+    prm = params.params_1d(L_n=1e-6)
+    s = solver1d.Solver1D(m.x[:, 0], batch=1)
+    s.set_params([prm])
+    path = np.array([[-0.5, -1.0]])
+    for floor, want in ((1e-6, 4), (0.0, 1)):
+        u = solver1d.bulk_state(1, s.n, _dev())
+        o = NewtonOpts.steady(xtol=1e-20, jac_rule=1, xtol_floor=floor, maxit=12)
+        o.pivot = 0
+        out = s.steady(u, path, o)
+        assert out["status"].tolist() == [want], (floor, out["status"].tolist(), out["dx"].tolist())
+        assert 0.0 <= float(out["dx"][0]) < 1e-9
+    u = solver1d.bulk_state(1, s.n, _dev())
+    out = s.steady(u, path, NewtonOpts.steady(xtol=1e-12, jac_rule=1))
+    assert out["status"].tolist() == [0] and float(out["dx"][0]) <= 1e-12
+
+
 def test_steady_continuation_matches_golden_50um(lib):
     """Steady parity: rel-L2 per field <= 1e-8 at V = -1, -2.5, -5, -7.5, -10, -12.5,
     each reached by its own continuation path inside one batched launch."""
