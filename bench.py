@@ -6,8 +6,7 @@ config 2: {K,Cs} x 256 voltages x {0.1,0.5,1.0} M x 5 meshes = 7680 steady probl
 
 A "step" = one pass of the hot path over the whole batch: every sweep point goes from the bulk
 state to its converged steady solution (voltage continuation + Newton, all inside the CUDA
-kernels; points that end at the round-off floor are polished with the pivoted elimination and
-failed points retried INSIDE the step).  Prints ONE JSON line (see the task contract):
+kernels; failed points are retried INSIDE the step and only strictly converged points count).  Prints ONE JSON line (see the task contract):
 `value` = solves/s with inputs resident in HBM, `e2e` = the same through the public host API with
 host buffers (H2D of parameters and continuation paths, D2H of every solution profile and the
 gather of the per-point summaries inside the timed region), `roofline` for the fused
@@ -57,11 +56,14 @@ def parse():
     ap.add_argument("--pore3d-batch", type=int, default=128, help="3D pore problems per GPU in the 3D part (0: skip)")
     ap.add_argument("--no-config1", action="store_true", help="skip the config-1 latency measurement")
     ap.add_argument("--pivot", type=int, default=0, help="partial pivoting inside the 7x7 blocks (0: none; "
-                    "stalled points are polished / failed points retried with pivoting, see Sweep1D)")
+                    "failed points are retried with pivoting, see Sweep1D)")
     ap.add_argument("--dv", type=float, default=0.75, help="largest voltage increment of the continuation [V_T]")
     ap.add_argument("--xtol-path", type=float, default=1.0,
                     help="increment tolerance of the intermediate continuation stages (1.0 = one Newton corrector "
-                         "per voltage increment); the final stage always converges to xtol = 1e-12")
+                         "per voltage increment); the final stage always converges to --xtol")
+    ap.add_argument("--xtol", type=float, default=1e-10,
+                    help="increment tolerance at the target voltage: ||dx||_inf <= xtol * max(1, ||u||_inf); 1e-12 is below "
+                         "the fp64 round-off floor of the 200 um-mesh problems (profiles/r02_floor_diagnostic.log)")
     ap.add_argument("--scaling", default="both", choices=["weak", "strong", "both"],
                     help="N > 1: which arms to run (the headline is always the weak one)")
     return ap.parse_args()
@@ -71,7 +73,7 @@ def base_config(args):
     """Workload description shared verbatim by both arms (b200 and reference)."""
     return {"workload": WORKLOAD if args.voltages == 256 else f"reduced sweep ({args.voltages} V/chain)",
             "continuation": f"dV<={args.dv:g} V_T, one Newton corrector per increment (xtol_path {args.xtol_path:g}), "
-                            "xtol 1e-12 at the target voltage, consistent Jacobian (jac_rule 1)",
+                            f"xtol {args.xtol:g} at the target voltage, consistent Jacobian (jac_rule 1)",
             "points_total_config2": 30 * args.voltages}
 
 
@@ -93,7 +95,7 @@ def _worker_init():
 
 
 def _cpu_solve_point(task):
-    cation, conc, L_n, V, dv, xtol_path, want_u = task
+    cation, conc, L_n, V, dv, xtol_path, want_u, xtol = task
     import numpy as np
     from gmpnp_b200 import meshio, params
     from gmpnp_b200.sweep_points import voltage_paths
@@ -108,7 +110,7 @@ def _cpu_solve_point(task):
     info = {}
     t = time.perf_counter()
     try:
-        u, its = osolver.steady_1d(x, prm, path, xtol=1e-12, xtol_path=xtol_path, jac_rule=1, info=info)
+        u, its = osolver.steady_1d(x, prm, path, xtol=xtol, xtol_path=xtol_path, jac_rule=1, info=info)
         ok = True
     except RuntimeError:
         u, its, ok = None, [], False
@@ -144,8 +146,8 @@ class CpuPool:
         # touch every worker once (imports done, meshes cached lazily)
         self.pool.map(_noop, range(4 * self.cores), chunksize=1)
 
-    def solve(self, points, dv, xtol_path, want_u=False):
-        work = [(p.cation, p.conc, p.L_n, p.V, dv, xtol_path, want_u) for p in points]
+    def solve(self, points, dv, xtol_path, want_u=False, xtol=1e-10):
+        work = [(p.cation, p.conc, p.L_n, p.V, dv, xtol_path, want_u, xtol) for p in points]
         # longest first (LPT) so the tail of the sample does not idle the cores
         order = sorted(range(len(work)), key=lambda i: -abs(work[i][3]) * (1 + 1e6 * work[i][2]))
         t = time.perf_counter()
@@ -238,12 +240,12 @@ def reference_arm(args):
     np.random.default_rng(2).shuffle(pts)
     step_pts = [pts[i * args.ref_sample:(i + 1) * args.ref_sample] for i in range(args.steps + 1)]
     if min(args.warmup, 1):
-        pool.solve(step_pts[args.steps], args.dv, args.xtol_path)       # warm-up step (meshes cached in the workers)
+        pool.solve(step_pts[args.steps], args.dv, args.xtol_path, xtol=args.xtol)   # warm-up (meshes cached in the workers)
     # the K steps' samples are independent sweep points (the reference: one process per point, README.md:37), so they
     # stream through the pool without a barrier between steps; ms_per_step = total wall / K
     timed = [p for k in range(args.steps) for p in step_pts[k]]
     n_pts = len(timed)
-    res_all, T = pool.solve(timed, args.dv, args.xtol_path)
+    res_all, T = pool.solve(timed, args.dv, args.xtol_path, xtol=args.xtol)
     pool.close()
     v = n_pts / T
     info = cpu_summary(res_all, T, pool.cores, n_pts,
@@ -435,7 +437,8 @@ class SweepArm:
         from gmpnp_b200.solver1d import NC
         self.torch, self.sweep, self.world, self.dev, self.args = torch, sweep, world, dev, args
         self.n_global = n_global
-        self.sw = sweep.Sweep1D(pts, device=local, dv_max=args.dv, xtol_path=args.xtol_path, pivot=args.pivot)
+        self.sw = sweep.Sweep1D(pts, device=local, dv_max=args.dv, xtol_path=args.xtol_path, pivot=args.pivot,
+                                xtol=args.xtol)
         sw = self.sw
         self.h_params = [torch.as_tensor(g["packed"]).pin_memory() for g in sw.groups]
         self.h_paths = [torch.as_tensor(g["path"]).pin_memory() for g in sw.groups]
@@ -457,7 +460,7 @@ class SweepArm:
 
     def resident_step(self):
         outs = self.sw.solve_resident()
-        self.fin = self.sw.finish(outs)                 # polish stalled points / retry failed ones (syncs the step)
+        self.fin = self.sw.finish(outs)                 # retry failed points, if any (one D2H read of two counters)
         return outs
 
     def e2e_step(self):
@@ -544,8 +547,8 @@ def parity_block(gpu_u, cpu_res, pts, gpu_its):
             "max_rel_l2_per_field": {n: float(v) for n, v in zip(names, worst)},
             "newton_count_diff_max_abs": int(max(abs(d) for d in dits)) if dits else None,
             "worst_point": worst_pt, "ok": bool(n_cmp > 0 and worst.max() <= PARITY_TOL),
-            "setting": "the benchmarked one: pivot-free elimination, consistent Jacobian, Euler-Newton path, xtol 1e-12; "
-                       "stratified over cation x concentration x mesh"}
+            "setting": "the benchmarked one (pivot-free elimination, consistent Jacobian, Euler-Newton path, same xtol on "
+                       "both sides); stratified over cation x concentration x mesh"}
 
 
 def main():
@@ -612,7 +615,7 @@ def main():
     rc = 0
     if rank == 0:
         ms, ms_e2e = W["ms"], W["ms_e2e"]
-        n_ok = W["converged"]                                     # strictly converged points only
+        n_ok = W["converged"]                                     # strictly converged points only (status 0)
         achieved = (W["alg_bytes"] / world) / (ms * 1e-3) / 1e9    # per-GPU GB/s of the kernel
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         ratio = json.load(open(prof)).get("newton1d_dram_bytes_over_algorithmic_bytes") if os.path.exists(prof) else None
@@ -623,13 +626,13 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": cfg,
             "run": {"points_per_gpu": n_cfg, "points": W["n_points"], "converged": W["converged"],
-                    "stagnated_at_floor_after_polish": W["stagnated"], "failed": W["failed"],
-                    "polished_with_pivoting_per_step": W["polished"], "retried_per_step": W["retried"],
+                    "stagnated_at_floor": W["stagnated"], "failed": W["failed"],
+                    "retried_per_step": W["retried"],
                     "max_final_dx_converged": W["summary"]["max_final_dx_converged"],
+                    "max_final_dx_stagnated": W["summary"]["max_final_dx_stagnated"],
                     "newton_iterations_per_step": W["newton_iterations"],
-                    "in_block_pivoting": "on" if args.pivot else "off (equilibrated rows); points that stall at the "
-                                         "round-off floor (status 4) are polished with the pivoted elimination and failed "
-                                         "points retried inside the timed step",
+                    "in_block_pivoting": "on" if args.pivot else "off (equilibrated rows); failed points are retried with "
+                                         "pivoting inside the timed step; only status-0 points count in `value`",
                     "cache": "working set (elimination workspace 10.7 GB/GPU) >> 126 MB L2, no flush needed",
                     "parallelism": f"weak: one full sweep per GPU, {world} GPU(s), no data-path collective; "
                                    "one all_gather of the per-point summaries in the e2e region"},
@@ -654,7 +657,7 @@ def main():
                 "value": S["converged"] / (S["ms"] * 1e-3), "ms_per_step": S["ms"],
                 "e2e": {"value": S["converged"] / (S["ms_e2e"] * 1e-3), "ms_per_step": S["ms_e2e"],
                         "h2d_bytes_per_step": S["h2d"], "d2h_bytes_per_step": S["d2h"]},
-                "points": S["n_points"], "converged": S["converged"], "stagnated_at_floor_after_polish": S["stagnated"],
+                "points": S["n_points"], "converged": S["converged"], "stagnated_at_floor": S["stagnated"],
                 "failed": S["failed"], "gpu_launches": S["launches"],
                 "roofline_frac_per_gpu": (S["alg_bytes"] / world) / (S["ms"] * 1e-3) / 1e9 / peak}
         # fp64: executed flops of the hot kernel per block row and Newton iteration (thread-level DFMA x2 + DMUL + DADD,
@@ -674,7 +677,7 @@ def main():
         if pore3d is not None:
             line["pore3d"] = pore3d
         if pool is not None:
-            res, wall = pool.solve(sample, args.dv, args.xtol_path, want_u=True)
+            res, wall = pool.solve(sample, args.dv, args.xtol_path, want_u=True, xtol=args.xtol)
             line["cpu_baseline"] = cpu_summary(res, wall, pool.cores, len(sample),
                                                f"{len(sample)} of the {n_cfg} sweep points, {args.cpu_sample} per (mesh, "
                                                "concentration, cation) chain, random voltages (seed 0)")

@@ -49,18 +49,23 @@ class Sweep1D:
     """All sweep points of one rank, grouped by mesh into one :class:`Solver1D` each."""
 
     def __init__(self, points, device: int = 0, utilities_dir=None, dv_max: float = 0.5,
-                 xtol: float = 1e-12, xtol_path: float = 1e-1, maxit: int = 50, jac_rule: int = 1,
-                 pivot: int = 0, xtol_floor: float = 1e-6):
+                 xtol: float = 1e-10, xtol_path: float = 1e-1, maxit: int = 50, jac_rule: int = 1,
+                 pivot: int = 0, xtol_floor: float = 1e-8):
         """``pivot``: partial pivoting inside the 7x7 blocks of the block-Thomas elimination.  The sweep default is
         0: with the Poisson row equilibrated the in-block pivot is the diagonal in 99.95 % of the steps, and a
         Newton iteration that converges (increment criterion, residual evaluated independently of the linear
         solve) is correct whatever the pivoting of its linear solves; points that do NOT converge are re-run
         with pivoting and halved voltage increments by :meth:`retry_failed`.
 
-        ``xtol_floor`` (gmpnp.h): with the pivot-free elimination the last increments of a few points stall at the
-        round-off floor of the linear solve, above ``xtol``.  Those points end with status 4 (GMPNP_STAGNATED), never
-        with 0; :meth:`summary` counts them and reports their largest final relative increment, and
-        :meth:`retry_failed` (``include_stagnated=True``) polishes them with the pivoted elimination."""
+        ``xtol`` = 1e-10: measured on a B200 (profiles/r02_floor_diagnostic.log), the Newton increments of the
+        200 um-mesh problems do not contract below 4e-12 ... 2e-11 of max|u| whatever the pivoting or the Jacobian
+        rule -- that is the fp64 round-off floor of the residual evaluation of these ill-conditioned problems (the
+        converged states of this library and of the SuperLU oracle differ by 4e-10 there, of 1e-12 ... 1e-15 on the
+        short meshes) -- so 1e-12 is not a reachable increment tolerance for 18 % of config 2.  With quadratic
+        convergence an accepted increment of 1e-10 leaves an error far below that.  ``xtol_floor`` (gmpnp.h) is the
+        safety net: an increment that stalls between ``xtol`` and ``xtol_floor`` ends with status 4
+        (GMPNP_STAGNATED), never with 0; :meth:`summary` counts those points and reports their largest final
+        relative increment."""
         self.points = list(points)
         self.device = torch.device("cuda", int(device))
         self.dv_max, self.xtol, self.xtol_path, self.maxit = dv_max, xtol, xtol_path, maxit
@@ -142,13 +147,14 @@ class Sweep1D:
         res["max_final_dx_stagnated"] = float(dx[st == 4].max()) if (st == 4).any() else None
         return res
 
-    def finish(self, outs):
-        """End of a sweep pass: points that stalled at the round-off floor are polished with the pivoted elimination,
-        failed points are retried with halved increments.  One device->host read of two counters when there is
-        nothing to do."""
+    def finish(self, outs, polish: bool = False):
+        """End of a sweep pass: failed points are retried with pivoting and halved voltage increments; with
+        ``polish`` the points that stalled above ``xtol`` (status 4) take a few pivoted iterations more (measured: it
+        does not help, the floor is not the pivoting).  One device->host read of two counters when there is nothing
+        to do."""
         st = torch.cat([o["status"] for o in outs])
         n4, nbad = torch.stack([(st == 4).sum(), ((st != 0) & (st != 4)).sum()]).tolist()
-        polished = self.polish_stagnated(outs) if n4 else 0
+        polished = self.polish_stagnated(outs) if (n4 and polish) else 0
         retried = self.retry_failed(outs) if nbad else 0
         return dict(polished=int(polished), retried=int(retried))
 

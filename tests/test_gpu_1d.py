@@ -198,7 +198,7 @@ def test_config1_full_default_run_100_steps(lib):
                                               ("Cs", 0.5, 1e-6, -12.5 * 77 / 256), ("K", 1.0, 10e-6, -12.5 * 140 / 256)])
 def test_benchmarked_setting_matches_oracle(lib, cation, conc, L_n, V):
     """The bench's own setting (Sweep1D defaults of bench.py: pivot-free elimination, consistent Jacobian, Euler-Newton
-    path with dV <= 0.75 and one corrector per increment, xtol 1e-12, stalled points polished) against the oracle
+    path with dV <= 0.75 and one corrector per increment, xtol 1e-10) against the oracle
     solving the same sweep point with the same continuation: rel-L2 per field <= 1e-8, Newton counts within 1."""
     from gmpnp_b200 import meshio, params, sweep
     from oracle import solver as osolver
@@ -213,7 +213,7 @@ def test_benchmarked_setting_matches_oracle(lib, cation, conc, L_n, V):
     x = meshio.load_mesh(params.mesh_name_1d(L_n)).x[:, 0]
     prm = params.params_1d(concentration_elec=conc, cation=cation, L_n=L_n, voltage_multiplier=V)
     path = sweep.voltage_paths(np.array([V]), 0.75)[0]
-    uo, its = osolver.steady_1d(x, prm, path[~np.isnan(path)], xtol=1e-12, xtol_path=1.0, jac_rule=1)
+    uo, its = osolver.steady_1d(x, prm, path[~np.isnan(path)], xtol=1e-10, xtol_path=1.0, jac_rule=1)
     for c in range(7):
         assert rel_l2(got[:, c], uo[:, c]) < 1e-8, (c, rel_l2(got[:, c], uo[:, c]))
     assert abs(int(outs[0]["iters"].sum()) - sum(its)) <= 1, (outs[0]["iters"].tolist(), its)
