@@ -71,6 +71,9 @@ SIGNATURES = {
     "gmpnp_spmv_3d": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "gmpnp_newton_3d": (_i, [_vp, _vp, _vp, _po, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gmpnp_median_3d": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "gmpnp_set_march_data_3d": (_i, [_vp, C.POINTER(C.c_byte), _pd, _pd, _i]),
+    "gmpnp_march_3d": (_i, [_vp, _vp, _vp, _i, _po, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gmpnp_steady_3d": (_i, [_vp, _vp, _vp, _po, _d, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _pi, _vp]),
     "gmpnp_spmv_rows_3d": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "gmpnp_vec_multi_dot": (_i, [_vp, _vp, C.c_longlong, _i, _vp, C.c_longlong, _vp, _vp]),
     "gmpnp_vec_lincomb": (_i, [_vp, _vp, C.c_longlong, _i, _vp, _d, _vp, _vp, C.c_longlong, _vp]),

@@ -60,4 +60,5 @@ struct gmpnp_handle {
     int* d_ismall = nullptr;
     void* h_pinned = nullptr;     // pinned host scratch for control read-backs
     double* d_sort = nullptr;     // median scratch
+    void* ext3d = nullptr;        // 3D-only state (pore3d.cu: Host3D), owned by the handle
 };

@@ -13,10 +13,12 @@
 // HBM layout:  u[problem][vertex][9];  J[problem][block][9][9] (BSR, row-major blocks, blocks of a
 // row sorted by column);  per-tet moment records mom[problem][tet][60], Fe[problem][tet][4][9].
 #include <algorithm>
-#include <map>
-#include <mutex>
+#include <cmath>
 #include <numeric>
+#include <cooperative_groups.h>
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace pore3d {
 
@@ -38,9 +40,7 @@ __constant__ double QF_W[5];
 __constant__ double QJ_L[14][4];
 __constant__ double QJ_W[14];
 
-static void upload_rules() {
-    static bool done = false;
-    if (done) return;
+static void upload_rules() {       // per handle creation: constant memory belongs to the current device's context
     double fx[5][3] = {{0.25, 0.25, 0.25}, {0.5, 1.0 / 6.0, 1.0 / 6.0}, {1.0 / 6.0, 0.5, 1.0 / 6.0},
                        {1.0 / 6.0, 1.0 / 6.0, 0.5}, {1.0 / 6.0, 1.0 / 6.0, 1.0 / 6.0}};
     double fw[5] = {-0.8, 0.45, 0.45, 0.45, 0.45};
@@ -66,7 +66,6 @@ static void upload_rules() {
     cudaMemcpyToSymbol(QF_W, fw, sizeof(fw));
     cudaMemcpyToSymbol(QJ_L, jl, sizeof(jl));
     cudaMemcpyToSymbol(QJ_W, jw, sizeof(jw));
-    done = true;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -535,104 +534,6 @@ __global__ void bjacobi_invert_kernel(int n_vert, int n_blocks, const int* __res
 }
 
 // ---------------------------------------------------------------------------------------
-// Coarse space (piecewise constants per z-slab and component): A_c = P^T J P, explicit inverse
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-coarse_setup_kernel(int n_vert, int n_blocks, const int* __restrict__ row_ptr, const int* __restrict__ col_idx,
-                    const int* __restrict__ agg, const int* __restrict__ dir_flag, const double* __restrict__ J,
-                    double* __restrict__ Aci) {
-    extern __shared__ double Ac[];          // [NCO][NCO]
-    const int prob = blockIdx.x;
-    for (int i = threadIdx.x; i < NCO * NCO; i += blockDim.x) Ac[i] = 0.0;
-    __syncthreads();
-    const double* Jp = J + (long)prob * n_blocks * 81;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int row = w; row < n_vert; row += nw) {
-        const int I = agg[row];
-        for (int s = row_ptr[row]; s < row_ptr[row + 1]; ++s) {
-            const int col = col_idx[s];
-            const int Jc = agg[col];
-            for (int e = lane; e < 81; e += 32) {
-                const int i = e / 9, j = e % 9;
-                if (dir_flag[(long)row * NC + i] >= 0 || dir_flag[(long)col * NC + j] >= 0) continue;
-                atomicAdd(&Ac[(I * NC + i) * NCO + Jc * NC + j], Jp[(long)s * 81 + e]);
-            }
-        }
-    }
-    __syncthreads();
-    // empty coarse columns (all members Dirichlet) -> identity
-    for (int i = threadIdx.x; i < NCO; i += blockDim.x)
-        if (Ac[i * NCO + i] == 0.0) Ac[i * NCO + i] = 1.0;
-    __syncthreads();
-    // in-place Gauss-Jordan inversion without pivoting on the (diagonally dominant-ish) Galerkin matrix;
-    // a vanishing pivot is replaced to keep the preconditioner finite
-    __shared__ double pivinv;
-    for (int c = 0; c < NCO; ++c) {
-        if (threadIdx.x == 0) {
-            double p = Ac[c * NCO + c];
-            if (!(fabs(p) > 1e-300)) p = 1.0;
-            pivinv = 1.0 / p;
-        }
-        __syncthreads();
-        const double pi = pivinv;
-        // scale pivot row (except pivot), pivot element becomes 1/p
-        for (int j = threadIdx.x; j < NCO; j += blockDim.x)
-            if (j != c) Ac[c * NCO + j] *= pi;
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < NCO * NCO; idx += blockDim.x) {
-            const int r = idx / NCO, j = idx % NCO;
-            if (r == c || j == c) continue;
-            Ac[idx] -= Ac[r * NCO + c] * Ac[c * NCO + j];
-        }
-        __syncthreads();
-        for (int r = threadIdx.x; r < NCO; r += blockDim.x)
-            Ac[r * NCO + c] = (r == c) ? pi : -Ac[r * NCO + c] * pi;
-        __syncthreads();
-    }
-    for (int i = threadIdx.x; i < NCO * NCO; i += blockDim.x) Aci[(long)prob * NCO * NCO + i] = Ac[i];
-}
-
-// yc = A_c^{-1} P^T r   (one CTA per problem; deterministic)
-__global__ void __launch_bounds__(NCO)
-coarse_solve_kernel(int n_vert, const int* __restrict__ agg_ptr, const int* __restrict__ agg_nodes,
-                    const int* __restrict__ dir_flag, const double* __restrict__ Aci, const double* __restrict__ r,
-                    long rstride, double* __restrict__ yc) {
-    __shared__ double rc[NCO];
-    const int prob = blockIdx.x;
-    const int t = threadIdx.x, I = t / NC, i = t % NC;
-    const double* rp = r + (long)prob * rstride;
-    double s = 0.0;
-    for (int k = agg_ptr[I]; k < agg_ptr[I + 1]; ++k) {
-        const int v = agg_nodes[k];
-        if (dir_flag[(long)v * NC + i] < 0) s += rp[(long)v * NC + i];
-    }
-    rc[t] = s;
-    __syncthreads();
-    const double* A = Aci + (long)prob * NCO * NCO + (long)t * NCO;
-    double y = 0.0;
-    for (int j = 0; j < NCO; ++j) y += A[j] * rc[j];
-    yc[(long)prob * NCO + t] = y;
-}
-
-// z = D^{-1} r + P yc
-__global__ void precond_apply_kernel(int n_vert, const int* __restrict__ agg, const int* __restrict__ dir_flag,
-                                     const double* __restrict__ Dinv, const double* __restrict__ yc,
-                                     const double* __restrict__ r, long rstride, double* __restrict__ z,
-                                     int use_coarse) {
-    const int prob = blockIdx.y;
-    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long)n_vert * NC) return;
-    const int v = (int)(idx / NC), i = (int)(idx % NC);
-    const double* D = Dinv + ((long)prob * n_vert + v) * 81 + i * 9;
-    const double* rp = r + (long)prob * rstride + (long)v * NC;
-    double s = 0.0;
-#pragma unroll
-    for (int j = 0; j < 9; ++j) s += D[j] * rp[j];
-    if (use_coarse && dir_flag[idx] < 0) s += yc[(long)prob * NCO + agg[v] * NC + i];
-    z[(long)prob * n_vert * NC + idx] = s;
-}
-
-// ---------------------------------------------------------------------------------------
 // Krylov vector kernels (one CTA per problem for reductions: deterministic)
 // ---------------------------------------------------------------------------------------
 __device__ double block_sum(double v, double* sh) {
@@ -645,31 +546,6 @@ __device__ double block_sum(double v, double* sh) {
     const int nw = (blockDim.x + 31) >> 5;
     for (int k = 0; k < nw; ++k) s += sh[k];
     return s;
-}
-
-// dots[prob][k] = V_k . w for k < nvec   (grid = (nvec, batch))
-__global__ void __launch_bounds__(256)
-multi_dot_kernel(long n, long vstride, const double* __restrict__ V, const double* __restrict__ w,
-                 double* __restrict__ dots, int ld) {
-    __shared__ double sh[8];
-    const int k = blockIdx.x, prob = blockIdx.y;
-    const double* vk = V + ((long)prob * ld + k) * vstride;
-    const double* wp = w + (long)prob * n;
-    double s = 0.0;
-    for (long i = threadIdx.x; i < n; i += blockDim.x) s += vk[i] * wp[i];
-    s = block_sum(s, sh);
-    if (threadIdx.x == 0) dots[(long)prob * ld + k] = s;
-}
-
-// w -= sum_k dots[k] V_k ; optionally hacc[k] += dots[k]
-__global__ void gs_update_kernel(long n, long vstride, int nvec, const double* __restrict__ V,
-                                 const double* __restrict__ dots, double* __restrict__ w, int ld) {
-    const int prob = blockIdx.y;
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double s = w[(long)prob * n + i];
-    for (int k = 0; k < nvec; ++k) s -= dots[(long)prob * ld + k] * V[((long)prob * ld + k) * vstride + i];
-    w[(long)prob * n + i] = s;
 }
 
 // nrm[prob] = ||w|| ; vout[prob * vstride + :] = w / ||w||   (one CTA per problem)
@@ -688,71 +564,6 @@ norm_scale_kernel(long n, const double* __restrict__ w, double* __restrict__ vou
         const double inv = (nr > 0.0) ? 1.0 / nr : 0.0;
         for (long i = threadIdx.x; i < n; i += blockDim.x) vout[(long)prob * vstride + i] = wp[i] * inv;
     }
-}
-
-// Hessenberg column j: h = h1 + h2 (CGS2), h[j+1] = nrm; apply stored Givens, create new one, update g.
-// state per problem: H[(m+1) x m] column-major, cs[m], sn[m], gvec[m+1], jdone, beta
-__global__ void givens_kernel(int batch, int j, int m, const double* __restrict__ d1, const double* __restrict__ d2,
-                              const double* __restrict__ nrm, double* __restrict__ H, double* __restrict__ cs,
-                              double* __restrict__ sn, double* __restrict__ gvec, int* __restrict__ jdone,
-                              const double* __restrict__ tol_abs, int ld) {
-    const int prob = blockIdx.x * blockDim.x + threadIdx.x;
-    if (prob >= batch) return;
-    if (jdone[prob] >= 0) return;                 // this problem already converged in this cycle
-    double* h = H + ((long)prob * m + j) * (m + 1);
-    for (int k = 0; k <= j; ++k) h[k] = d1[(long)prob * ld + k] + d2[(long)prob * ld + k];
-    h[j + 1] = nrm[prob];
-    double* c = cs + (long)prob * m;
-    double* s = sn + (long)prob * m;
-    for (int k = 0; k < j; ++k) {
-        const double t = c[k] * h[k] + s[k] * h[k + 1];
-        h[k + 1] = -s[k] * h[k] + c[k] * h[k + 1];
-        h[k] = t;
-    }
-    const double a = h[j], b = h[j + 1];
-    const double d = hypot(a, b);
-    const double cj = (d > 0.0) ? a / d : 1.0, sj = (d > 0.0) ? b / d : 0.0;
-    c[j] = cj; s[j] = sj;
-    h[j] = d; h[j + 1] = 0.0;
-    double* g = gvec + (long)prob * (m + 1);
-    g[j + 1] = -sj * g[j];
-    g[j] = cj * g[j];
-    if (fabs(g[j + 1]) <= tol_abs[prob] || !(nrm[prob] > 0.0)) jdone[prob] = j + 1;
-}
-
-// y = H^{-1} g (upper triangular, first jd columns); coef[prob][k] = y_k (0 beyond jd)
-__global__ void hsolve_kernel(int batch, int m, const double* __restrict__ H, const double* __restrict__ gvec,
-                              const int* __restrict__ jdone, double* __restrict__ coef, int ld) {
-    const int prob = blockIdx.x * blockDim.x + threadIdx.x;
-    if (prob >= batch) return;
-    const int jd = (jdone[prob] >= 0) ? jdone[prob] : m;
-    double* y = coef + (long)prob * ld;
-    const double* g = gvec + (long)prob * (m + 1);
-    for (int k = 0; k < ld; ++k) y[k] = 0.0;
-    for (int k = jd - 1; k >= 0; --k) {
-        double s = g[k];
-        for (int l = k + 1; l < jd; ++l) s -= H[((long)prob * m + l) * (m + 1) + k] * y[l];
-        const double d = H[((long)prob * m + k) * (m + 1) + k];
-        y[k] = (d != 0.0) ? s / d : 0.0;
-    }
-}
-
-// out = sum_k coef[k] V_k
-__global__ void lincomb_kernel(long n, long vstride, int nvec, const double* __restrict__ V,
-                               const double* __restrict__ coef, double* __restrict__ out, int ld) {
-    const int prob = blockIdx.y;
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double s = 0.0;
-    for (int k = 0; k < nvec; ++k) s += coef[(long)prob * ld + k] * V[((long)prob * ld + k) * vstride + i];
-    out[(long)prob * n + i] = s;
-}
-
-// y = a*x + b*y (per problem scalars optional)
-__global__ void axpby_kernel(long n, double a, const double* __restrict__ x, double b, double* __restrict__ y) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x + (long)blockIdx.y * n;
-    if ((long)blockIdx.x * blockDim.x + threadIdx.x >= n) return;
-    y[i] = a * x[i] + b * y[i];
 }
 
 // Newton update with per-problem mask: u -= relax * dx where active; dxmax/umax per problem
@@ -1057,6 +868,652 @@ bjacobi_apply_kernel(int n_rows, const double* __restrict__ Dinv, const double* 
     z[idx] = s;
 }
 
+// ---------------------------------------------------------------------------------------
+// Coarse-space set-up, deterministic (ordered partial sums, no atomics) with a pivoted inverse.
+// Host side (gmpnp_create_3d) sorts the BSR blocks by (slab of row, slab of column) pair and cuts every
+// pair's list into chunks of <= CP_CHUNK blocks; pass 1 sums the non-Dirichlet entries of a chunk in list
+// order, pass 2 adds the chunk sums of a pair in chunk order, inverts A_c = P^T J P by Gauss-Jordan with
+// partial pivoting and stores the TRANSPOSED inverse (coalesced reads in the solve).
+// ---------------------------------------------------------------------------------------
+constexpr int CP_CHUNK = 128;
+
+__global__ void __launch_bounds__(96)
+coarse_partial_kernel(int n_blocks, const int* __restrict__ chunk_ptr, const int* __restrict__ cp_blk,
+                      const int* __restrict__ blk_row, const int* __restrict__ col_idx,
+                      const int* __restrict__ dir_flag, const double* __restrict__ J, double* __restrict__ part,
+                      int n_chunk) {
+    const int chunk = blockIdx.x, prob = blockIdx.y, e = threadIdx.x;
+    if (e >= 81) return;
+    const int i = e / 9, j = e % 9;
+    const double* Jp = J + (long)prob * n_blocks * 81;
+    double s = 0.0;
+    for (int c = chunk_ptr[chunk]; c < chunk_ptr[chunk + 1]; ++c) {
+        const int b = cp_blk[c];
+        if (dir_flag[(long)blk_row[b] * NC + i] >= 0 || dir_flag[(long)col_idx[b] * NC + j] >= 0) continue;
+        s += Jp[(long)b * 81 + e];
+    }
+    part[((long)prob * n_chunk + chunk) * 81 + e] = s;
+}
+
+// one CTA per problem; Ac in shared memory [NCO][NCO]; flag[prob] = number of vanishing pivots replaced by 1
+__global__ void __launch_bounds__(1024)
+coarse_invert_pivoted_kernel(const int* __restrict__ chunk_pair, const double* __restrict__ part, int n_chunk,
+                             double* __restrict__ AciT, int* __restrict__ flag) {
+    extern __shared__ double Ac[];          // [NCO][NCO]
+    __shared__ int perm[NCO];
+    __shared__ double pivinv;
+    __shared__ int prow, nbad;
+    const int prob = blockIdx.x, tid = threadIdx.x;
+    for (int i = tid; i < NCO * NCO; i += blockDim.x) Ac[i] = 0.0;
+    if (tid == 0) nbad = 0;
+    __syncthreads();
+    // chunks are sorted by pair, so the chunks of a pair are consecutive: 12 groups of 81 threads walk the chunk
+    // list; group g owns the pairs with (pair % 12 == g), and adds their chunk sums in chunk order
+    const int grp = tid / 81, e = tid % 81;
+    if (grp < 12) {
+        const int i = e / 9, j = e % 9;
+        for (int c = 0; c < n_chunk; ++c) {
+            const int pr = chunk_pair[c];
+            if (pr % 12 != grp) continue;
+            const int I = pr / NZ, Jc = pr % NZ;
+            Ac[(I * NC + i) * NCO + Jc * NC + j] += part[((long)prob * n_chunk + c) * 81 + e];
+        }
+    }
+    __syncthreads();
+    // empty coarse rows (all members Dirichlet) -> identity
+    for (int i = tid; i < NCO; i += blockDim.x) {
+        bool empty = true;
+        for (int j = 0; j < NCO; ++j) if (Ac[i * NCO + j] != 0.0) { empty = false; break; }
+        if (empty) Ac[i * NCO + i] = 1.0;
+    }
+    __syncthreads();
+    // in-place Gauss-Jordan inversion with partial pivoting (row swaps recorded in perm)
+    for (int c = 0; c < NCO; ++c) {
+        if (tid < 32) {
+            double best = -1.0; int bi = c;
+            for (int r = c + tid; r < NCO; r += 32) {
+                const double a = fabs(Ac[r * NCO + c]);
+                if (a > best) { best = a; bi = r; }
+            }
+            for (int o = 16; o >= 1; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            if (tid == 0) { prow = bi; perm[c] = bi; }
+        }
+        __syncthreads();
+        const int p = prow;
+        if (p != c) {
+            for (int j = tid; j < NCO; j += blockDim.x) {
+                const double t = Ac[c * NCO + j]; Ac[c * NCO + j] = Ac[p * NCO + j]; Ac[p * NCO + j] = t;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double pv = Ac[c * NCO + c];
+            if (!(fabs(pv) > 1e-300) || !isfinite(pv)) { pv = 1.0; nbad++; }
+            pivinv = 1.0 / pv;
+        }
+        __syncthreads();
+        const double pi = pivinv;
+        for (int j = tid; j < NCO; j += blockDim.x)
+            if (j != c) Ac[c * NCO + j] *= pi;
+        __syncthreads();
+        for (int idx = tid; idx < NCO * NCO; idx += blockDim.x) {
+            const int r = idx / NCO, j = idx % NCO;
+            if (r == c || j == c) continue;
+            Ac[idx] -= Ac[r * NCO + c] * Ac[c * NCO + j];
+        }
+        __syncthreads();
+        for (int r = tid; r < NCO; r += blockDim.x)
+            Ac[r * NCO + c] = (r == c) ? pi : -Ac[r * NCO + c] * pi;
+        __syncthreads();
+    }
+    // (P A)^-1 = A^-1 P^T: undo the row swaps as column swaps, last swap first
+    for (int c = NCO - 1; c >= 0; --c) {
+        const int p = perm[c];
+        if (p != c) {
+            for (int r = tid; r < NCO; r += blockDim.x) {
+                const double t = Ac[r * NCO + c]; Ac[r * NCO + c] = Ac[r * NCO + p]; Ac[r * NCO + p] = t;
+            }
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < NCO * NCO; idx += blockDim.x) {
+        const int r = idx / NCO, j = idx % NCO;
+        AciT[(long)prob * NCO * NCO + (long)j * NCO + r] = Ac[idx];      // transposed
+    }
+    if (tid == 0 && flag) flag[prob] = nbad;
+}
+
+// ---------------------------------------------------------------------------------------
+// Persistent GMRES: one thread-block CLUSTER per problem runs the whole right-preconditioned restarted
+// GMRES(m) solve  J dx = b  (block-Jacobi + z-slab coarse correction, CGS2) in ONE launch, with no host
+// synchronisation: the G CTAs of a cluster own contiguous chunks of block rows / vector entries, exchange their
+// partial dot products through distributed shared memory (fixed rank order: deterministic, every CTA gets the
+// bitwise-identical sum, so the control flow stays cluster-uniform) and meet at cluster barriers.  The small
+// Hessenberg / Givens recurrences are done redundantly by thread 0 of every CTA.
+// ---------------------------------------------------------------------------------------
+constexpr int GM_THREADS = 512;
+constexpr int GM_WARPS = GM_THREADS / 32;
+constexpr int GM_KT = 8;                 // dot products per pass over the chunk
+
+struct GmresArgs {
+    int n_vert, n_blocks, m, maxit;
+    double rtol;
+    const int *row_ptr, *col_idx, *agg, *agg_ptr, *agg_nodes, *dir_flag;
+    const double *J, *Dinv, *AciT, *b;
+    double *x, *V, *w, *z;
+    const int* enabled;                  // [batch] or nullptr: problems with 0 are skipped
+    int* its;                            // [batch] GMRES iterations done
+    double* relres;                      // [batch] final true relative residual ||b - J x|| / ||b||
+};
+
+struct GmresSmem {
+    double* red;      // [2][RED_N]  partial sums of this CTA, double-buffered (read by the cluster through DSMEM)
+    double* sums;     // [RED_N]     cluster-wide sums
+    double* wpart;    // [GM_WARPS][GM_KT]
+    double* spart;    // [GM_WARPS][96] SpMV segment sums
+    double* rc;       // [3][NCO] restriction slices, then rc in slice 0
+    double* yc;       // [3][NCO]
+    double* H;        // [(m+1)*m] column-major columns of length m+1
+    double* cs; double* sn; double* g; double* y;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// sums[k] (k < K) = sum over the cluster's CTAs (rank order) of red[buf][k]; red[buf][0..K) must be written by
+// this CTA (by any thread) before the call.  Contains two __syncthreads and one cluster barrier.
+__device__ __forceinline__ void cluster_reduce(cg::cluster_group& cl, const GmresSmem& S, int& buf, int K, int red_n) {
+    cl.sync();                                        // partials of every CTA complete (also a CTA barrier)
+    const int G = cl.num_blocks();
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        double s = 0.0;
+        for (int q = 0; q < G; ++q) {
+            const double* remote = cl.map_shared_rank(S.red + buf * red_n, q);
+            s += remote[k];
+        }
+        S.sums[k] = s;
+    }
+    buf ^= 1;
+    __syncthreads();
+}
+
+// partial dot products of w with V_k (k0 <= k < k0+kn, kn <= GM_KT) over [i0, i1) -> red[buf][k]
+__device__ __forceinline__ void chunk_dots(const GmresSmem& S, int buf, int red_n, const double* __restrict__ Vp, long n,
+                                           const double* __restrict__ w, long i0, long i1, int k0, int kn) {
+    double acc[GM_KT];
+#pragma unroll
+    for (int q = 0; q < GM_KT; ++q) acc[q] = 0.0;
+    for (long i = i0 + threadIdx.x; i < i1; i += GM_THREADS) {
+        const double wi = w[i];
+#pragma unroll
+        for (int q = 0; q < GM_KT; ++q)
+            if (q < kn) acc[q] += Vp[(long)(k0 + q) * n + i] * wi;
+    }
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < GM_KT; ++q) {
+        const double v = warp_sum(acc[q]);
+        if (lane == 0) S.wpart[wp * GM_KT + q] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < kn) {
+        double s = 0.0;
+        for (int ww = 0; ww < GM_WARPS; ++ww) s += S.wpart[ww * GM_KT + threadIdx.x];
+        S.red[buf * red_n + k0 + threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
+// yc = A_c^-1 P^T r for the FULL vector r (every CTA redundantly; r must be visible cluster-wide)
+__device__ __forceinline__ void coarse_correction(const GmresSmem& S, const GmresArgs& a, const double* __restrict__ AciT,
+                                                  const double* __restrict__ r) {
+    const int tid = threadIdx.x;
+    if (tid < 3 * NCO) {
+        const int sl = tid / NCO, t = tid % NCO, I = t / NC, i = t % NC;
+        double s = 0.0;
+        for (int k = a.agg_ptr[I] + sl; k < a.agg_ptr[I + 1]; k += 3) {
+            const int v = a.agg_nodes[k];
+            if (a.dir_flag[(long)v * NC + i] < 0) s += r[(long)v * NC + i];
+        }
+        S.rc[sl * NCO + t] = s;
+    }
+    __syncthreads();
+    if (tid < NCO) S.rc[tid] = S.rc[tid] + S.rc[NCO + tid] + S.rc[2 * NCO + tid];
+    __syncthreads();
+    if (tid < 3 * NCO) {
+        const int sl = tid / NCO, t = tid % NCO;
+        double s = 0.0;
+        for (int j = sl * (NCO / 3); j < (sl + 1) * (NCO / 3); ++j) s += AciT[(long)j * NCO + t] * S.rc[j];
+        S.yc[sl * NCO + t] = s;
+    }
+    __syncthreads();
+    if (tid < NCO) S.yc[tid] = S.yc[tid] + S.yc[NCO + tid] + S.yc[2 * NCO + tid];
+    __syncthreads();
+}
+
+// z[i0,i1) = D^-1 r + P yc on this CTA's chunk
+__device__ __forceinline__ void precond_chunk(const GmresSmem& S, const GmresArgs& a, const double* __restrict__ Dinv,
+                                              const double* __restrict__ r, double* __restrict__ z, long i0, long i1) {
+    for (long idx = i0 + threadIdx.x; idx < i1; idx += GM_THREADS) {
+        const int v = (int)(idx / NC), i = (int)(idx % NC);
+        const double* D = Dinv + (long)v * 81 + i * 9;
+        const double* rp = r + (long)v * NC;
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) s += D[j] * rp[j];
+        if (a.dir_flag[idx] < 0) s += S.yc[a.agg[v] * NC + i];
+        z[idx] = s;
+    }
+}
+
+// y[v0..v1) = J x (own block rows; x must be visible cluster-wide); mode 0: y = Jx, mode 1: y = b - Jx
+__device__ __forceinline__ void spmv_chunk(const GmresSmem& S, const GmresArgs& a, const double* __restrict__ Jp,
+                                           const double* __restrict__ xp, double* __restrict__ y,
+                                           const double* __restrict__ bp, int v0, int v1) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int j0 = lane % 9, j1 = (lane + 32) % 9, j2 = (lane + 64) % 9;
+    const bool third = lane + 64 < 81;
+    double* part = S.spart + w * 96;
+    for (int row = v0 + w; row < v1; row += GM_WARPS) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        const int s0 = a.row_ptr[row], s1 = a.row_ptr[row + 1];
+        for (int base = s0; base < s1; base += 32) {
+            const int cnt = min(32, s1 - base);
+            const int mycol = (lane < cnt) ? a.col_idx[base + lane] : 0;
+            const double* blk = Jp + (long)base * 81;
+            int t = 0;
+            for (; t + 4 <= cnt; t += 4, blk += 4 * 81) {
+                double v[4][3];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    v[q][0] = __ldcs(blk + q * 81 + lane);
+                    v[q][1] = __ldcs(blk + q * 81 + lane + 32);
+                    v[q][2] = third ? __ldcs(blk + q * 81 + lane + 64) : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double* xc = xp + (long)__shfl_sync(0xffffffffu, mycol, t + q) * NC;
+                    a0 += v[q][0] * xc[j0];
+                    a1 += v[q][1] * xc[j1];
+                    a2 += v[q][2] * xc[j2];
+                }
+            }
+            for (; t < cnt; ++t, blk += 81) {
+                const double v0_ = __ldcs(blk + lane), v1_ = __ldcs(blk + lane + 32);
+                const double v2_ = third ? __ldcs(blk + lane + 64) : 0.0;
+                const double* xc = xp + (long)__shfl_sync(0xffffffffu, mycol, t) * NC;
+                a0 += v0_ * xc[j0];
+                a1 += v1_ * xc[j1];
+                a2 += v2_ * xc[j2];
+            }
+        }
+        part[lane] = a0; part[lane + 32] = a1; part[lane + 64] = a2;
+        __syncwarp();
+        if (lane < NC) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) s += part[lane * 9 + j];
+            const long o = (long)row * NC + lane;
+            y[o] = bp ? bp[o] - s : s;
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(GM_THREADS, 1)
+gmres_cluster_kernel(GmresArgs a) {
+    cg::cluster_group cl = cg::this_cluster();
+    const int G = (int)cl.num_blocks(), rank = (int)cl.block_rank();
+    const int prob = blockIdx.x / G;
+    if (a.enabled && !a.enabled[prob]) return;          // cluster-uniform
+    const int tid = threadIdx.x;
+    const int V = a.n_vert, m = a.m, ld = m + 1;
+    const long n = (long)V * NC;
+    const int v0 = (int)((long)V * rank / G), v1 = (int)((long)V * (rank + 1) / G);
+    const long i0 = (long)v0 * NC, i1 = (long)v1 * NC;
+    extern __shared__ double smem[];
+    const int red_n = ld + 3;
+    GmresSmem S;
+    {
+        double* p = smem;
+        S.red = p; p += 2 * red_n;
+        S.sums = p; p += red_n;
+        S.wpart = p; p += GM_WARPS * GM_KT;
+        S.spart = p; p += GM_WARPS * 96;
+        S.rc = p; p += 3 * NCO;
+        S.yc = p; p += 3 * NCO;
+        S.H = p; p += (long)ld * m;
+        S.cs = p; p += m; S.sn = p; p += m; S.g = p; p += ld; S.y = p; p += ld;
+    }
+    __shared__ int s_flag;
+    const double* Jp = a.J + (long)prob * a.n_blocks * 81;
+    const double* Dinv = a.Dinv + (long)prob * V * 81;
+    const double* AciT = a.AciT + (long)prob * NCO * NCO;
+    const double* b = a.b + (long)prob * n;
+    double* x = a.x + (long)prob * n;
+    double* Vp = a.V + (long)prob * ld * n;
+    double* w = a.w + (long)prob * n;
+    double* z = a.z + (long)prob * n;
+    int buf = 0;
+
+    auto chunk_norm2 = [&](const double* vec) {          // -> red[buf][0]
+        double s = 0.0;
+        for (long i = i0 + tid; i < i1; i += GM_THREADS) { const double t = vec[i]; s += t * t; }
+        s = warp_sum(s);
+        if ((tid & 31) == 0) S.wpart[(tid >> 5) * GM_KT] = s;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int ww = 0; ww < GM_WARPS; ++ww) t += S.wpart[ww * GM_KT];
+            S.red[buf * red_n] = t;
+        }
+        __syncthreads();
+    };
+
+    for (long i = i0 + tid; i < i1; i += GM_THREADS) x[i] = 0.0;
+    chunk_norm2(b);
+    cluster_reduce(cl, S, buf, 1, red_n);
+    const double beta0 = sqrt(S.sums[0]);
+    const double tol = a.rtol * beta0;
+    const double* rcur = b;
+    double beta = beta0;
+    int total = 0;
+    bool fin = isfinite(beta0) && beta0 > 0.0;
+    while (fin && beta > tol && total < a.maxit) {
+        // ---- cycle start: V_0 = r / beta, g = (beta, 0, ...) --------------------------------------
+        const double ib = 1.0 / beta;
+        for (long i = i0 + tid; i < i1; i += GM_THREADS) Vp[i] = rcur[i] * ib;
+        if (tid == 0) { for (int k = 0; k <= m; ++k) S.g[k] = 0.0; S.g[0] = beta; }
+        cl.sync();
+        const int mcyc = min(m, a.maxit - total);
+        int jd = mcyc;
+        for (int j = 0; j < mcyc; ++j) {
+            const double* vj = Vp + (long)j * n;
+            // w = J M^-1 v_j
+            coarse_correction(S, a, AciT, vj);
+            precond_chunk(S, a, Dinv, vj, z, i0, i1);
+            cl.sync();                                   // z complete
+            spmv_chunk(S, a, Jp, z, w, nullptr, v0, v1);
+            __syncthreads();
+            // CGS2: two classical Gram-Schmidt passes; h = d1 + d2
+            for (int pass = 0; pass < 2; ++pass) {
+                for (int k0 = 0; k0 <= j; k0 += GM_KT) chunk_dots(S, buf, red_n, Vp, n, w, i0, i1, k0, min(GM_KT, j + 1 - k0));
+                cluster_reduce(cl, S, buf, j + 1, red_n);
+                double nrm2 = 0.0;
+                for (long i = i0 + tid; i < i1; i += GM_THREADS) {
+                    double s = w[i];
+                    for (int k = 0; k <= j; ++k) s -= S.sums[k] * Vp[(long)k * n + i];
+                    w[i] = s;
+                    nrm2 += s * s;
+                }
+                // Hessenberg column accumulates both passes (column j of H used as scratch until the Givens step)
+                if (tid == 0) {
+                    double* h = S.H + (long)j * ld;
+                    for (int k = 0; k <= j; ++k) h[k] = (pass == 0 ? 0.0 : h[k]) + S.sums[k];
+                }
+                if (pass == 1) {
+                    nrm2 = warp_sum(nrm2);
+                    if ((tid & 31) == 0) S.wpart[(tid >> 5) * GM_KT] = nrm2;
+                    __syncthreads();
+                    if (tid == 0) {
+                        double t = 0.0;
+                        for (int ww = 0; ww < GM_WARPS; ++ww) t += S.wpart[ww * GM_KT];
+                        S.red[buf * red_n] = t;
+                    }
+                }
+                __syncthreads();
+            }
+            cluster_reduce(cl, S, buf, 1, red_n);
+            const double nrm = sqrt(S.sums[0]);
+            const double inrm = (nrm > 0.0) ? 1.0 / nrm : 0.0;
+            for (long i = i0 + tid; i < i1; i += GM_THREADS) Vp[(long)(j + 1) * n + i] = w[i] * inrm;
+            if (tid == 0) {
+                double* h = S.H + (long)j * ld;
+                h[j + 1] = nrm;
+                for (int k = 0; k < j; ++k) {
+                    const double t = S.cs[k] * h[k] + S.sn[k] * h[k + 1];
+                    h[k + 1] = -S.sn[k] * h[k] + S.cs[k] * h[k + 1];
+                    h[k] = t;
+                }
+                const double aa = h[j], bb = h[j + 1];
+                const double d = hypot(aa, bb);
+                const double cj = (d > 0.0) ? aa / d : 1.0, sj = (d > 0.0) ? bb / d : 0.0;
+                S.cs[j] = cj; S.sn[j] = sj;
+                h[j] = d; h[j + 1] = 0.0;
+                S.g[j + 1] = -sj * S.g[j];
+                S.g[j] = cj * S.g[j];
+                s_flag = (fabs(S.g[j + 1]) <= tol || !(nrm > 0.0) || !isfinite(nrm)) ? 1 : 0;
+            }
+            cl.sync();                                   // V_{j+1} visible cluster-wide; s_flag visible in the CTA
+            if (s_flag) { jd = j + 1; break; }
+        }
+        total += jd;
+        // ---- x += M^-1 (V y),  y = H^-1 g -----------------------------------------------------------
+        if (tid == 0) {
+            for (int k = jd - 1; k >= 0; --k) {
+                double s = S.g[k];
+                for (int l = k + 1; l < jd; ++l) s -= S.H[(long)l * ld + k] * S.y[l];
+                const double d = S.H[(long)k * ld + k];
+                S.y[k] = (d != 0.0) ? s / d : 0.0;
+            }
+        }
+        __syncthreads();
+        for (long i = i0 + tid; i < i1; i += GM_THREADS) {
+            double s = 0.0;
+            for (int k = 0; k < jd; ++k) s += S.y[k] * Vp[(long)k * n + i];
+            w[i] = s;
+        }
+        cl.sync();                                       // t = V y complete (in w)
+        coarse_correction(S, a, AciT, w);
+        precond_chunk(S, a, Dinv, w, z, i0, i1);
+        for (long i = i0 + tid; i < i1; i += GM_THREADS) x[i] += z[i];
+        cl.sync();                                       // x complete; nobody reads w (= t) any more
+        // true residual r = b - J x -> w
+        spmv_chunk(S, a, Jp, x, w, b, v0, v1);
+        __syncthreads();
+        chunk_norm2(w);
+        cluster_reduce(cl, S, buf, 1, red_n);
+        beta = sqrt(S.sums[0]);
+        rcur = w;
+        fin = isfinite(beta);
+    }
+    if (rank == 0 && tid == 0) {
+        a.its[prob] = total;
+        a.relres[prob] = (beta0 > 0.0) ? beta / beta0 : (isfinite(beta0) ? 0.0 : NAN);
+    }
+    cl.sync();                                           // no CTA exits while its shared memory may still be read
+}
+
+// ---------------------------------------------------------------------------------------
+// Device-resident Newton / march control (per-problem state, no host arithmetic)
+// ---------------------------------------------------------------------------------------
+struct NewtonCtl {      // per-problem arrays, device
+    int* active;        // 1: still iterating in this solve
+    int* status;        // -1 while running, then GMPNP_* code
+    int* iters;         // Newton iterations of this solve
+    int* lin_total;     // GMRES iterations of this solve
+    double* r0;         // ||F(u0)||
+    double* r;          // ||F(u_k)||
+};
+
+// after the first residual evaluation of a solve
+__global__ void newton_begin_kernel(int B, const int* __restrict__ enabled, const double* __restrict__ nrm, NewtonCtl c,
+                                    int criterion, double atol, int* __restrict__ n_active) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    c.iters[p] = 0; c.lin_total[p] = 0;
+    const double r0 = nrm[p];
+    c.r0[p] = r0; c.r[p] = r0;
+    int act = 1, st = -1;
+    if (enabled && !enabled[p]) { act = 0; st = GMPNP_CONVERGED; c.r0[p] = 0.0; c.r[p] = 0.0; }
+    else if (!isfinite(r0)) { act = 0; st = GMPNP_NOT_FINITE; }
+    else if (criterion == 0 && r0 < atol) { act = 0; st = GMPNP_CONVERGED; }
+    c.active[p] = act; c.status[p] = st;
+    if (act) atomicAdd(n_active, 1);
+}
+
+// after the update and the residual evaluation of Newton iteration k (0-based)
+__global__ void newton_step_kernel(int B, int k, int maxit, const double* __restrict__ nrm, const double* __restrict__ dxmax,
+                                   const double* __restrict__ umax, const int* __restrict__ lin_its,
+                                   const double* __restrict__ relres, NewtonCtl c, int criterion, double rtol,
+                                   double atol, double xtol, double lin_rtol, int* __restrict__ n_active) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    if (!c.active[p]) return;
+    c.iters[p] = k + 1;
+    c.lin_total[p] += lin_its[p];
+    const double rn = nrm[p];
+    c.r[p] = rn;
+    const bool linfail = !(relres[p] <= 1e3 * lin_rtol);
+    int act = 1, st = -1;
+    if (!isfinite(rn) || !isfinite(dxmax[p])) { act = 0; st = GMPNP_NOT_FINITE; }
+    else {
+        const bool conv = (criterion == 0) ? ((rn / c.r0[p] < rtol) || (rn < atol))
+                                           : (dxmax[p] <= xtol * fmax(1.0, umax[p]));
+        if (conv) { act = 0; st = GMPNP_CONVERGED; }
+        else if (linfail) { act = 0; st = GMPNP_LINEAR_FAILED; }
+        else if (k + 1 >= maxit) { act = 0; st = GMPNP_MAXIT; }
+    }
+    c.active[p] = act; c.status[p] = st;
+    if (act) atomicAdd(n_active, 1);
+}
+
+// Dirichlet values from the kind table (3D:460-467, 835-838): kind 0 -> 0, 1 -> wall potential V * ramp,
+// 2 -> CO2 entry value (per problem, updated by the Sechenov feedback), 3/4 -> CO / H2 entry values
+__global__ void dirichlet_fill_kernel(int B, int n_dir, const signed char* __restrict__ kind, const double* __restrict__ tab,
+                                      const double* __restrict__ co2, double ramp, double* __restrict__ vals,
+                                      double* __restrict__ params) {
+    const int p = blockIdx.y;
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    const double Vw = tab[p * 4 + 0] * ramp;
+    if (d == 0 && params) params[(long)p * GMPNP_NPAR + GMPNP_P_V] = Vw;
+    if (d >= n_dir) return;
+    const int k = kind[d];
+    double v = 0.0;
+    if (k == 1) v = Vw;
+    else if (k == 2) v = co2[p];
+    else if (k == 3) v = tab[p * 4 + 2];
+    else if (k == 4) v = tab[p * 4 + 3];
+    vals[(long)p * n_dir + d] = v;
+}
+
+// medians of up to four components per problem in one launch (grid = (batch, ncomp)); bitonic sort in shared memory
+__global__ void __launch_bounds__(1024)
+median4_kernel(int n_vert, int npow2, int c0, int c1, int c2, int c3, const double* __restrict__ u, double* __restrict__ med) {
+    extern __shared__ double sv[];
+    const int prob = blockIdx.x;
+    const int comps[4] = {c0, c1, c2, c3};
+    const int comp = comps[blockIdx.y];
+    for (int i = threadIdx.x; i < npow2; i += blockDim.x)
+        sv[i] = (i < n_vert) ? u[((long)prob * n_vert + i) * NC + comp] : INFINITY;
+    __syncthreads();
+    for (int k = 2; k <= npow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const bool up = ((i & k) == 0);
+                    const double a = sv[i], b = sv[ixj];
+                    if ((a > b) == up) { sv[i] = b; sv[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0)
+        med[prob * 4 + blockIdx.y] = (n_vert & 1) ? sv[n_vert / 2] : 0.5 * (sv[n_vert / 2 - 1] + sv[n_vert / 2]);
+}
+
+// Sechenov CO2 entry value from the nodal medians (3D:817-838; CO2_conc 3D:70-93).  sech[p][8] =
+// {A = fugacity * K_H * 1000 / c0_CO2, (h_OH + h_CO2) c0_OH / 1000, (h_HCO3 + h_CO2) c0_HCO3 / 1000,
+//  (h_CO32 + h_CO2) c0_CO32 / 1000, (h_cat + h_CO2) c0_cat / 1000, mode, c0_H, -}.
+// mode 0 (GMPNP): med = (OH, HCO3, CO32, cat).  mode 1 (rxn-diff, RD3:575-601): med = (H, OH, HCO3, CO32) and the
+// cation is the electroneutral estimate c_cat = c_HCO3 + 2 c_CO32 + c_OH - c_H.
+__global__ void sechenov_kernel(int B, const int* __restrict__ alive, const double* __restrict__ med,
+                                const double* __restrict__ sech, double* __restrict__ co2) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    if (alive && !alive[p]) return;
+    const double* s = sech + (long)p * 8;
+    const double* m = med + (long)p * 4;
+    double e;
+    if (s[5] == 0.0) {
+        e = s[1] * m[0];
+        e += s[2] * m[1];
+        e += s[3] * m[2];
+        e += s[4] * m[3];
+    } else {
+        // coefficients are per scaled unit: s[1..3] for OH, HCO3, CO32; cation from electroneutrality in mol/m3:
+        // s[4] holds (h_cat + h_CO2) / 1000 and s[6], s[7].. are unused; the c0 factors are folded by the host into
+        // s[1..3] (own term + cation share) and s[6] (H share, negative)
+        e = s[1] * m[1];
+        e += s[2] * m[2];
+        e += s[3] * m[3];
+        e += s[6] * m[0];
+    }
+    co2[p] = s[0] * pow(10.0, -e);
+}
+
+// per problem: inc = max|u - un| / max(1, max|u|); optional un <- u and history row
+__global__ void __launch_bounds__(1024)
+march_advance_kernel(long n, const int* __restrict__ alive, const double* __restrict__ u, double* __restrict__ un,
+                     double* __restrict__ hist, long hist_stride, double* __restrict__ inc) {
+    __shared__ double sh1[32], sh2[32];
+    const int prob = blockIdx.x;
+    if (alive && !alive[prob]) { if (threadIdx.x == 0 && inc) inc[prob] = 0.0; return; }
+    double m1 = 0.0, m2 = 0.0;
+    for (long i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = u[(long)prob * n + i];
+        m1 = fmax(m1, fabs(v - un[(long)prob * n + i]));
+        m2 = fmax(m2, fabs(v));
+        un[(long)prob * n + i] = v;
+        if (hist) hist[(long)prob * hist_stride + i] = v;
+    }
+    for (int o = 16; o >= 1; o >>= 1) {
+        m1 = fmax(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+        m2 = fmax(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { sh1[w] = m1; sh2[w] = m2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { m1 = fmax(m1, sh1[k]); m2 = fmax(m2, sh2[k]); }
+        if (inc) inc[prob] = m1 / fmax(1.0, m2);
+    }
+}
+
+// steady-state test of the march: a problem whose last relative increment is <= tol stops marching (converged)
+__global__ void steady_check_kernel(int B, double tol, int* __restrict__ alive, const double* __restrict__ inc,
+                                    int* __restrict__ conv, int* __restrict__ n_alive) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    if (!alive[p]) return;
+    if (inc[p] <= tol) { alive[p] = 0; conv[p] = 1; }
+    else atomicAdd(n_alive, 1);
+}
+
+// march bookkeeping after a Newton solve of step `step`: per-problem iteration counts, alive flags, final status
+__global__ void march_record_kernel(int B, int step, int n_steps, NewtonCtl c, int* __restrict__ alive,
+                                    int* __restrict__ iters_out, int* __restrict__ lin_out, int* __restrict__ status_out,
+                                    int* __restrict__ steps_done, const double* __restrict__ co2, double* __restrict__ co2_out,
+                                    int* __restrict__ n_alive) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    if (!alive[p]) return;
+    if (iters_out) iters_out[(long)p * n_steps + step] = c.iters[p];
+    if (lin_out) lin_out[(long)p * n_steps + step] = c.lin_total[p];
+    if (co2_out) co2_out[(long)p * n_steps + step] = co2[p];
+    if (c.status[p] != GMPNP_CONVERGED) { alive[p] = 0; status_out[p] = c.status[p]; }
+    else { steps_done[p] = step + 1; atomicAdd(n_alive, 1); }
+}
+
 }  // namespace pore3d
 
 // =======================================================================================
@@ -1088,35 +1545,35 @@ struct Host3D {   // device arrays that only the 3D path needs and common.cuh do
     double* d_gp = nullptr;         // gradient-projection work vectors [4][batch][V][27] + scalars
     double* d_partial = nullptr;    // first-stage partial sums of the partitioned-mode reductions
     size_t partial_doubles = 0;
+    // coarse set-up: blocks sorted by (row slab, column slab) pair, cut into chunks (deterministic ordered sums)
+    int* d_cp_blk = nullptr; int* d_chunk_ptr = nullptr; int* d_chunk_pair = nullptr; int n_chunk = 0;
+    double* d_cpart = nullptr;      // [batch][n_chunk][81]
+    double* d_AciT = nullptr;       // [batch][NCO][NCO] transposed pivoted inverse (batched solver)
+    int* d_cflag = nullptr;         // [batch] vanishing pivots met by the coarse inverse
+    // persistent-GMRES / device-resident Newton workspace (ensure_solver)
     int restart_alloc = 0;
-    double *d_V = nullptr, *d_w = nullptr, *d_z = nullptr, *d_dx = nullptr, *d_d1 = nullptr, *d_d2 = nullptr;
-    double *d_nrm = nullptr, *d_H = nullptr, *d_cs = nullptr, *d_sn = nullptr, *d_g = nullptr, *d_tol = nullptr;
-    double *d_coef = nullptr, *d_beta = nullptr, *d_dxmax = nullptr, *d_umax = nullptr;
-    int *d_jdone = nullptr, *d_active = nullptr;
+    double *d_V = nullptr, *d_w = nullptr, *d_z = nullptr, *d_dx = nullptr, *d_nrm = nullptr, *d_dxmax = nullptr;
+    double *d_umax = nullptr, *d_relres = nullptr, *d_r0 = nullptr, *d_r = nullptr;
+    int *d_active = nullptr, *d_status = nullptr, *d_iters = nullptr, *d_lin_total = nullptr, *d_lin_its = nullptr;
+    int* d_nact = nullptr;
+    // march / steady drivers (gmpnp_set_march_data_3d)
+    signed char* d_kind = nullptr;  // [n_dir] Dirichlet kind 0..4
+    double *d_tab = nullptr, *d_sech = nullptr, *d_co2 = nullptr, *d_med = nullptr, *d_inc = nullptr;
+    int *d_alive = nullptr, *d_steps = nullptr, *d_mstatus = nullptr, *d_conv = nullptr;
+    bool march_set = false, sech_mode1 = false;
 };
-// side table keyed by handle (handles are independent; the table itself is guarded so that different handles can be
-// created, used and destroyed from different threads)
-static std::map<gmpnp_handle*, Host3D*> g_ext;
-static std::mutex g_ext_mutex;
-
-static Host3D* ext(gmpnp_handle* h) {
-    std::lock_guard<std::mutex> lk(g_ext_mutex);
-    auto it = g_ext.find(h);
-    return it == g_ext.end() ? nullptr : it->second;
-}
+// owned by the handle (gmpnp_handle::ext3d): no process-wide state, handles are independent
+static Host3D* ext(gmpnp_handle* h) { return static_cast<Host3D*>(h->ext3d); }
 
 void pore3d_free_ext(gmpnp_handle* h) {
-    Host3D* e = nullptr;
-    {
-        std::lock_guard<std::mutex> lk(g_ext_mutex);
-        auto it = g_ext.find(h);
-        if (it == g_ext.end()) return;
-        e = it->second;
-        g_ext.erase(it);
-    }
+    Host3D* e = ext(h);
+    if (!e) return;
+    h->ext3d = nullptr;
     void* bufs[] = {e->d_wall_w, e->d_exit_m, e->d_exit_flag, e->d_bc, e->d_mass, e->d_gp, e->d_partial, e->d_blk_row, e->d_blk_geo, e->d_agg, e->d_agg_ptr, e->d_agg_nodes, e->d_Aci, e->d_yc, e->d_V, e->d_w, e->d_z,
-                    e->d_dx, e->d_d1, e->d_d2, e->d_nrm, e->d_H, e->d_cs, e->d_sn, e->d_g, e->d_tol, e->d_coef,
-                    e->d_beta, e->d_dxmax, e->d_umax, e->d_jdone, e->d_active};
+                    e->d_dx, e->d_nrm, e->d_dxmax, e->d_umax, e->d_relres, e->d_r0, e->d_r, e->d_active, e->d_status,
+                    e->d_iters, e->d_lin_total, e->d_lin_its, e->d_nact, e->d_cp_blk, e->d_chunk_ptr, e->d_chunk_pair,
+                    e->d_cpart, e->d_AciT, e->d_cflag, e->d_kind, e->d_tab, e->d_sech, e->d_co2, e->d_med, e->d_inc,
+                    e->d_alive, e->d_steps, e->d_mstatus, e->d_conv};
     for (void* b : bufs) if (b) cudaFree(b);
     delete e;
 }
@@ -1137,10 +1594,7 @@ int gmpnp_create_3d(gmpnp_handle** out, int device, const double* h_xyz, int n_v
     h->n_nodes = n_vert; h->n_tet = n_tet; h->n_dir = n_dir;
     *out = h;
     Host3D* e = new Host3D();
-    {
-        std::lock_guard<std::mutex> lk(g_ext_mutex);
-        g_ext[h] = e;
-    }
+    h->ext3d = e;
     GMPNP_CUDA_TRY(h, cudaSetDevice(device));
     upload_rules();
     // ---- geometry: grad lambda_a and volume (same formulas as oracle/forms.py:geometry) -------
@@ -1275,6 +1729,28 @@ int gmpnp_create_3d(gmpnp_handle** out, int device, const double* h_xyz, int n_v
     if ((rc = dev_upload(h, &e->d_agg_ptr, agg_ptr))) return rc;
     if ((rc = dev_upload(h, &e->d_agg_nodes, agg_nodes))) return rc;
     const size_t B = batch;
+    {   // coarse set-up lists: blocks sorted by (slab of row, slab of column), stable in the block index, cut in chunks
+        std::vector<int> order(nb);
+        std::iota(order.begin(), order.end(), 0);
+        auto pair_of = [&](int s_) { return agg[blk_row[s_]] * NZ + agg[h->h_col_idx[s_]]; };
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return pair_of(x) < pair_of(y); });
+        std::vector<int> chunk_ptr(1, 0), chunk_pair;
+        for (int c = 0; c < nb;) {
+            const int pr = pair_of(order[c]);
+            int end = c;
+            while (end < nb && end - c < CP_CHUNK && pair_of(order[end]) == pr) ++end;
+            chunk_pair.push_back(pr);
+            chunk_ptr.push_back(end);
+            c = end;
+        }
+        e->n_chunk = (int)chunk_pair.size();
+        if ((rc = dev_upload(h, &e->d_cp_blk, order))) return rc;
+        if ((rc = dev_upload(h, &e->d_chunk_ptr, chunk_ptr))) return rc;
+        if ((rc = dev_upload(h, &e->d_chunk_pair, chunk_pair))) return rc;
+        GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_cpart, sizeof(double) * 81 * (size_t)e->n_chunk * B));
+        GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_AciT, sizeof(double) * NCO * NCO * B));
+        GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_cflag, sizeof(int) * B));
+    }
     GMPNP_CUDA_TRY(h, cudaMalloc(&h->d_params, sizeof(double) * GMPNP_NPAR * B));
     GMPNP_CUDA_TRY(h, cudaMalloc(&h->d_dir_val, sizeof(double) * std::max(1, n_dir) * B));
     GMPNP_CUDA_TRY(h, cudaMalloc(&h->d_mom, sizeof(double) * NMOM * (size_t)n_tet * B));
@@ -1351,130 +1827,151 @@ static int launch_spmv(gmpnp_handle* h, const double* d_J, const double* d_x, do
     return GMPNP_OK;
 }
 
-static int ensure_krylov(gmpnp_handle* h, int m) {
+// ---- solver workspace (GMRES basis, Newton control arrays): allocated into temporaries and swapped in on success ----
+static int ensure_solver(gmpnp_handle* h, int m) {
     Host3D* e = ext(h);
-    if (e->restart_alloc >= m) return GMPNP_OK;
-    void* old[] = {e->d_V, e->d_w, e->d_z, e->d_dx, e->d_d1, e->d_d2, e->d_nrm, e->d_H, e->d_cs, e->d_sn, e->d_g,
-                   e->d_tol, e->d_coef, e->d_beta, e->d_dxmax, e->d_umax, e->d_jdone, e->d_active};
-    for (void* b : old) if (b) cudaFree(b);
+    if (e->restart_alloc >= m && e->d_V) return GMPNP_OK;
     const size_t B = h->batch, n = (size_t)h->n_nodes * NC, ld = m + 1;
-    GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_V, sizeof(double) * B * ld * n));
-    GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_w, sizeof(double) * B * n));
-    GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_z, sizeof(double) * B * n));
-    GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_dx, sizeof(double) * B * n));
-    GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_d1, sizeof(double) * B * ld));
-    GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_d2, sizeof(double) * B * ld));
-    GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_coef, sizeof(double) * B * ld));
-    GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_nrm, sizeof(double) * B));
-    GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_H, sizeof(double) * B * m * ld));
-    GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_cs, sizeof(double) * B * m));
-    GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_sn, sizeof(double) * B * m));
-    GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_g, sizeof(double) * B * ld));
-    GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_tol, sizeof(double) * B));
-    GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_beta, sizeof(double) * B));
-    GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_dxmax, sizeof(double) * B));
-    GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_umax, sizeof(double) * B));
-    GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_jdone, sizeof(int) * B));
-    GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_active, sizeof(int) * B));
+    struct Req { void** dst; size_t bytes; };
+    double *V = nullptr, *w = nullptr, *z = nullptr, *dx = nullptr, *nrm = nullptr, *dxmax = nullptr, *umax = nullptr;
+    double *relres = nullptr, *r0 = nullptr, *r = nullptr;
+    int *active = nullptr, *status = nullptr, *iters = nullptr, *lin_total = nullptr, *lin_its = nullptr, *nact = nullptr;
+    Req reqs[] = {{(void**)&V, sizeof(double) * B * ld * n}, {(void**)&w, sizeof(double) * B * n},
+                  {(void**)&z, sizeof(double) * B * n}, {(void**)&dx, sizeof(double) * B * n},
+                  {(void**)&nrm, sizeof(double) * B}, {(void**)&dxmax, sizeof(double) * B},
+                  {(void**)&umax, sizeof(double) * B}, {(void**)&relres, sizeof(double) * B},
+                  {(void**)&r0, sizeof(double) * B}, {(void**)&r, sizeof(double) * B},
+                  {(void**)&active, sizeof(int) * B}, {(void**)&status, sizeof(int) * B},
+                  {(void**)&iters, sizeof(int) * B}, {(void**)&lin_total, sizeof(int) * B},
+                  {(void**)&lin_its, sizeof(int) * B}, {(void**)&nact, sizeof(int) * 4}};
+    // free the old set first (a longer restart replaces the basis; peak memory stays one basis), and forget it
+    void* old[] = {e->d_V, e->d_w, e->d_z, e->d_dx, e->d_nrm, e->d_dxmax, e->d_umax, e->d_relres, e->d_r0, e->d_r,
+                   e->d_active, e->d_status, e->d_iters, e->d_lin_total, e->d_lin_its, e->d_nact};
+    for (void* b : old) if (b) cudaFree(b);
+    e->d_V = e->d_w = e->d_z = e->d_dx = e->d_nrm = e->d_dxmax = e->d_umax = e->d_relres = e->d_r0 = e->d_r = nullptr;
+    e->d_active = e->d_status = e->d_iters = e->d_lin_total = e->d_lin_its = e->d_nact = nullptr;
+    e->restart_alloc = 0;
+    for (auto& q : reqs) {
+        if (cudaMalloc(q.dst, q.bytes) != cudaSuccess) {
+            cudaGetLastError();
+            for (auto& f : reqs) if (*f.dst) { cudaFree(*f.dst); *f.dst = nullptr; }
+            h->last_cuda_error = "cudaMalloc of the GMRES workspace failed";
+            return GMPNP_ERR_ALLOC;
+        }
+    }
+    e->d_V = V; e->d_w = w; e->d_z = z; e->d_dx = dx; e->d_nrm = nrm; e->d_dxmax = dxmax; e->d_umax = umax;
+    e->d_relres = relres; e->d_r0 = r0; e->d_r = r; e->d_active = active; e->d_status = status; e->d_iters = iters;
+    e->d_lin_total = lin_total; e->d_lin_its = lin_its; e->d_nact = nact;
     e->restart_alloc = m;
     return GMPNP_OK;
 }
 
-// z = M^{-1} r  (block-Jacobi + additive z-slab coarse correction)
-static void launch_precond(gmpnp_handle* h, const double* r, long rstride, double* z, cudaStream_t st) {
-    Host3D* e = ext(h);
-    const int V = h->n_nodes, B = h->batch;
-    coarse_solve_kernel<<<B, NCO, 0, st>>>(V, e->d_agg_ptr, e->d_agg_nodes, h->d_dir_flag, e->d_Aci, r, rstride,
-                                           e->d_yc);
-    dim3 g(((long)V * NC + 255) / 256, B);
-    precond_apply_kernel<<<g, 256, 0, st>>>(V, e->d_agg, h->d_dir_flag, h->d_Dinv, e->d_yc, r, rstride, z, 1);
-    h->launches += 2;
+// cluster size of the persistent GMRES kernel: fill the 148 SMs when the batch is small
+static int gmres_cluster_size(int batch) {
+    int g = 1;
+    while (g < 8 && batch * g * 2 <= 148) g *= 2;
+    return g;
 }
 
-// Right-preconditioned restarted GMRES on J dx = F for the whole batch.  Returns per-problem iteration
-// counts and the final relative residual estimates in host arrays.
-static int gmres_solve(gmpnp_handle* h, const double* d_b, double* d_x, int m, int maxit, double rtol,
-                       std::vector<int>& its, std::vector<double>& relres, cudaStream_t st) {
+static size_t gmres_smem_bytes(int m) {
+    const size_t ld = m + 1, red_n = ld + 3;
+    return sizeof(double) * (3 * red_n + GM_WARPS * GM_KT + GM_WARPS * 96 + 6 * NCO + ld * m + 2 * m + 2 * ld);
+}
+
+// Jacobian of the current iterate is in h->d_J: block-Jacobi inverses + coarse inverse (deterministic, pivoted)
+static int launch_precond_setup(gmpnp_handle* h, cudaStream_t st) {
+    Host3D* e = ext(h);
+    const int V = h->n_nodes, B = h->batch;
+    dim3 gj((V + 63) / 64, B);
+    bjacobi_invert_kernel<<<gj, 64, 0, st>>>(V, h->n_blocks, h->d_diag_idx, h->d_J, h->d_Dinv);
+    dim3 gp(e->n_chunk, B);
+    coarse_partial_kernel<<<gp, 96, 0, st>>>(h->n_blocks, e->d_chunk_ptr, e->d_cp_blk, e->d_blk_row, h->d_col_idx,
+                                             h->d_dir_flag, h->d_J, e->d_cpart, e->n_chunk);
+    cudaFuncSetAttribute(coarse_invert_pivoted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(sizeof(double) * NCO * NCO));
+    coarse_invert_pivoted_kernel<<<B, 1024, sizeof(double) * NCO * NCO, st>>>(e->d_chunk_pair, e->d_cpart, e->n_chunk,
+                                                                              e->d_AciT, e->d_cflag);
+    h->launches += 3;
+    GMPNP_CUDA_TRY(h, cudaGetLastError());
+    return GMPNP_OK;
+}
+
+// J dx = b for every enabled problem: ONE launch, no host synchronisation (gmres_cluster_kernel)
+static int launch_gmres(gmpnp_handle* h, const double* d_b, double* d_x, int m, int maxit, double rtol,
+                        const int* d_enabled, cudaStream_t st) {
+    Host3D* e = ext(h);
+    GmresArgs a;
+    a.n_vert = h->n_nodes; a.n_blocks = h->n_blocks; a.m = m; a.maxit = maxit; a.rtol = rtol;
+    a.row_ptr = h->d_row_ptr; a.col_idx = h->d_col_idx; a.agg = e->d_agg; a.agg_ptr = e->d_agg_ptr;
+    a.agg_nodes = e->d_agg_nodes; a.dir_flag = h->d_dir_flag;
+    a.J = h->d_J; a.Dinv = h->d_Dinv; a.AciT = e->d_AciT; a.b = d_b;
+    a.x = d_x; a.V = e->d_V; a.w = e->d_w; a.z = e->d_z;
+    a.enabled = d_enabled; a.its = e->d_lin_its; a.relres = e->d_relres;
+    const int G = gmres_cluster_size(h->batch);
+    const size_t smem = gmres_smem_bytes(m);
+    GMPNP_CUDA_TRY(h, cudaFuncSetAttribute(gmres_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(h->batch * G, 1, 1);
+    cfg.blockDim = dim3(GM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    GMPNP_CUDA_TRY(h, cudaLaunchKernelEx(&cfg, gmres_cluster_kernel, a));
+    h->launches++;
+    return GMPNP_OK;
+}
+
+// One reference `solve(F == 0, u, bcs)` per enabled problem (dolfin NewtonSolver semantics), control
+// state on the device (NewtonCtl arrays in the handle); the host reads ONE counter (problems still active) per Newton
+// iteration.  d_enabled (device, may be NULL): problems with 0 are left untouched and report GMPNP_CONVERGED, 0 iterations.
+static int newton_run(gmpnp_handle* h, double* d_u, const double* d_un, const gmpnp_newton_opts* o, const int* d_enabled,
+                      cudaStream_t st) {
     Host3D* e = ext(h);
     const int V = h->n_nodes, B = h->batch;
     const long n = (long)V * NC;
-    const int ld = m + 1;
-    int rc = ensure_krylov(h, m); if (rc) return rc;
-    double* hp = (double*)h->h_pinned;
-    const int gridn = (int)((n + 255) / 256);
-    its.assign(B, 0); relres.assign(B, 0.0);
-    GMPNP_CUDA_TRY(h, cudaMemsetAsync(d_x, 0, sizeof(double) * n * B, st));
-    // r0 = b (x0 = 0)
-    norm_scale_kernel<<<B, 1024, 0, st>>>(n, d_b, nullptr, 0, e->d_beta);
-    h->launches++;
-    GMPNP_CUDA_TRY(h, cudaMemcpyAsync(hp, e->d_beta, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
-    GMPNP_CUDA_TRY(h, cudaStreamSynchronize(st));
-    std::vector<double> beta0(hp, hp + B), tol(B);
-    for (int p = 0; p < B; ++p) tol[p] = rtol * beta0[p];
-    GMPNP_CUDA_TRY(h, cudaMemcpyAsync(e->d_tol, tol.data(), sizeof(double) * B, cudaMemcpyHostToDevice, st));
-    const double* rcur = d_b;
-    int total = 0;
-    std::vector<char> done(B, 0);
-    for (int p = 0; p < B; ++p) if (!(beta0[p] > 0.0)) done[p] = 1;
-    std::vector<double> g0((size_t)B * ld);
-    std::vector<int> jd(B);
-    while (total < maxit) {
-        // cycle start: V_0 = r / ||r||, g = (||r||, 0, ...)
-        norm_scale_kernel<<<B, 1024, 0, st>>>(n, rcur, e->d_V, (long)ld * n, e->d_beta);
+    const int m = o->lin_restart > 0 ? o->lin_restart : 50;
+    const int lin_maxit = o->lin_maxit > 0 ? o->lin_maxit : 1000;
+    const double lin_rtol = o->lin_rtol > 0 ? o->lin_rtol : 1e-10;
+    if (gmres_smem_bytes(m) > 220 * 1024) return GMPNP_ERR_ARG;          // restart length too long for shared memory
+    int rc = ensure_solver(h, m); if (rc) return rc;
+    NewtonCtl c{e->d_active, e->d_status, e->d_iters, e->d_lin_total, e->d_r0, e->d_r};
+    int* hp = (int*)h->h_pinned;
+    const int gB = (B + 127) / 128;
+    auto residual_norms = [&]() -> int {
+        int rc2 = launch_assemble(h, d_u, d_un, h->d_F, nullptr, st); if (rc2) return rc2;
+        norm_scale_kernel<<<B, 1024, 0, st>>>(n, h->d_F, nullptr, 0, e->d_nrm);
         h->launches++;
-        GMPNP_CUDA_TRY(h, cudaMemcpyAsync(hp, e->d_beta, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+        return GMPNP_OK;
+    };
+    auto read_active = [&](int& n_act) -> int {
+        GMPNP_CUDA_TRY(h, cudaMemcpyAsync(hp, e->d_nact, sizeof(int), cudaMemcpyDeviceToHost, st));
         GMPNP_CUDA_TRY(h, cudaStreamSynchronize(st));
-        std::fill(g0.begin(), g0.end(), 0.0);
-        bool all = true;
-        for (int p = 0; p < B; ++p) {
-            g0[(size_t)p * ld] = hp[p];
-            relres[p] = beta0[p] > 0 ? hp[p] / beta0[p] : 0.0;
-            jd[p] = -1;
-            if (done[p] || !(hp[p] > tol[p])) { done[p] = 1; jd[p] = 0; }
-            else all = false;
-        }
-        if (all) break;
-        GMPNP_CUDA_TRY(h, cudaMemcpyAsync(e->d_g, g0.data(), sizeof(double) * B * ld, cudaMemcpyHostToDevice, st));
-        GMPNP_CUDA_TRY(h, cudaMemcpyAsync(e->d_jdone, jd.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
-        const int mcyc = std::min(m, maxit - total);
-        for (int j = 0; j < mcyc; ++j) {
-            // w = J M^{-1} v_j
-            launch_precond(h, e->d_V + (long)j * n, (long)ld * n, e->d_z, st);
-            launch_spmv(h, h->d_J, e->d_z, e->d_w, st);
-            // classical Gram-Schmidt, twice (CGS2): two reductions per step, deterministic
-            dim3 gd(j + 1, B), gu(gridn, B);
-            multi_dot_kernel<<<gd, 256, 0, st>>>(n, n, e->d_V, e->d_w, e->d_d1, ld);
-            gs_update_kernel<<<gu, 256, 0, st>>>(n, n, j + 1, e->d_V, e->d_d1, e->d_w, ld);
-            multi_dot_kernel<<<gd, 256, 0, st>>>(n, n, e->d_V, e->d_w, e->d_d2, ld);
-            gs_update_kernel<<<gu, 256, 0, st>>>(n, n, j + 1, e->d_V, e->d_d2, e->d_w, ld);
-            norm_scale_kernel<<<B, 1024, 0, st>>>(n, e->d_w, e->d_V + (long)(j + 1) * n, (long)ld * n, e->d_nrm);
-            givens_kernel<<<(B + 63) / 64, 64, 0, st>>>(B, j, m, e->d_d1, e->d_d2, e->d_nrm, e->d_H, e->d_cs, e->d_sn,
-                                                        e->d_g, e->d_jdone, e->d_tol, ld);
-            h->launches += 6;
-        }
-        total += mcyc;
-        // x += M^{-1} (V y)
-        hsolve_kernel<<<(B + 63) / 64, 64, 0, st>>>(B, m, e->d_H, e->d_g, e->d_jdone, e->d_coef, ld);
-        dim3 gu(gridn, B);
-        lincomb_kernel<<<gu, 256, 0, st>>>(n, n, mcyc, e->d_V, e->d_coef, e->d_w, ld);
-        launch_precond(h, e->d_w, n, e->d_z, st);
-        axpby_kernel<<<gu, 256, 0, st>>>(n, 1.0, e->d_z, 1.0, d_x);
-        // true residual r = b - J x  -> e->d_w
-        launch_spmv(h, h->d_J, d_x, e->d_w, st);
-        axpby_kernel<<<gu, 256, 0, st>>>(n, 1.0, d_b, -1.0, e->d_w);
-        h->launches += 5;
-        GMPNP_CUDA_TRY(h, cudaMemcpyAsync(jd.data(), e->d_jdone, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
-        GMPNP_CUDA_TRY(h, cudaStreamSynchronize(st));
-        for (int p = 0; p < B; ++p)
-            if (!done[p]) its[p] += (jd[p] >= 0) ? jd[p] : mcyc;
-        rcur = e->d_w;
-    }
-    // final residual check
-    norm_scale_kernel<<<B, 1024, 0, st>>>(n, rcur, nullptr, 0, e->d_beta);
+        n_act = hp[0];
+        return GMPNP_OK;
+    };
+    rc = residual_norms(); if (rc) return rc;
+    GMPNP_CUDA_TRY(h, cudaMemsetAsync(e->d_nact, 0, sizeof(int), st));
+    newton_begin_kernel<<<gB, 128, 0, st>>>(B, d_enabled, e->d_nrm, c, o->criterion, o->atol, e->d_nact);
     h->launches++;
-    GMPNP_CUDA_TRY(h, cudaMemcpyAsync(hp, e->d_beta, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
-    GMPNP_CUDA_TRY(h, cudaStreamSynchronize(st));
-    for (int p = 0; p < B; ++p) relres[p] = beta0[p] > 0 ? hp[p] / beta0[p] : 0.0;
+    int n_act = 0;
+    rc = read_active(n_act); if (rc) return rc;
+    for (int k = 0; k < o->maxit && n_act > 0; ++k) {
+        // Jacobian at the current iterate, preconditioner, linear solve, masked update, new residual, control
+        rc = launch_assemble(h, d_u, d_un, nullptr, h->d_J, st); if (rc) return rc;
+        rc = launch_precond_setup(h, st); if (rc) return rc;
+        rc = launch_gmres(h, h->d_F, e->d_dx, m, lin_maxit, lin_rtol, e->d_active, st); if (rc) return rc;
+        newton_update_kernel<<<B, 1024, 0, st>>>(n, o->relax, e->d_active, e->d_dx, d_u, e->d_dxmax, e->d_umax);
+        h->launches++;
+        rc = residual_norms(); if (rc) return rc;
+        GMPNP_CUDA_TRY(h, cudaMemsetAsync(e->d_nact, 0, sizeof(int), st));
+        newton_step_kernel<<<gB, 128, 0, st>>>(B, k, o->maxit, e->d_nrm, e->d_dxmax, e->d_umax, e->d_lin_its, e->d_relres, c,
+                                               o->criterion, o->rtol, o->atol, o->xtol, lin_rtol, e->d_nact);
+        h->launches++;
+        rc = read_active(n_act); if (rc) return rc;
+    }
     GMPNP_CUDA_TRY(h, cudaGetLastError());
     return GMPNP_OK;
 }
@@ -1511,74 +2008,164 @@ int gmpnp_newton_3d(gmpnp_handle* h, double* d_u, const double* d_un, const gmpn
     if (!d_u || !d_un || !o) return GMPNP_ERR_ARG;
     GMPNP_CUDA_TRY(h, cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
+    rc = newton_run(h, d_u, d_un, o, nullptr, st); if (rc) return rc;
+    Host3D* e = ext(h);
+    const size_t B = h->batch;
+    const cudaMemcpyKind dd = cudaMemcpyDeviceToDevice;
+    if (d_iters) GMPNP_CUDA_TRY(h, cudaMemcpyAsync(d_iters, e->d_iters, sizeof(int) * B, dd, st));
+    if (d_status) GMPNP_CUDA_TRY(h, cudaMemcpyAsync(d_status, e->d_status, sizeof(int) * B, dd, st));
+    if (d_lin_iters) GMPNP_CUDA_TRY(h, cudaMemcpyAsync(d_lin_iters, e->d_lin_total, sizeof(int) * B, dd, st));
+    if (d_r0) GMPNP_CUDA_TRY(h, cudaMemcpyAsync(d_r0, e->d_r0, sizeof(double) * B, dd, st));
+    if (d_r) GMPNP_CUDA_TRY(h, cudaMemcpyAsync(d_r, e->d_r, sizeof(double) * B, dd, st));
+    GMPNP_CUDA_TRY(h, cudaStreamSynchronize(st));
+    return GMPNP_OK;
+}
+
+// ---- the reference's loop inside the library (3D/MPNP_CO2ER_pore.py:782-858) ----------------------------------
+int gmpnp_set_march_data_3d(gmpnp_handle* h, const signed char* h_kind, const double* h_tab, const double* h_sech,
+                            int batch) {
+    if (!h || h->dim != 3 || batch != h->batch || !h_tab || !h_sech || (h->n_dir > 0 && !h_kind)) return GMPNP_ERR_ARG;
+    for (int d = 0; d < h->n_dir; ++d)
+        if (h_kind[d] < 0 || h_kind[d] > 4) return GMPNP_ERR_ARG;
+    GMPNP_CUDA_TRY(h, cudaSetDevice(h->device));
+    Host3D* e = ext(h);
+    const size_t B = batch;
+    if (!e->d_kind) {
+        GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_kind, std::max(1, h->n_dir)));
+        GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_tab, sizeof(double) * 4 * B));
+        GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_sech, sizeof(double) * 8 * B));
+        GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_co2, sizeof(double) * B));
+        GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_med, sizeof(double) * 4 * B));
+        GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_inc, sizeof(double) * B));
+        GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_alive, sizeof(int) * B));
+        GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_steps, sizeof(int) * B));
+        GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_mstatus, sizeof(int) * B));
+        GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_conv, sizeof(int) * B));
+    }
+    if (h->n_dir > 0) GMPNP_CUDA_TRY(h, cudaMemcpy(e->d_kind, h_kind, h->n_dir, cudaMemcpyHostToDevice));
+    GMPNP_CUDA_TRY(h, cudaMemcpy(e->d_tab, h_tab, sizeof(double) * 4 * B, cudaMemcpyHostToDevice));
+    GMPNP_CUDA_TRY(h, cudaMemcpy(e->d_sech, h_sech, sizeof(double) * 8 * B, cudaMemcpyHostToDevice));
+    e->sech_mode1 = (h_sech[5] != 0.0);
+    e->march_set = true;
+    h->dir_set = true;                  // the march fills the Dirichlet values itself
+    return GMPNP_OK;
+}
+
+// one pseudo-time step for all alive problems: Dirichlet values (wall voltage * ramp, current CO2 entry value), one
+// Newton solve, bookkeeping, Sechenov update from the medians, u_n <- u
+static int march_step(gmpnp_handle* h, double* d_u, double* d_un, const gmpnp_newton_opts* o, int step, int n_steps,
+                      double ramp, double* d_hist_row, long hist_stride, int* d_iters, int* d_lin_iters, double* d_co2_out,
+                      int* n_alive, cudaStream_t st, double steady_tol = 0.0) {
     Host3D* e = ext(h);
     const int V = h->n_nodes, B = h->batch;
     const long n = (long)V * NC;
-    const int m = o->lin_restart > 0 ? o->lin_restart : 50;
-    const int lin_maxit = o->lin_maxit > 0 ? o->lin_maxit : 1000;
-    rc = ensure_krylov(h, m); if (rc) return rc;
-    double* hp = (double*)h->h_pinned;
-    std::vector<int> iters(B, 0), status(B, -1), lin_total(B, 0), active(B, 1);
-    std::vector<double> r0(B, 0.0), r(B, 0.0);
-    cudaFuncSetAttribute(coarse_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * NCO * NCO));
-    auto residual_norms = [&](std::vector<double>& out) -> int {
-        int rc2 = launch_assemble(h, d_u, d_un, h->d_F, nullptr, st); if (rc2) return rc2;
-        norm_scale_kernel<<<B, 1024, 0, st>>>(n, h->d_F, nullptr, 0, e->d_nrm);
+    dim3 gd((std::max(1, h->n_dir) + 255) / 256, B);
+    dirichlet_fill_kernel<<<gd, 256, 0, st>>>(B, h->n_dir, e->d_kind, e->d_tab, e->d_co2, ramp, h->d_dir_val, h->d_params);
+    h->launches++;
+    int rc = newton_run(h, d_u, d_un, o, e->d_alive, st); if (rc) return rc;
+    NewtonCtl c{e->d_active, e->d_status, e->d_iters, e->d_lin_total, e->d_r0, e->d_r};
+    GMPNP_CUDA_TRY(h, cudaMemsetAsync(e->d_nact, 0, sizeof(int), st));
+    march_record_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, step, n_steps, c, e->d_alive, d_iters, d_lin_iters, e->d_mstatus,
+                                                        e->d_steps, e->d_co2, d_co2_out, e->d_nact);
+    int np2 = 1;
+    while (np2 < V) np2 <<= 1;
+    cudaFuncSetAttribute(median4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(np2 * sizeof(double)));
+    dim3 gm(B, 4);
+    if (e->sech_mode1) median4_kernel<<<gm, 1024, np2 * sizeof(double), st>>>(V, np2, 0, 1, 2, 3, d_u, e->d_med);
+    else median4_kernel<<<gm, 1024, np2 * sizeof(double), st>>>(V, np2, 1, 2, 3, 7, d_u, e->d_med);
+    sechenov_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, e->d_alive, e->d_med, e->d_sech, e->d_co2);
+    march_advance_kernel<<<B, 1024, 0, st>>>(n, e->d_alive, d_u, d_un, d_hist_row, hist_stride, e->d_inc);
+    h->launches += 4;
+    if (steady_tol > 0.0) {
+        GMPNP_CUDA_TRY(h, cudaMemsetAsync(e->d_nact, 0, sizeof(int), st));
+        steady_check_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, steady_tol, e->d_alive, e->d_inc, e->d_conv, e->d_nact);
         h->launches++;
-        GMPNP_CUDA_TRY(h, cudaMemcpyAsync(hp, e->d_nrm, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
-        GMPNP_CUDA_TRY(h, cudaStreamSynchronize(st));
-        out.assign(hp, hp + B);
-        return GMPNP_OK;
-    };
-    rc = residual_norms(r0); if (rc) return rc;
-    r = r0;
-    for (int p = 0; p < B; ++p) {
-        if (!std::isfinite(r0[p])) { status[p] = GMPNP_NOT_FINITE; active[p] = 0; }
-        else if (o->criterion == 0 && r0[p] < o->atol) { status[p] = GMPNP_CONVERGED; active[p] = 0; }
     }
-    for (int k = 0; k < o->maxit; ++k) {
-        bool any = false;
-        for (int p = 0; p < B; ++p) any |= (active[p] != 0);
-        if (!any) break;
-        // Jacobian at the current iterate, preconditioner setup
-        rc = launch_assemble(h, d_u, d_un, nullptr, h->d_J, st); if (rc) return rc;
-        dim3 gj((V + 63) / 64, B);
-        bjacobi_invert_kernel<<<gj, 64, 0, st>>>(V, h->n_blocks, h->d_diag_idx, h->d_J, h->d_Dinv);
-        coarse_setup_kernel<<<B, 1024, sizeof(double) * NCO * NCO, st>>>(V, h->n_blocks, h->d_row_ptr, h->d_col_idx,
-                                                                         e->d_agg, h->d_dir_flag, h->d_J, e->d_Aci);
-        h->launches += 2;
-        std::vector<int> lits; std::vector<double> rel;
-        rc = gmres_solve(h, h->d_F, e->d_dx, m, lin_maxit, o->lin_rtol > 0 ? o->lin_rtol : 1e-10, lits, rel, st);
+    int* hp = (int*)h->h_pinned;
+    GMPNP_CUDA_TRY(h, cudaMemcpyAsync(hp, e->d_nact, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GMPNP_CUDA_TRY(h, cudaStreamSynchronize(st));
+    *n_alive = hp[0];
+    GMPNP_CUDA_TRY(h, cudaGetLastError());
+    return GMPNP_OK;
+}
+
+static int march_begin(gmpnp_handle* h, cudaStream_t st) {
+    Host3D* e = ext(h);
+    const int B = h->batch;
+    if (!e->march_set) return GMPNP_ERR_STATE;
+    int np2 = 1;
+    while (np2 < h->n_nodes) np2 <<= 1;
+    if ((size_t)np2 * sizeof(double) > 200 * 1024) {
+        h->last_cuda_error = "the Sechenov median (shared-memory sort) supports meshes of at most 16384 vertices";
+        return GMPNP_ERR_ARG;
+    }
+    std::vector<int> ones(B, 1), zeros(B, 0);
+    std::vector<double> co2(B);
+    std::vector<double> tab(4 * (size_t)B);
+    GMPNP_CUDA_TRY(h, cudaMemcpy(tab.data(), e->d_tab, sizeof(double) * 4 * B, cudaMemcpyDeviceToHost));
+    for (int p = 0; p < B; ++p) co2[p] = tab[4 * (size_t)p + 1];
+    GMPNP_CUDA_TRY(h, cudaMemcpyAsync(e->d_co2, co2.data(), sizeof(double) * B, cudaMemcpyHostToDevice, st));
+    GMPNP_CUDA_TRY(h, cudaMemcpyAsync(e->d_alive, ones.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
+    GMPNP_CUDA_TRY(h, cudaMemcpyAsync(e->d_steps, zeros.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
+    GMPNP_CUDA_TRY(h, cudaMemcpyAsync(e->d_mstatus, zeros.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
+    GMPNP_CUDA_TRY(h, cudaMemcpyAsync(e->d_conv, zeros.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
+    GMPNP_CUDA_TRY(h, cudaStreamSynchronize(st));
+    return GMPNP_OK;
+}
+
+int gmpnp_march_3d(gmpnp_handle* h, double* d_u, double* d_un, int n_steps, const gmpnp_newton_opts* opts,
+                   double* d_hist, int* d_iters, int* d_lin_iters, double* d_co2, int* d_steps, int* d_status,
+                   void* stream) {
+    if (!h || h->dim != 3 || !h->params_set) return h ? GMPNP_ERR_STATE : GMPNP_ERR_ARG;
+    if (!d_u || !d_un || !opts || n_steps < 1) return GMPNP_ERR_ARG;
+    GMPNP_CUDA_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = march_begin(h, st); if (rc) return rc;
+    Host3D* e = ext(h);
+    const long n = (long)h->n_nodes * NC;
+    const size_t B = h->batch;
+    for (int s = 0; s < n_steps; ++s) {
+        int n_alive = 0;
+        rc = march_step(h, d_u, d_un, opts, s, n_steps, 1.0, d_hist ? d_hist + (long)s * n : nullptr, (long)n_steps * n,
+                        d_iters, d_lin_iters, d_co2, &n_alive, st);
         if (rc) return rc;
-        GMPNP_CUDA_TRY(h, cudaMemcpyAsync(e->d_active, active.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
-        newton_update_kernel<<<B, 1024, 0, st>>>(n, o->relax, e->d_active, e->d_dx, d_u, e->d_dxmax, e->d_umax);
-        h->launches++;
-        GMPNP_CUDA_TRY(h, cudaMemcpyAsync(hp, e->d_dxmax, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
-        GMPNP_CUDA_TRY(h, cudaMemcpyAsync(hp + B, e->d_umax, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
-        GMPNP_CUDA_TRY(h, cudaStreamSynchronize(st));
-        std::vector<double> dxm(hp, hp + B), um(hp + B, hp + 2 * B);
-        std::vector<double> rn;
-        rc = residual_norms(rn); if (rc) return rc;
-        for (int p = 0; p < B; ++p) {
-            if (!active[p]) continue;
-            iters[p] = k + 1;
-            lin_total[p] += lits[p];
-            r[p] = rn[p];
-            const bool linfail = rel[p] > 1e3 * (o->lin_rtol > 0 ? o->lin_rtol : 1e-10);
-            if (!std::isfinite(rn[p]) || !std::isfinite(dxm[p])) { status[p] = GMPNP_NOT_FINITE; active[p] = 0; continue; }
-            bool conv;
-            if (o->criterion == 0) conv = (rn[p] / r0[p] < o->rtol) || (rn[p] < o->atol);
-            else conv = dxm[p] <= o->xtol * std::max(1.0, um[p]);
-            if (conv) { status[p] = GMPNP_CONVERGED; active[p] = 0; }
-            else if (linfail) { status[p] = GMPNP_LINEAR_FAILED; active[p] = 0; }
-        }
+        if (n_alive == 0) break;
     }
-    for (int p = 0; p < B; ++p) if (status[p] < 0) status[p] = GMPNP_MAXIT;
-    if (d_iters) GMPNP_CUDA_TRY(h, cudaMemcpyAsync(d_iters, iters.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
-    if (d_status) GMPNP_CUDA_TRY(h, cudaMemcpyAsync(d_status, status.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
-    if (d_lin_iters) GMPNP_CUDA_TRY(h, cudaMemcpyAsync(d_lin_iters, lin_total.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
-    if (d_r0) GMPNP_CUDA_TRY(h, cudaMemcpyAsync(d_r0, r0.data(), sizeof(double) * B, cudaMemcpyHostToDevice, st));
-    if (d_r) GMPNP_CUDA_TRY(h, cudaMemcpyAsync(d_r, r.data(), sizeof(double) * B, cudaMemcpyHostToDevice, st));
+    if (d_steps) GMPNP_CUDA_TRY(h, cudaMemcpyAsync(d_steps, e->d_steps, sizeof(int) * B, cudaMemcpyDeviceToDevice, st));
+    if (d_status) GMPNP_CUDA_TRY(h, cudaMemcpyAsync(d_status, e->d_mstatus, sizeof(int) * B, cudaMemcpyDeviceToDevice, st));
+    GMPNP_CUDA_TRY(h, cudaStreamSynchronize(st));
+    return GMPNP_OK;
+}
+
+int gmpnp_steady_3d(gmpnp_handle* h, double* d_u, double* d_un, const gmpnp_newton_opts* opts, double tol, int max_steps,
+                    int n_ramp, int* d_iters, double* d_inc_hist, double* d_co2, int* d_steps, int* d_status,
+                    int* d_converged, int* h_steps_run, void* stream) {
+    if (!h || h->dim != 3 || !h->params_set) return h ? GMPNP_ERR_STATE : GMPNP_ERR_ARG;
+    if (!d_u || !d_un || !opts || max_steps < 1 || n_ramp < 1 || !(tol > 0.0)) return GMPNP_ERR_ARG;
+    GMPNP_CUDA_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = march_begin(h, st); if (rc) return rc;
+    Host3D* e = ext(h);
+    const size_t B = h->batch;
+    int steps = 0;
+    for (int s = 0; s < max_steps; ++s) {
+        const double ramp = std::min(1.0, (double)(s + 1) / (double)n_ramp);
+        int n_alive = 0;
+        // the steady-state test (per problem, on the device) starts once the ramp is complete
+        rc = march_step(h, d_u, d_un, opts, s, max_steps, ramp, nullptr, 0, d_iters, nullptr, nullptr, &n_alive, st,
+                        (s + 1 >= n_ramp) ? tol : 0.0);
+        if (rc) return rc;
+        steps = s + 1;
+        if (d_inc_hist)
+            GMPNP_CUDA_TRY(h, cudaMemcpyAsync(d_inc_hist + (size_t)s * B, e->d_inc, sizeof(double) * B, cudaMemcpyDeviceToDevice, st));
+        if (n_alive == 0) break;
+    }
+    if (h_steps_run) *h_steps_run = steps;
+    const cudaMemcpyKind dd = cudaMemcpyDeviceToDevice;
+    if (d_co2) GMPNP_CUDA_TRY(h, cudaMemcpyAsync(d_co2, e->d_co2, sizeof(double) * B, dd, st));
+    if (d_steps) GMPNP_CUDA_TRY(h, cudaMemcpyAsync(d_steps, e->d_steps, sizeof(int) * B, dd, st));
+    if (d_status) GMPNP_CUDA_TRY(h, cudaMemcpyAsync(d_status, e->d_mstatus, sizeof(int) * B, dd, st));
+    if (d_converged) GMPNP_CUDA_TRY(h, cudaMemcpyAsync(d_converged, e->d_conv, sizeof(int) * B, dd, st));
     GMPNP_CUDA_TRY(h, cudaStreamSynchronize(st));
     return GMPNP_OK;
 }

@@ -130,6 +130,54 @@ class Solver3D:
                                        ptr(st), self._stream()), self._h)
         return dict(iters=it, r0=r0, r=r, lin_iters=li, status=st)
 
+    def set_march_data(self, kind, tab, sech):
+        """Per-DOF Dirichlet kinds (0..4, ``marking.dirichlet_sets``), per-problem value table [batch, 4] =
+        (wall potential, initial CO2 entry value, CO entry, H2 entry) and Sechenov records [batch, 8]
+        (``PoreProblem.march_data``) for the library-side loops ``march`` / ``steady``."""
+        kind = np.ascontiguousarray(kind, dtype=np.int8)
+        tab = np.ascontiguousarray(tab, dtype=np.float64).reshape(self.batch, 4)
+        sech = np.ascontiguousarray(sech, dtype=np.float64).reshape(self.batch, 8)
+        assert kind.shape == (len(self.dir_dofs),)
+        check(self.lib.gmpnp_set_march_data_3d(self._h, kind.ctypes.data_as(C.POINTER(C.c_byte)),
+                                               tab.ctypes.data_as(C.POINTER(C.c_double)),
+                                               sech.ctypes.data_as(C.POINTER(C.c_double)), self.batch), self._h)
+
+    def march(self, u, un, n_steps: int, opts: NewtonOpts | None = None, history: bool = False):
+        """The reference's loop 3D:782-858 inside the library: per step the Dirichlet values (incl. the current CO2
+        entry value), one damped Newton solve, the Sechenov update from the nodal medians, u_n <- u.  A problem whose
+        Newton solve fails stops (status), the others go on."""
+        opts = opts or NewtonOpts.reference_3d()
+        self._chk(u); self._chk(un)
+        dev, B = self.device, self.batch
+        hist = torch.zeros(B, n_steps, self.n, NC, dtype=torch.float64, device=dev) if history else None
+        it = torch.zeros(B, n_steps, dtype=torch.int32, device=dev)
+        li = torch.zeros(B, n_steps, dtype=torch.int32, device=dev)
+        co2 = torch.zeros(B, n_steps, dtype=torch.float64, device=dev)
+        steps = torch.zeros(B, dtype=torch.int32, device=dev)
+        st = torch.zeros(B, dtype=torch.int32, device=dev)
+        check(self.lib.gmpnp_march_3d(self._h, ptr(u), ptr(un), int(n_steps), C.byref(opts), ptr(hist), ptr(it), ptr(li),
+                                      ptr(co2), ptr(steps), ptr(st), self._stream()), self._h)
+        return dict(history=hist, iters=it, lin_iters=li, co2_entry=co2, steps=steps, status=st)
+
+    def steady(self, u, un, opts: NewtonOpts | None = None, tol: float = 1e-10, max_steps: int = 200, n_ramp: int = 1):
+        """Pseudo-time march to the steady state inside the library, wall voltage ramped over ``n_ramp`` steps; stops
+        when the last relative increment of every problem still alive is <= tol (after the ramp)."""
+        opts = opts or NewtonOpts.reference_3d()
+        self._chk(u); self._chk(un)
+        dev, B = self.device, self.batch
+        it = torch.zeros(B, max_steps, dtype=torch.int32, device=dev)
+        inc = torch.zeros(max_steps, B, dtype=torch.float64, device=dev)
+        co2 = torch.zeros(B, dtype=torch.float64, device=dev)
+        steps = torch.zeros(B, dtype=torch.int32, device=dev)
+        st = torch.zeros(B, dtype=torch.int32, device=dev)
+        cv = torch.zeros(B, dtype=torch.int32, device=dev)
+        run = C.c_int(0)
+        check(self.lib.gmpnp_steady_3d(self._h, ptr(u), ptr(un), C.byref(opts), float(tol), int(max_steps), int(n_ramp),
+                                       ptr(it), ptr(inc), ptr(co2), ptr(steps), ptr(st), ptr(cv), C.byref(run),
+                                       self._stream()), self._h)
+        k = run.value
+        return dict(iters=it[:, :k], increments=inc[:k], co2_entry=co2, steps=steps, status=st, converged=cv, steps_run=k)
+
     def median(self, u, comp: int):
         self._chk(u)
         med = torch.empty(self.batch, dtype=torch.float64, device=self.device)
@@ -194,74 +242,87 @@ class PoreProblem:
             out.append(_params.sechenov_co2_scaled(p, med[1][b], med[2][b], med[3][b], cat / c0[7]))
         return out
 
+    def march_data(self, V=None):
+        """Arrays for ``Solver3D.set_march_data``: value table and Sechenov records (CO2_conc, 3D:70-93, with the
+        constant factors folded: co2_scaled = A * 10^-(sum_k coef_k * median_k))."""
+        import math
+        tab, sech = [], []
+        for b, p in enumerate(self.plist):
+            e = p.extras
+            eq = e["eq_scaled"]
+            tab.append([p.V if V is None else V[b], float(eq[0]), float(eq[1]), float(eq[2])])
+            h = e["h_sechenov"]
+            temp = e["temp"]
+            lnK = 93.4517 * (100 / temp) - 60.2409 + 23.3585 * math.log(temp / 100)
+            h_co2 = h["CO2_0"] + h["CO2_T"] * (temp - 298.15)
+            A = e["fugacity_CO2"] * math.exp(lnK) * 1000 / p.c0[4]
+            cat = p.species[-1]
+            c = p.c0
+            if not self.rxn_diff:
+                sech.append([A, (h["OH"] + h_co2) * c[1] / 1000, (h["HCO3"] + h_co2) * c[2] / 1000,
+                             (h["CO32"] + h_co2) * c[3] / 1000, (h[cat] + h_co2) * c[7] / 1000, 0.0, 0.0, 0.0])
+            else:           # electroneutral cation c_HCO3 + 2 c_CO32 + c_OH - c_H (RD3:589-592) folded into the ion terms
+                hc = h[cat] + h_co2
+                sech.append([A, (h["OH"] + h_co2 + hc) * c[1] / 1000, (h["HCO3"] + h_co2 + hc) * c[2] / 1000,
+                             (h["CO32"] + h_co2 + 2 * hc) * c[3] / 1000, 0.0, 1.0, -hc * c[0] / 1000, 0.0])
+        return self.kind.astype(np.int8), np.array(tab), np.array(sech)
+
     def march(self, n_steps: int, opts: NewtonOpts | None = None, history=True):
         """The reference's loop (3D:782-858): u = 0, u_n = (1,..,1,0); per step one damped Newton solve,
-        then the CO2 entry Dirichlet value is re-evaluated from the nodal MEDIANS (3D:817-838)."""
+        then the CO2 entry Dirichlet value is re-evaluated from the nodal MEDIANS (3D:817-838).  The whole loop runs
+        inside the library (``gmpnp_march_3d``); like dolfin, a failed Newton solve raises."""
         opts = opts or NewtonOpts.reference_3d()
         s = self.solver
         B = s.batch
+        s.set_params(self.plist)
+        s.set_march_data(*self.march_data())
         u = torch.zeros(B, s.n, NC, dtype=torch.float64, device=self.device)
         if self.rxn_diff:
             u[:, :, 7] = 1.0                               # passenger cation: stays at its bulk value
         un = bulk_state(B, s.n, self.device)
-        co2 = [float(p.extras["eq_scaled"][0]) for p in self.plist]
-        hist, its, lin, co2s = [un.cpu().numpy().copy()], [], [], []
-        for _ in range(n_steps):
-            s.set_dirichlet(self.dirichlet_values(co2))
-            co2s.append(list(co2))
-            out = s.newton(u, un, opts)
-            st = out["status"].cpu().numpy()
-            if (st != 0).any():
-                raise RuntimeError(f"Newton solver did not converge: status {st.tolist()}")   # dolfin raises too
-            its.append(out["iters"].cpu().numpy().copy())
-            lin.append(out["lin_iters"].cpu().numpy().copy())
-            co2 = self._sechenov_update(u)
-            if history:
-                hist.append(u.cpu().numpy().copy())
-            un.copy_(u)
-        return dict(u=u, history=np.array(hist) if history else None, iters=np.array(its), lin_iters=np.array(lin),
-                    co2_entry=np.array(co2s))
+        first = un.cpu().numpy().copy() if history else None
+        out = s.march(u, un, n_steps, opts, history=history)
+        st = out["status"].cpu().numpy()
+        if (st != 0).any():
+            raise RuntimeError(f"Newton solver did not converge: status {st.tolist()}")   # dolfin raises too
+        hist = None
+        if history:
+            hist = np.concatenate([first[None], out["history"].permute(1, 0, 2, 3).cpu().numpy()])
+        return dict(u=u, history=hist, iters=out["iters"].cpu().numpy().T, lin_iters=out["lin_iters"].cpu().numpy().T,
+                    co2_entry=out["co2_entry"].cpu().numpy().T)
 
-    def steady(self, opts: NewtonOpts | None = None, tol: float = 1e-10, max_steps: int = 200, dt_growth: float = 1.0,
-               u0=None, dv_max: float | None = None):
-        """Steady state as the limit of the reference's pseudo-time march, optionally with a VOLTAGE RAMP.
+    def steady(self, opts: NewtonOpts | None = None, tol: float = 1e-10, max_steps: int = 200,
+               u0=None, dv_max: float | None = None, raise_on_failure: bool = True):
+        """Steady state as the limit of the reference's pseudo-time march, optionally with a VOLTAGE RAMP, inside the
+        library (``gmpnp_steady_3d``).
 
         With the as-executed boundary conditions (3D:460-467, no facet integrals -- SURVEY finding 3) every ionic
         species is pure-Neumann, so the time-independent equations are singular: the total amount of, e.g., the
         cation is fixed only by the initial state, which backward Euler conserves exactly.  The steady state is
         therefore computed the way the reference reaches it (3D:782-858: backward Euler with dt_scaled = 73.84,
-        Sechenov median update per step) and marched until max|u - u_n| <= tol * max(1, max|u|), optionally
-        growing the step.  Each step is one damped Newton solve (relaxation 0.9, 3D:796) from the previous state.
+        Sechenov median update per step) and marched until max|u - u_n| <= tol * max(1, max|u|) for every problem.
+        Each step is one damped Newton solve (relaxation 0.9, 3D:796) from the previous state.
 
         ``dv_max`` (in V_T): the reference applies the full wall voltage in the first step, from which its Newton
         iteration diverges beyond |V| ~ 1.5 V_T on L_50_R_5; with ``dv_max`` the wall voltage of every problem is
         ramped proportionally over ceil(max|V| / dv_max) pseudo-time steps (voltage continuation, BASELINE
-        north_star), and the convergence test only starts once the ramp is complete."""
+        north_star), and the convergence test only starts once the ramp is complete.  A problem whose Newton solve
+        fails is parked (status != 0, ``converged`` False); with ``raise_on_failure`` that raises like dolfin."""
         opts = opts or NewtonOpts.reference_3d()
         s = self.solver
         B = s.batch
+        s.set_params(self.plist)
+        s.set_march_data(*self.march_data())
         un = bulk_state(B, s.n, self.device) if u0 is None else u0.clone()
         u = un.clone()
-        co2 = [float(p.extras["eq_scaled"][0]) for p in self.plist]
-        packed = np.stack([p.pack() for p in self.plist])
         Vt = np.array([p.V for p in self.plist], dtype=np.float64)
         n_ramp = 1 if not dv_max else max(1, int(np.ceil(np.abs(Vt).max() / dv_max - 1e-12)))
-        its, incs = [], []
-        for step in range(max_steps):
-            Vk = Vt * min(1.0, (step + 1) / n_ramp)
-            packed[:, _params.P_V] = Vk
-            s.set_params(packed)
-            s.set_dirichlet(self.dirichlet_values(co2, V=Vk))
-            out = s.newton(u, un, opts)
-            st = out["status"].cpu().numpy()
-            if (st != 0).any():
-                raise RuntimeError(f"Newton solver did not converge in pseudo-time step {step}: status {st.tolist()}")
-            its.append(out["iters"].cpu().numpy().copy())
-            co2 = self._sechenov_update(u)
-            inc = float((u - un).abs().max() / max(1.0, float(u.abs().max())))
-            incs.append(inc)
-            un.copy_(u)
-            packed[:, _params.P_KAPPA] /= dt_growth
-            if inc <= tol and step + 1 >= n_ramp:
-                break
-        return dict(u=u, iters=np.array(its), increments=np.array(incs), co2_entry=np.array(co2), steps=len(incs))
+        out = s.steady(u, un, opts, tol=tol, max_steps=max_steps, n_ramp=n_ramp)
+        st = out["status"].cpu().numpy()
+        if raise_on_failure and (st != 0).any():
+            raise RuntimeError(f"Newton solver did not converge in the pseudo-time march: status {st.tolist()}")
+        inc = out["increments"].cpu().numpy()                       # [steps, B]
+        conv = (st == 0) & (out["converged"].cpu().numpy() != 0)
+        return dict(u=u, iters=out["iters"].cpu().numpy().T, increments=inc.max(axis=1), increments_per_problem=inc,
+                    co2_entry=out["co2_entry"].cpu().numpy(), steps=out["steps_run"], status=st, converged=conv,
+                    steps_per_problem=out["steps"].cpu().numpy())

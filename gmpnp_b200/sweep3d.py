@@ -78,57 +78,24 @@ class Sweep3D:
         return res
 
     def _steady_with_parking(self, pp: PoreProblem):
+        """One batch through ``gmpnp_steady_3d``: the wall voltages are ramped together, every point stops marching
+        when its own increment is below ``tol``; a point whose Newton solve fails is PARKED by the library (its
+        status is reported, the rest of the batch goes on).  Status 1 also marks points that did not reach ``tol``
+        within ``max_steps``."""
         s = pp.solver
-        B = s.batch
-        dev = pp.device
-        un = bulk_state(B, s.n, dev)
-        u = un.clone()
-        co2 = [float(p.extras["eq_scaled"][0]) for p in pp.plist]
-        packed = np.stack([p.pack() for p in pp.plist])
-        Vt = np.array([p.V for p in pp.plist], dtype=np.float64)
-        n_ramp = max(1, int(np.ceil(np.abs(Vt).max() / self.dv_max - 1e-12)))
-        status = np.zeros(B, dtype=np.int64)
-        its = np.zeros(B, dtype=np.int64)
-        steps = np.zeros(B, dtype=np.int64)
-        parked = np.zeros(B, dtype=bool)
-        done = np.zeros(B, dtype=bool)
-        bulk = bulk_state(1, s.n, dev)[0]
-        for step in range(self.max_steps):
-            Vk = np.where(parked, 0.0, Vt * min(1.0, (step + 1) / n_ramp))
-            packed[:, _params.P_V] = Vk
-            s.set_params(packed)
-            s.set_dirichlet(pp.dirichlet_values(co2, V=Vk))
-            out = s.newton(u, un, self.opts)
-            st = out["status"].cpu().numpy()
-            k = out["iters"].cpu().numpy()
-            newly = (st != 0) & ~parked
-            for b in np.nonzero(newly)[0]:
-                status[b] = st[b]
-                parked[b] = True
-                u[b].copy_(bulk)
-                un[b].copy_(bulk)
-                co2[b] = float(pp.plist[b].extras["eq_scaled"][0])
-            live = ~parked & ~done
-            its[live] += k[live]
-            steps[live] += 1
-            med = [s.median(u, c).cpu().numpy() for c in (1, 2, 3, 7)]
-            for b in np.nonzero(~parked)[0]:
-                co2[b] = _params.sechenov_co2_scaled(pp.plist[b], med[0][b], med[1][b], med[2][b], med[3][b])
-            inc = ((u - un).abs().amax(dim=(1, 2)) / u.abs().amax(dim=(1, 2)).clamp(min=1.0)).cpu().numpy()
-            un.copy_(u)
-            if step + 1 >= n_ramp:
-                done |= (inc <= self.tol) & ~parked
-            if (done | parked).all():
-                break
-        status[~parked & ~done] = 1                                  # max_steps reached
+        out = pp.steady(opts=self.opts, tol=self.tol, max_steps=self.max_steps, dv_max=self.dv_max,
+                        raise_on_failure=False)
+        u = out["u"]
+        status = out["status"].astype(np.int64).copy()
+        status[(status == 0) & ~out["converged"]] = 1                 # max_steps reached
         med = [s.median(u, c).cpu().numpy() for c in (1, 2, 3, 7)]
         ucat = u[:, :, 7].amax(dim=1).cpu().numpy()
-        out = np.zeros((B, self.NCOL))
-        out[:, 0], out[:, 1], out[:, 2] = status, steps, its
+        res = np.zeros((s.batch, self.NCOL))
+        res[:, 0], res[:, 1], res[:, 2] = status, out["steps_per_problem"], out["iters"].sum(axis=0)
         for j in range(4):
-            out[:, 3 + j] = med[j]
-        out[:, 7], out[:, 8] = np.array(co2), ucat
-        return out
+            res[:, 3 + j] = med[j]
+        res[:, 7], res[:, 8] = out["co2_entry"], ucat
+        return res
 
 
 def shard(points, rank: int, world: int):

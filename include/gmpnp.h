@@ -11,8 +11,8 @@
  *     see gmpnp_strerror); numerical outcomes are reported per problem in `status[]`;
  *   - all `d_*` pointers are caller-owned DEVICE buffers (e.g. torch tensors' data_ptr());
  *     `h_*` pointers are host buffers; `stream` is a cudaStream_t passed as void*;
- *   - a handle owns only its mesh copy, parameter records and elimination workspace;
- *     handles are independent (thread-compatible per handle), there are no globals.
+ *   - a handle owns its mesh copy, parameter records and work buffers; handles are independent
+ *     (thread-compatible per handle); the library has no process-wide state.
  *
  * Unknown layout: node-major interleaved, u[problem][node][comp], comp = species in the
  * reference's order (1D:117 / 3D:138) with the potential last (1D:303, 3D:407).
@@ -186,6 +186,35 @@ int gmpnp_spmv_3d(gmpnp_handle* h, const double* d_J, const double* d_x, double*
 int gmpnp_newton_3d(gmpnp_handle* h, double* d_u, const double* d_un,
                     const gmpnp_newton_opts* opts, int* d_iters, double* d_r0, double* d_r,
                     int* d_lin_iters, int* d_status, void* stream);
+
+/* ---- the reference's loop inside the library (3D/MPNP_CO2ER_pore.py:782-858) -------------------------------------
+ * gmpnp_set_march_data_3d: what the loop needs besides the parameter records:
+ *   h_kind[n_dir]   kind of every Dirichlet DOF of gmpnp_create_3d's list: 0 -> 0 (potential at pore entry / exit,
+ *                   3D:460-461), 1 -> wall potential (3D:462), 2/3/4 -> CO2 / CO / H2 entry value (3D:463-465);
+ *   h_tab[batch][4] (wall potential, initial CO2 entry value, CO entry value, H2 entry value), scaled;
+ *   h_sech[batch][8] Sechenov record of the per-step update of the CO2 entry value from the nodal MEDIANS (3D:817-838,
+ *                   CO2_conc 3D:70-93): co2 = s[0] * 10^-(s[1] m_OH + s[2] m_HCO3 + s[3] m_CO32 + s[4] m_cat) (s[5] = 0;
+ *                   s[5] = 1: the reaction-diffusion script's electroneutral cation, 3D/rxn_diff_CO2ER_pore.py:575-601:
+ *                   medians of (H, OH, HCO3, CO32), exponent s[6] m_H + s[1] m_OH + s[2] m_HCO3 + s[3] m_CO32).
+ * gmpnp_march_3d: n_steps times { Dirichlet values with the current CO2 entry value (3D:835-838); solve (3D:789-799);
+ *   medians + Sechenov update (3D:817-834); u_n <- u (3D:856) }.  A problem whose Newton solve fails stops (its status is
+ *   the Newton status; dolfin would raise), the others continue.  Optional outputs (device): d_hist
+ *   [batch][n_steps][n_vert][9], d_iters / d_lin_iters [batch][n_steps], d_co2 [batch][n_steps] (entry value USED in the
+ *   step), d_steps [batch] (steps completed), d_status [batch].  Control flow is device-resident: the host reads one
+ *   counter per Newton iteration and one per step; the linear solves run in one launch each.
+ * gmpnp_steady_3d: the same loop run to the steady state, with the wall potential ramped linearly over the first
+ *   n_ramp steps (voltage continuation).  From step n_ramp on, a problem whose last increment satisfies max|u - u_n|
+ *   <= tol * max(1, max|u|) stops marching (d_converged[p] = 1, d_steps[p] = its number of steps); the loop ends when
+ *   no problem is marching any more or after max_steps.  d_iters [batch][max_steps], d_inc_hist [max_steps][batch]
+ *   (relative increment per step, 0 for stopped problems), d_co2 [batch] (final entry value), *h_steps_run = steps run.  */
+int gmpnp_set_march_data_3d(gmpnp_handle* h, const signed char* h_kind, const double* h_tab, const double* h_sech,
+                            int batch);
+int gmpnp_march_3d(gmpnp_handle* h, double* d_u, double* d_un, int n_steps, const gmpnp_newton_opts* opts,
+                   double* d_hist, int* d_iters, int* d_lin_iters, double* d_co2, int* d_steps, int* d_status,
+                   void* stream);
+int gmpnp_steady_3d(gmpnp_handle* h, double* d_u, double* d_un, const gmpnp_newton_opts* opts, double tol, int max_steps,
+                    int n_ramp, int* d_iters, double* d_inc_hist, double* d_co2, int* d_steps, int* d_status,
+                    int* d_converged, int* h_steps_run, void* stream);
 
 /* ---- mesh-partitioned mode (one problem spans the GPUs of a box; SURVEY 8e (2), BASELINE config 5) -----------
  * The reference has no distributed path; these are the per-rank building blocks of the
