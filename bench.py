@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pore3d-batch", type=int, default=128, help="3D pore problems per GPU in the 3D part (0: skip)")
     ap.add_argument("--no-config1", action="store_true", help="skip the config-1 latency measurement")
+    ap.add_argument("--mesh5-refine", type=int, default=3,
+                    help="N > 1: red-refinement level of the mesh-partitioned config-5 part (3 = 6.17 M DOFs; 0: skip)")
     ap.add_argument("--pivot", type=int, default=0, help="partial pivoting inside the 7x7 blocks (0: none; "
                     "failed points are retried with pivoting, see Sweep1D)")
     ap.add_argument("--dv", type=float, default=0.75, help="largest voltage increment of the continuation [V_T]")
@@ -312,32 +314,42 @@ def bench_pore3d(local, world, dev, batch, peak):
     b_asm = batch * (8 * 81 * nb + 8 * 9 * Vn + 2 * 8 * 9 * Vn + 8 * 3 * Vn + 4 * 4 * T + 4 * 16 * T)
     b_spmv = batch * (8 * 81 * nb + 4 * nb + 4 * (Vn + 1) + 2 * 8 * 9 * Vn)
     del F, J, x
-    o3 = NewtonOpts.sweep_3d()
-    pp.steady(opts=o3, tol=1e-8, max_steps=3)             # warm-up (allocations of the Krylov basis)
-    sync()
-    l1 = s.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    out = pp.steady(opts=o3, tol=1e-8, max_steps=20)
-    e1.record()
-    sync()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_steady = float(t[0])
     traffic = {}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp))
-    n_conv = int(batch if out.get("converged") is None else int(np.sum(out["converged"])))
+
+    def steady_run(opts):
+        pp.steady(opts=opts, tol=1e-8, max_steps=2, raise_on_failure=False)      # warm-up (workspace allocation)
+        sync()
+        l1 = s.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = pp.steady(opts=opts, tol=1e-8, max_steps=20, raise_on_failure=False)
+        e1.record()
+        sync()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_ = float(t[0])
+        n_conv = int(np.sum(out["converged"]))
+        return out, dict(steady_solves_per_s=world * n_conv / (ms_ * 1e-3), ms_per_batch=ms_, converged=n_conv,
+                         problems=batch, pseudo_time_steps=int(out["steps"]),
+                         newton_iterations_per_problem=int(out["iters"].sum(axis=0).max()),
+                         gpu_launches=int(s.launch_count() - l1))
+
+    out, main_run = steady_run(NewtonOpts.sweep_3d())
+    out2, fast_run = steady_run(NewtonOpts.sweep_3d_inexact())
+    d = (out2["u"] - out["u"]).abs().amax(dim=(1, 2)) / out["u"].abs().amax(dim=(1, 2))
+    fast_run["max_rel_distance_to_the_1e-8_iterate"] = float(d.max())
+    fast_run["setting"] = "NewtonOpts.sweep_3d_inexact: GMRES(40) to eta = 1e-4 (constant forcing term)"
     res = {
         "workload": f"config3 batch: L_50_R_5 (V=3679, T=17297, 33111 DOFs), {batch} wall voltages in [-0.5,-1.25] V_T per GPU, "
-                    "pseudo-time march to steady state (increment <= 1e-8); damped Newton (relaxation 0.9, residual "
-                    "criterion 1e-4 as 3D:789-798), GMRES(40) to 1e-8 + block-Jacobi + z-slab coarse space",
-        "steady_solves_per_s": world * n_conv / (ms_steady * 1e-3), "ms_per_batch": ms_steady,
-        "converged": n_conv, "problems": batch,
-        "pseudo_time_steps": int(out["steps"]), "newton_iterations_per_problem": int(out["iters"].sum(axis=0).max()),
-        "gpu_launches": int(s.launch_count() - l1),
+                    "pseudo-time march to steady state (increment <= 1e-8 per problem) inside the library "
+                    "(gmpnp_steady_3d: device-resident control, one launch per linear solve); damped Newton (relaxation "
+                    "0.9, residual criterion 1e-4 as 3D:789-798), GMRES(40) to 1e-8 + block-Jacobi + z-slab coarse space",
+        **main_run,
+        "inexact": fast_run,
         "assemble": {"ms": ms_asm, "GBs": b_asm / ms_asm / 1e6, "frac_of_hbm_peak": b_asm / ms_asm / 1e6 / peak,
                      "algorithmic_bytes": b_asm,
                      "dram_traffic_over_algorithmic_ncu": traffic.get("assemble3d_dram_bytes_over_algorithmic_bytes"),
@@ -349,6 +361,109 @@ def bench_pore3d(local, world, dev, batch, peak):
     }
     pp.solver.close()
     return res
+
+
+def bench_mesh5(local, world, rank, dev, refine, peak):
+    """BASELINE config 5: the synthetic refined pore (L_10_R_5 red-refined `refine` times = the aspect of the missing
+    L_100_R_50 mesh; x3: 6.17 M DOFs, 6.5 GB Jacobian) PARTITIONED over the ranks (z-slabs, halo exchange over
+    NCCL/NVLink, all-reduced dot products): assembly, SpMV incl. halo, GMRES iterations at the full size, and a complete
+    damped Newton solve of the reference's first time step at x(refine-1) (the x3 linear systems need ~2400 GMRES
+    iterations per Newton step with the block-Jacobi + 16-slab coarse preconditioner: profiles/r02_config5_*)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from gmpnp_b200 import marking, meshio, params, partition
+    from gmpnp_b200.dist3d import PartitionedPore, TorchComm
+    L, R = 100e-9, 50e-9
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def tmax(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        barrier()
+        return tmax(e0.elapsed_time(e1) / reps)
+
+    def build(level):
+        t0 = time.time()
+        mesh = meshio.load_mesh("L_10_R_5")
+        for _ in range(level):
+            mesh = meshio.red_refine(mesh, project_radius=R / L)
+        prm = params.params_3d(L=L, R=R)
+        part = partition.partition_z(mesh, world, ranks=[rank])
+        pp = PartitionedPore(mesh, L, R, prm, part, TorchComm(part[0]), device=local,
+                             dirichlet=marking.dirichlet_sets(mesh, L, R))
+        return mesh, part, pp, time.time() - t0
+
+    # ---- kernels and one GMRES cycle at the full size ------------------------------------------------------
+    mesh, part, pp, setup_s = build(refine)
+    nv, nt = mesh.x.shape[0], mesh.cells.shape[0]
+    rng = np.random.default_rng(0)
+    ug = np.ones((nv, 9)); ug[:, 8] = 0.0
+    ung = ug.copy()
+    ug += 0.01 * rng.random((nv, 9))
+    us, uns = pp.from_global(ug), pp.from_global(ung)
+    Fs, _ = pp.assemble(us, uns)
+    ms_asm = timed(lambda: pp.assemble(us, uns), 5)
+    xs = pp.from_global(rng.normal(size=(nv, 9)))
+    ms_spmv = timed(lambda: pp.spmv(xs), 20)
+    ms_spmv_local = timed(lambda: [s.spmv(J, x) for s, J, x in zip(pp.solvers, pp.J, xs)], 20)
+    pp.gmres(Fs, m=30, maxit=30, rtol=1e-30)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _, its, _rel = pp.gmres(Fs, m=30, maxit=30, rtol=1e-30)
+    e1.record()
+    barrier()
+    ms_gmres = tmax(e0.elapsed_time(e1)) / max(its, 1)
+    cnt = torch.tensor([sum(s.n_blocks for s in pp.solvers), part[0].n_own, part[0].n_ghost,
+                        part[0].halo_doubles() * 8], dtype=torch.float64, device=dev)
+    dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    nb_tot, own_tot, ghost_tot, halo_tot = [float(v) for v in cnt.tolist()]
+    b_spmv = 8 * 81 * nb_tot + 4 * nb_tot + 4 * (own_tot + world) + 2 * 8 * 9 * own_tot
+    b_asm = 8 * 81 * nb_tot + 3 * 8 * 9 * own_tot + 8 * 3 * own_tot + (4 * 4 + 4 * 16) * nt
+    pp.close()
+    del pp, us, uns, xs, Fs
+    torch.cuda.empty_cache()
+    # ---- a complete damped Newton solve (reference's first time step, from u = 0) one level coarser ------------------
+    mesh2, part2, pp2, setup2 = build(refine - 1)
+    nv2 = mesh2.x.shape[0]
+    ub = np.ones((nv2, 9)); ub[:, 8] = 0.0
+    u0, un0 = pp2.from_global(ub * 0.0), pp2.from_global(ub)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = pp2.newton(u0, un0, maxit=50, lin_rtol=1e-6, lin_restart=100, lin_maxit=3000)
+    e1.record()
+    barrier()
+    ms_newton = tmax(e0.elapsed_time(e1))
+    pp2.close()
+    return {"workload": f"config5: L_10_R_5 red-refined x{refine} (aspect of L_100_R_50), {nv} vertices, {nt} tets, "
+                        f"{9 * nv} DOFs, Jacobian {8 * 81 * nb_tot / 1e9:.2f} GB, z-slab partition over {world} GPUs",
+            "setup_s": setup_s, "assemble_ms": ms_asm, "assemble_GBs_aggregate": b_asm / ms_asm / 1e6,
+            "spmv_incl_halo_ms": ms_spmv, "spmv_local_kernel_ms": ms_spmv_local,
+            "spmv_GBs_aggregate": b_spmv / ms_spmv / 1e6,
+            "spmv_frac_of_hbm_peak_per_gpu": b_spmv / ms_spmv / 1e6 / (peak * world),
+            "halo_bytes_per_spmv_total": int(halo_tot), "ghost_vertices_total": int(ghost_tot),
+            "gmres_ms_per_iteration": ms_gmres, "gmres_krylov_dim": 30,
+            "newton_solve": {"mesh": f"x{refine - 1}: {9 * nv2} DOFs", "converged": bool(out["converged"]),
+                             "newton_iterations": int(out["iters"]), "gmres_iterations": int(out["lin_iters"]),
+                             "r0": out["r0"], "r": out["r"], "ms": ms_newton, "setup_s": setup2,
+                             "setting": "reference's first time step from u = 0 (3D:782-799): relaxation 0.9, residual "
+                                        "criterion 1e-4, GMRES(100) to 1e-6, block-Jacobi + distributed 16-slab coarse space"}}
 
 
 def bench_config1(dev):
@@ -611,6 +726,7 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     pore3d = bench_pore3d(local, world, dev, args.pore3d_batch, peak) if args.pore3d_batch > 0 else None
     config1 = bench_config1(dev) if (rank == 0 and not args.no_config1) else None
+    mesh5 = bench_mesh5(local, world, rank, dev, args.mesh5_refine, peak) if (world > 1 and args.mesh5_refine > 0) else None
 
     rc = 0
     if rank == 0:
@@ -676,6 +792,8 @@ def main():
             line["config1"] = config1
         if pore3d is not None:
             line["pore3d"] = pore3d
+        if mesh5 is not None:
+            line["mesh5"] = mesh5
         if pool is not None:
             res, wall = pool.solve(sample, args.dv, args.xtol_path, want_u=True, xtol=args.xtol)
             line["cpu_baseline"] = cpu_summary(res, wall, pool.cores, len(sample),

@@ -39,6 +39,18 @@ class NewtonOpts(C.Structure):
         return o
 
     @classmethod
+    def sweep_3d_inexact(cls, eta: float = 1e-4):
+        """sweep_3d with a constant forcing term: GMRES stops at ||J dx - F|| <= eta ||F||.  The damped iteration of
+        the reference (relaxation 0.9, 3D:796) contracts the error by 0.1 per iteration whatever the accuracy of the
+        linear solve beyond ~1e-2, so the Newton counts do not change while GMRES needs about a third of the
+        iterations (profiles/r01_inexact_newton_cpu_study.md; GPU-measured distance to the 1e-8 iterate:
+        tests/test_gpu_3d.py::test_inexact_linear_solves_same_march, bench.py -> pore3d.inexact).  A throughput
+        setting for sweeps, not the parity path."""
+        o = cls.sweep_3d()
+        o.lin_rtol = eta
+        return o
+
+    @classmethod
     def steady(cls, xtol=1e-12, maxit=50, relax=1.0, xtol_path=0.0, jac_rule=0, xtol_floor=0.0):
         return cls(1e-4, 1e-4, relax, xtol, maxit, 1, 1, 2000, 100, 1e-12, xtol_path, jac_rule, 0, xtol_floor)
 
