@@ -1,5 +1,9 @@
-// 1D planar EDL: fused P1 assembly + block-tridiagonal (7x7) Thomas elimination + Newton,
-// one 8-lane group per problem, whole Newton / time-march / continuation loop device-resident.
+// 1D planar EDL: fused P1 assembly + block-tridiagonal (7x7) Thomas elimination + Newton, whole Newton /
+// time-march / continuation loop device-resident.  A problem is handled by FOUR 8-lane groups: two-sided
+// ("twisted") elimination -- top half downwards, bottom half upwards -- and, per half, a PRODUCER group that
+// integrates the cells and assembles block row k+1 while the CONSUMER group eliminates block row k
+// (warp-specialised: producers and consumers live in different warps of the CTA and hand block rows over through a
+// three-slot shared-memory queue guarded by named barriers).
 //
 // Replaces the FEniCS work behind `solve(F + J_OH*v_OH*ds + J_H*v_H*ds == 0, u, bcs)`
 // (1D/MPNP_CO2ER_EDL.py:737-742): FFC element kernels for the forms 1D:381-595, dolfin's
@@ -20,12 +24,21 @@ namespace edl1d {
 constexpr int NS = 6;
 constexpr int NC = 7;
 // Shared memory of newton1d_kernel, per 8-lane group (doubles):
-constexpr int SM_A = 0;       // sub-diagonal block A_k = block (1,0) of the cell behind, row-major, double-buffered [2][7][8]
-constexpr int SM_B = 112;     // block (1,1) of the cell behind, [i*8+c], double-buffered [2][7][8]
-constexpr int SM_M = 224;     // residual rows of the current node [8]
-constexpr int SM_X = 232;     // back-substitution: solution of the neighbour row, double-buffered [2][8]
-constexpr int SM_PC = 248;    // Gauss-Jordan: pivot column broadcast, double-buffered [2][8]
-constexpr int SM_GROUP = 264; // doubles per group (== 8 mod 16: the two groups of a half-warp use disjoint banks)
+// Block-row queue between a producer group and its consumer group: NSLOT slots of
+//   A[7][8] (sub-diagonal block = block (1,0) of the cell behind, row-major: A[i*8+c]), B[7][8] (diagonal block),
+//   C[7][8] (coupling block ahead; column 7 of row 0 carries the half's residual sum of squares in the closing slot),
+//   d[8] (right-hand side = residual rows of the node)
+// Slot r % NSLOT carries block row r; while integrating the cell ahead of row r the producer already deposits that
+// cell's (1,0)/(1,1) blocks in slot (r+1) % NSLOT, so three slots keep producer and consumer one row apart.
+constexpr int NSLOT = 3;
+constexpr int Q_A = 0, Q_B = 56, Q_C = 112, Q_D = 168, Q_SLOT = 176;
+constexpr int SM_Q = 0;                     // [NSLOT][Q_SLOT]
+constexpr int SM_M = NSLOT * Q_SLOT;        // producer: residual rows of the current node [8]
+constexpr int SM_X = SM_M + 8;              // consumer, back-substitution: solution of the neighbour row, double-buffered [2][8]
+constexpr int SM_PC = SM_X + 16;            // consumer, Gauss-Jordan: pivot column broadcast, double-buffered [2][8]
+constexpr int SM_GROUP = SM_PC + 16 + 16;   // doubles per group (== 8 mod 16: the two groups of a half-warp use
+                                            // disjoint banks)
+static_assert(SM_GROUP % 16 == 8, "bank layout");
 // plus, per pair of groups (= problem): the parameter record [64]; the merge area of a pair aliases the
 // staging ring of its bottom-half group (idle between the two sweeps).
 // Shared memory of assemble1d_kernel, per group: params [64], staged nodal values [2][8], residual rows [8]
@@ -41,8 +54,20 @@ constexpr int AS_P = 0, AS_U = 64, AS_M = 80, AS_GROUP = 88;
 #endif
 constexpr int RING = GMPNP_RING;
 constexpr int SM_RING = RING * 72 + 8;  // doubles per group (== 8 mod 16, see SM_GROUP)
-constexpr int GROUPS_PER_BLOCK = 16;
+constexpr int GROUPS_PER_BLOCK = 16;    // assemble1d_kernel: one group per (problem, node)
 constexpr int THREADS = GROUPS_PER_BLOCK * 8;
+// newton1d_kernel: 4 warps = 2 consumer (master) warps + 2 producer warps; a warp holds 2 problems x 2 halves
+constexpr int NW_PAIRS = 2;                       // consumer/producer warp pairs per CTA
+constexpr int NW_THREADS = NW_PAIRS * 2 * 32;
+constexpr int NW_GROUPS = NW_PAIRS * 4;           // (problem, half) slots per CTA
+constexpr int NW_PROBLEMS = NW_PAIRS * 2;
+// named barriers (id 0 is __syncthreads): per warp pair full[NSLOT], empty[NSLOT], command
+constexpr int BAR_PER_PAIR = 2 * NSLOT + 1;
+static_assert(1 + NW_PAIRS * BAR_PER_PAIR <= 16, "named barriers");
+constexpr int CMD_FACTOR = 1, CMD_EXIT = 2;
+
+__device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 
 // 3-point and 2-point Gauss-Legendre on [0,1] (FFC: degree 4 -> 3 points for J, degree 3 ->
 // 2 points for F)
@@ -303,6 +328,8 @@ struct Group {
     unsigned pmask;   // participation mask of the pair
     int pbase;        // first lane of the pair
     double* psm;      // pair-shared merge area [8][8]
+    double* q;        // block-row queue shared by the producer group and its consumer group [NSLOT][Q_SLOT]
+    int bar;          // first named barrier of this warp pair: full[s] = bar + s, empty[s] = bar + NSLOT + s, command = bar + 2 NSLOT
 };
 
 // publish this lane's component of a node (already in a register) in sU[slot] and give every lane
@@ -396,20 +423,18 @@ __device__ __forceinline__ void eliminate_row(const Group& g, const double* __re
     }
 }
 
-// One elimination sweep over `rows` block rows starting at node `first` and moving in direction `dir`
-// (+1: top half, downwards; -1: bottom half, upwards -- a twisted / "burn at both ends" factorisation, so the
-// two halves of a problem are eliminated concurrently by the two groups of a pair).  Row by row: assemble just
-// in time from the cell behind and the cell ahead (in sweep order), eliminate, store (coupling' | rhs') in
-// ws[node].  The cell ahead always exists because each half stops short of the other end of the domain.
-// A cell is integrated in the sweep's own orientation (local node 0 = current node): the forms only contain
-// products of two gradients, so they are invariant under the reflection.
-// Returns this half's sum of squares of the residual (valid in every lane of the group); X returns the last
-// row's eliminated block column (lanes<7) / rhs (lane 7).
-template <bool PIVOT, int NQJ>
-__device__ double forward_sweep(const Group& g, const LaneConst& L, const double* __restrict__ x, int n,
-                                int first, int dir, int rows, const double* __restrict__ up,
-                                const double* __restrict__ unp, double* __restrict__ ws, double (&X)[NC],
-                                int& singular, double& f1_last) {
+// PRODUCER side of one elimination sweep over `rows` block rows starting at node `first` and moving in direction
+// `dir` (+1: top half, downwards; -1: bottom half, upwards -- a twisted / "burn at both ends" factorisation, so the
+// two halves of a problem are eliminated concurrently).  Row by row: integrate the cell ahead (in sweep order), form
+// block row k = (A | B | C | d) from the cell behind and the cell ahead, apply boundary rows, hand it to the consumer
+// group through queue slot r % NSLOT.  The cell ahead always exists because each half stops short of the other end of
+// the domain.  A cell is integrated in the sweep's own orientation (local node 0 = current node): the forms only
+// contain products of two gradients, so they are invariant under the reflection.
+// After the last row a closing slot carries what the merge needs: the (1,0)/(1,1) blocks and the residual row of the
+// last cell, and this half's sum of squares of the residual.
+template <int NQJ>
+__device__ void producer_sweep(const Group& g, const LaneConst& L, const double* __restrict__ x, int n, int first,
+                               int dir, int rows, const double* __restrict__ up, const double* __restrict__ unp) {
     const double* P = g.P;
     const int c = g.c;
     double* sF = g.sm + SM_M;                        // residual rows of the current node, gathered for lane 7
@@ -438,20 +463,17 @@ __device__ double forward_sweep(const Group& g, const LaneConst& L, const double
 #pragma unroll
     for (int j = 0; j < RING; ++j) issue(j);
     double f1_behind = 0.0;       // cell behind: this lane's residual row at the shared node
-#pragma unroll
-    for (int i = 0; i < NC; ++i) X[i] = 0.0;
     double rsq = 0.0;
+    int slot = 0;
     for (int r = 0; r < rows; ++r) {
         const int k = first + dir * r;               // current node
         const int s0 = (r & (RING - 1)) * 8, s1 = ((r + 1) & (RING - 1)) * 8;
-        // blocks (1,0) / (1,1) of a cell are produced one row before they are used: double-buffered in shared memory
-        double* sA_cur = g.sm + SM_A + (r & 1) * 56;
-        double* sA_nxt = g.sm + SM_A + ((r + 1) & 1) * 56;
-        double* sB_cur = g.sm + SM_B + (r & 1) * 56;
-        double* sB_nxt = g.sm + SM_B + ((r + 1) & 1) * 56;
+        const int nslot = (slot + 1 == NSLOT) ? 0 : slot + 1;
+        double* qs = g.q + slot * Q_SLOT;            // block row r
+        double* qn = g.q + nslot * Q_SLOT;           // receives the (1,0)/(1,1) blocks of the cell ahead (for row r+1)
+        if (r >= 2) bar_sync(g.bar + NSLOT + nslot); // the consumer is done with row r-2, which lived in slot nslot
         cp_async_wait<RING - 2>();                   // node r+1 has landed (groups 0 .. r+RING-1 are in flight)
         __syncwarp();
-        double B[NC], Y[NC];
         {
             // nodal values of the cell ahead (local node 0 = current node) straight from the staging ring
             double U0[NC], U1[NC];
@@ -467,49 +489,85 @@ __device__ double forward_sweep(const Group& g, const LaneConst& L, const double
             const double myU0 = fu[s0 + c], myU1 = fu[s1 + c];          // lane 7 reads the constant 1.0
             const double myN0 = (c < NC && use_un) ? fn[s0 + c] : 0.0, myN1 = (c < NC && use_un) ? fn[s1 + c] : 0.0;
             CellCols cc;
-            cell_columns<NQJ, true>(P, fu + s0, fu + s1, L, c, h, prow, U0, U1, myU0, myU1, myN0, myN1, cc, sA_nxt, sB_nxt);
-            // ---- row k: A = (1,0) behind, B = (1,1) behind + c00, coupling ahead = c01, d = F1behind + F0 ----
+            cell_columns<NQJ, true>(P, fu + s0, fu + s1, L, c, h, prow, U0, U1, myU0, myU1, myN0, myN1, cc, qn + Q_A, qn + Q_B);
+            // ---- row k: A = (1,0) behind (already in the slot), B = (1,1) behind + c00, coupling ahead = c01 ----
+            const bool dir_all = (r == 0 && k == n - 1);     // Dirichlet node x = 1: all components (1D:350-353)
+            const bool dir_pot = (r == 0 && k == 0);         // OHP: potential = V (1D:354)
 #pragma unroll
-            for (int i = 0; i < NC; ++i) { B[i] = cc.c00[i]; Y[i] = cc.c01[i]; }
+            for (int i = 0; i < NC; ++i) {
+                double bv = cc.c00[i] + ((r > 0) ? qs[Q_B + i * 8 + c] : 0.0);
+                double cv = cc.c01[i];
+                if (dir_all || (dir_pot && i == NS)) { bv = (i == c) ? 1.0 : 0.0; cv = 0.0; }
+                qs[Q_B + i * 8 + c] = bv;
+                qs[Q_C + i * 8 + c] = cv;
+            }
             sF[c] = f1_behind + cc.f0;               // this lane's residual row of node k
             f1_behind = cc.f1;
         }
-        if (r > 0) {
-#pragma unroll
-            for (int i = 0; i < NC; ++i) B[i] += sB_cur[i * 8 + c];
-        }
         __syncwarp();
         if (c == 7) {
+            double Y[NC];
 #pragma unroll
-            for (int i = 0; i < NC; ++i) Y[i] = sF[i];      // lane 7: rhs lives in Y
+            for (int i = 0; i < NC; ++i) Y[i] = sF[i];
             // point fluxes `J_i v_i ds` at both end points (1D:553, 738)
             if (r == 0) {
 #pragma unroll
                 for (int i = 0; i < NS; ++i) Y[i] += P[GMPNP_P_JFLUX + i];
             }
-        }
-        // Dirichlet rows (1D:350-355): x=1 all components = (1,..,1,0); x=0 potential = V.  Only the first row
-        // of a half is a boundary node (the halves start at nodes 0 and n-1).
-        if (r == 0 && k == n - 1) {
+            // Dirichlet rows (1D:350-355): x=1 all components = (1,..,1,0); x=0 potential = V.  Only the first row
+            // of a half is a boundary node (the halves start at nodes 0 and n-1).
+            if (r == 0 && k == n - 1) {
 #pragma unroll
-            for (int i = 0; i < NC; ++i) {
-                if (c < NC) { B[i] = (i == c) ? 1.0 : 0.0; Y[i] = 0.0; }
-                else Y[i] = fu[s0 + i] - ((i < NS) ? 1.0 : 0.0);
+                for (int i = 0; i < NC; ++i) Y[i] = fu[s0 + i] - ((i < NS) ? 1.0 : 0.0);
             }
-        }
-        if (r == 0 && k == 0) {
-            if (c < NC) { B[NS] = (c == NS) ? 1.0 : 0.0; Y[NS] = 0.0; }
-            else Y[NS] = fu[s0 + NS] - P[GMPNP_P_V];
-        }
-        if (c == 7) {
+            if (r == 0 && k == 0) Y[NS] = fu[s0 + NS] - P[GMPNP_P_V];
             // ||b||_2 of the reference's (unscaled) system: undo the Poisson-row scaling except on Dirichlet rows
 #pragma unroll
             for (int i = 0; i < NS; ++i) rsq += Y[i] * Y[i];
             const double yp = (r == 0) ? Y[NS] : Y[NS] * qscale;
             rsq += yp * yp;
+#pragma unroll
+            for (int i = 0; i < NC; ++i) qs[Q_D + i] = Y[i];
         }
-        issue(r + RING);                             // slot of node r is free: every lane is past its last read of it
-        eliminate_row<PIVOT>(g, r > 0 ? sA_cur : nullptr, B, Y, X, singular);
+        __syncwarp();                                // every lane is past its last read of ring slot r
+        issue(r + RING);
+        bar_arrive(g.bar + slot);                    // block row r is complete (each lane after its own writes)
+        slot = nslot;
+    }
+    // drain the staging ring first: the merge area of a pair aliases the ring of its bottom-half group
+    cp_async_wait<0>();
+    __syncwarp();
+    // closing slot: (1,0)/(1,1) blocks of the last cell are in it already; add its residual row and the half's sum
+    {
+        double* qs = g.q + slot * Q_SLOT;
+        qs[Q_D + c] = f1_behind;
+        if (c == 7) qs[Q_C + 7] = rsq;
+        bar_arrive(g.bar + slot);
+    }
+}
+
+// CONSUMER side of the sweep: takes block row r from queue slot r % NSLOT, eliminates it against the previous row
+// (B' = B - A C'_(k-1), Gauss-Jordan inside the block), stores (coupling'_k | d'_k) in ws[node].  Returns the index of
+// the closing slot (already waited for); X returns the last row's eliminated block column (lanes<7) / rhs (lane 7).
+template <bool PIVOT>
+__device__ int consumer_sweep(const Group& g, int first, int dir, int rows, double* __restrict__ ws, double (&X)[NC],
+                              int& singular) {
+    const int c = g.c;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) X[i] = 0.0;
+    int slot = 0;
+    for (int r = 0; r < rows; ++r) {
+        const int k = first + dir * r;
+        double* qs = g.q + slot * Q_SLOT;
+        bar_sync(g.bar + slot);                      // block row r has been assembled
+        double B[NC], Y[NC];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            B[i] = qs[Q_B + i * 8 + c];
+            Y[i] = (c < NC) ? qs[Q_C + i * 8 + c] : qs[Q_D + i];
+        }
+        eliminate_row<PIVOT>(g, r > 0 ? qs + Q_A : nullptr, B, Y, X, singular);
+        if (r + 2 < rows) bar_arrive(g.bar + NSLOT + slot);      // slot free for the producer's row r+2
         // ---- store (coupling'_k | d'_k) ------------------------------------------------------
         double* w = ws + (long)k * 56;
         if (g.live) {
@@ -518,13 +576,10 @@ __device__ double forward_sweep(const Group& g, const LaneConst& L, const double
         }
 #pragma unroll
         for (int i = 0; i < NC; ++i) X[i] = Y[i];
+        slot = (slot + 1 == NSLOT) ? 0 : slot + 1;
     }
-    f1_last = f1_behind;
-    cp_async_wait<0>();
-    __syncwarp();
-    // broadcast this half's residual sum from lane 7
-    rsq = __shfl_sync(0xffffffffu, rsq, g.base + 7);
-    return rsq;
+    bar_sync(g.bar + slot);                          // closing slot
+    return slot;
 }
 
 // Back substitution x_k = d'_k - coupling'_k x_(k-dir') over `rows` rows starting at node `first`, moving in
@@ -598,16 +653,20 @@ struct NewtonOut { int iters; double r0, r; int status; double dx; };
 // row (I - A'_m C'_{m-1}) x_m = d'_m - A'_m d'_{m-1}.  Odd n: node m is left over and is eliminated in the merge from
 // the blocks both halves stashed for it: (B_m - A_m C'_{m-1} - C_m A'_{m+1}) x_m = d_m - A_m d'_{m-1} - C_m d'_{m+1}.
 // x_m is broadcast to the pair.  Returns ||b||^2 of the whole problem.  Executed by all 32 lanes in lock step.
-template <bool PIVOT, int NQJ>
-__device__ double factor_problem(const Group& g, const LaneConst& L, const double* x, int n, const double* up,
-                                 const double* unp, double* ws, double (&xm)[NC], int& singular) {
+template <bool PIVOT>
+__device__ double factor_problem(const Group& g, int n, double* ws, double (&xm)[NC], int& singular, int* cmd) {
     const int m = n >> 1;
     const bool odd = (n & 1) != 0;
     const int c = g.c;
     double X[NC];
     const int first = g.half ? n - 1 : 0, dir = g.half ? -1 : 1;
-    double f1_last;
-    double rsq = forward_sweep<PIVOT, NQJ>(g, L, x, n, first, dir, m, up, unp, ws, X, singular, f1_last);
+    // wake the producer warp: it assembles the m block rows of both halves of the warp's two problems
+    if ((threadIdx.x & 31) == 0) *cmd = CMD_FACTOR;
+    bar_sync(g.bar + 2 * NSLOT);
+    const int cslot = consumer_sweep<PIVOT>(g, first, dir, m, ws, X, singular);
+    const double* qc = g.q + cslot * Q_SLOT;         // closing slot of this half
+    double rsq = qc[Q_C + 7];
+    const double f1_last = qc[Q_D + c];
     double Y[NC];
 #pragma unroll
     for (int i = 0; i < NC; ++i) Y[i] = 0.0;
@@ -630,18 +689,15 @@ __device__ double factor_problem(const Group& g, const LaneConst& L, const doubl
         if (!g.half) singular |= sing_m;
     } else {
         // each half: its part of row m = (block (1,1) | residual row) of its last cell minus (block (1,0)) * X
-        const double* sA_last = g.sm + SM_A + (m & 1) * 56;
-        const double* sB_last = g.sm + SM_B + (m & 1) * 56;
-        double* sF = g.sm + SM_M;
-        sF[c] = f1_last;
-        __syncwarp();
+        const double* sA_last = qc + Q_A;
+        const double* sB_last = qc + Q_B;
         double part[NC];
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
             const double2* row = reinterpret_cast<const double2*>(sA_last + i * 8);
             const double2 a0 = row[0], a1 = row[1], a2 = row[2], a3 = row[3];
             const double t = a0.x * X[0] + a0.y * X[1] + a1.x * X[2] + a1.y * X[3] + a2.x * X[4] + a2.y * X[5] + a3.x * X[6];
-            part[i] = ((c < NC) ? sB_last[i * 8 + c] : sF[i]) - t;
+            part[i] = ((c < NC) ? sB_last[i * 8 + c] : qc[Q_D + i]) - t;
         }
         if (g.half) {
 #pragma unroll
@@ -661,7 +717,7 @@ __device__ double factor_problem(const Group& g, const LaneConst& L, const doubl
             const double qscale = g.P[GMPNP_P_Q];
 #pragma unroll
             for (int i = 0; i < NC; ++i) {
-                double d = sF[i] + g.psm[56 + i];
+                double d = qc[Q_D + i] + g.psm[56 + i];
                 if (i == NS) d *= qscale;
                 rsq += d * d;
             }
@@ -712,13 +768,13 @@ __device__ void solve_problem(const Group& g, int n, const double (&xm)[NC], dou
 // store its u.  This costs nothing (the warp occupies its slot until its slower pair finishes anyway) and lets
 // every barrier and shuffle of the sweeps use the full-warp mask: the runtime 8-lane masks expanded to a
 // MATCH/VOTE sequence of six instructions per barrier, eleven barriers per block row.
-template <bool PIVOT, int NQJ>
-__device__ NewtonOut newton_solve(const Group& g, const LaneConst& L, const double* x, int n, double* up,
-                                  const double* unp, double* ws, const gmpnp_newton_opts& o, bool enabled) {
+template <bool PIVOT>
+__device__ NewtonOut newton_solve(const Group& g, int n, double* up, double* ws, const gmpnp_newton_opts& o,
+                                  bool enabled, int* cmd) {
     NewtonOut out;
     int singular = 0;
     double xm[NC];
-    double rsq = factor_problem<PIVOT, NQJ>(g, L, x, n, up, unp, ws, xm, singular);
+    double rsq = factor_problem<PIVOT>(g, n, ws, xm, singular, cmd);
     double r = sqrt(rsq);
     out.r0 = r;
     int k = 0;
@@ -749,7 +805,7 @@ __device__ NewtonOut newton_solve(const Group& g, const LaneConst& L, const doub
         if (!__any_sync(0xffffffffu, still)) break;   // nobody needs the re-assembly (increment stop / failure)
         __syncwarp();               // the other half's u updates must be visible before re-assembly
         int sing2 = 0;
-        const double rsq2 = factor_problem<PIVOT, NQJ>(g, L, x, n, up, unp, ws, xm, sing2);
+        const double rsq2 = factor_problem<PIVOT>(g, n, ws, xm, sing2, cmd);
         if (still) {
             r = sqrt(rsq2);
             if (!isfinite(r) || sing2) bad = true;
@@ -764,23 +820,31 @@ __device__ NewtonOut newton_solve(const Group& g, const LaneConst& L, const doub
     return out;
 }
 
-constexpr int PROBLEMS_PER_BLOCK = GROUPS_PER_BLOCK / 2;
+constexpr int PROBLEMS_PER_BLOCK = NW_PROBLEMS;
+constexpr size_t NEWTON_SMEM_DOUBLES = (size_t)NW_GROUPS * (SM_GROUP + SM_RING) + NW_PROBLEMS * GMPNP_NPAR + 8;
 
-__device__ __forceinline__ void group_setup(Group& g, int batch, int& prob, double* smem) {
-    const int lane = threadIdx.x & 31;
+// roles: warps [0, NW_PAIRS) are consumers (and run the Newton / march / continuation control), warp NW_PAIRS + w is
+// the producer of consumer warp w.  A lane and its twin in the partner warp handle the same (problem, half).
+__device__ __forceinline__ void group_setup(Group& g, int batch, int& prob, double* smem, bool& producer, int*& cmd) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    producer = warp >= NW_PAIRS;
+    const int wp = producer ? warp - NW_PAIRS : warp;          // warp pair
     g.c = lane & 7;
     g.base = lane & ~7;
     g.mask = 0xFFu << g.base;
     g.half = (lane >> 3) & 1;
     g.pbase = lane & ~15;
     g.pmask = 0xFFFFu << g.pbase;
-    const int gid = threadIdx.x >> 3;
+    const int gid = wp * 4 + (lane >> 3);                      // (problem, half) slot of the CTA
     g.sm = smem + gid * SM_GROUP;
-    g.ring = smem + GROUPS_PER_BLOCK * SM_GROUP + gid * SM_RING;
-    g.psm = smem + GROUPS_PER_BLOCK * SM_GROUP + (gid | 1) * SM_RING;      // ring of the pair's bottom-half group
-    g.P = smem + GROUPS_PER_BLOCK * (SM_GROUP + SM_RING) + (gid >> 1) * GMPNP_NPAR;
+    g.q = g.sm + SM_Q;
+    g.ring = smem + NW_GROUPS * SM_GROUP + gid * SM_RING;
+    g.psm = smem + NW_GROUPS * SM_GROUP + (gid | 1) * SM_RING;         // ring of the pair's bottom-half group
+    g.P = smem + NW_GROUPS * (SM_GROUP + SM_RING) + (gid >> 1) * GMPNP_NPAR;
     g.su = nullptr;
-    prob = blockIdx.x * PROBLEMS_PER_BLOCK + (threadIdx.x >> 4);
+    g.bar = 1 + wp * BAR_PER_PAIR;
+    cmd = reinterpret_cast<int*>(smem + NW_GROUPS * (SM_GROUP + SM_RING) + NW_PROBLEMS * GMPNP_NPAR) + wp;
+    prob = blockIdx.x * PROBLEMS_PER_BLOCK + wp * 2 + (lane >> 4);
     // padding pairs of the last CTA shadow the last problem (valid memory to read) but never store
     g.live = prob < batch;
     if (!g.live) prob = batch - 1;
@@ -796,12 +860,13 @@ __device__ __forceinline__ void load_params(const Group& g, const double* __rest
 // mode 0: single Newton solve (gmpnp_newton_1d)
 // mode 1: pseudo-time march  (gmpnp_march_1d): n_stage steps, H_OHP controller, u_n <- u
 // mode 2: steady continuation (gmpnp_steady_continuation_1d): kappa = 0, V from Vpath
-// Control flow is warp-uniform (see newton_solve): per-pair outcomes are flags, never early exits.
+// Control flow of the consumer warps is warp-uniform (see newton_solve): per-pair outcomes are flags, never early
+// exits; the producer warps only execute commands.
 #ifndef GMPNP_NEWTON_MIN_BLOCKS
 #define GMPNP_NEWTON_MIN_BLOCKS 3
 #endif
 template <bool PIVOT, int NQJ>
-__global__ void __launch_bounds__(THREADS, GMPNP_NEWTON_MIN_BLOCKS)
+__global__ void __launch_bounds__(NW_THREADS, GMPNP_NEWTON_MIN_BLOCKS)
 newton1d_kernel(int mode, int batch, int n, const double* __restrict__ x, const double* __restrict__ params,
                 double* __restrict__ u, double* __restrict__ un_rw, const double* __restrict__ un_ro,
                 double* __restrict__ wsall, gmpnp_newton_opts opts, int n_stage,
@@ -809,25 +874,45 @@ newton1d_kernel(int mode, int batch, int n, const double* __restrict__ x, const 
                 double* __restrict__ r0out, double* __restrict__ rout, double* __restrict__ hfrac_out,
                 int* __restrict__ stage_out, int* __restrict__ status) {
     extern __shared__ double smem[];
-    Group g; int prob;
-    group_setup(g, batch, prob, smem);
+    Group g; int prob; bool producer; int* cmd;
+    group_setup(g, batch, prob, smem, producer, cmd);
+    double* up = u + (long)prob * n * NC;
+    if (producer) {
+        // ---- producer warp: wait for a command, assemble the block rows of one factorisation sweep ------------------
+        // (the parameter record in shared memory is loaded and updated by the consumer warp; the command barrier
+        // orders those writes, and the consumer's updates of u, before the reads below)
+        const double* unp = (mode == 0) ? un_ro + (long)prob * n * NC : (mode == 1) ? un_rw + (long)prob * n * NC : up;
+        const int m = n >> 1;
+        const int first = g.half ? n - 1 : 0, dir = g.half ? -1 : 1;
+        LaneConst L;
+        bool have_L = false;
+        while (true) {
+            bar_sync(g.bar + 2 * NSLOT);
+            if (*cmd == CMD_EXIT) break;
+            if (!have_L) { lane_consts(g.P, g.c, L); have_L = true; }     // rate constants do not change during a launch
+            producer_sweep<NQJ>(g, L, x, n, first, dir, m, up, unp);
+        }
+        return;
+    }
+    // ---- consumer warp: control + elimination + back substitution ---------------------------------------------------
     load_params(g, params, prob);
     double* P = const_cast<double*>(g.P);
-    double* up = u + (long)prob * n * NC;
     double* ws = wsall + (long)prob * n * 56;
-    LaneConst L;
-    lane_consts(P, g.c, L);
     const bool writer = (g.c == 0 && g.half == 0 && g.live);
     const int lane16 = (threadIdx.x & 15);
+    auto finish = [&]() {
+        if ((threadIdx.x & 31) == 0) *cmd = CMD_EXIT;
+        bar_sync(g.bar + 2 * NSLOT);
+    };
     if (mode == 0) {
-        const double* unp = un_ro + (long)prob * n * NC;
-        NewtonOut o = newton_solve<PIVOT, NQJ>(g, L, x, n, up, unp, ws, opts, g.live);
+        NewtonOut o = newton_solve<PIVOT>(g, n, up, ws, opts, g.live, cmd);
         if (writer) {
             if (iters) iters[prob] = o.iters;
             if (r0out) r0out[prob] = o.r0;
             if (rout) rout[prob] = o.r;
             if (status) status[prob] = o.status;
         }
+        finish();
         return;
     }
     if (mode == 1) {
@@ -838,7 +923,7 @@ newton1d_kernel(int mode, int batch, int n, const double* __restrict__ x, const 
         bool alive = g.live;
         for (int s = 0; s < n_stage; ++s) {
             if (!__any_sync(0xffffffffu, alive)) break;
-            NewtonOut o = newton_solve<PIVOT, NQJ>(g, L, x, n, up, unp, ws, opts, alive);
+            NewtonOut o = newton_solve<PIVOT>(g, n, up, ws, opts, alive, cmd);
             if (alive) {
                 if (writer && iters) iters[(long)prob * n_stage + s] = o.iters;
                 if (o.status != GMPNP_CONVERGED) { st = o.status; alive = false; }
@@ -875,6 +960,7 @@ newton1d_kernel(int mode, int batch, int n, const double* __restrict__ x, const 
             if (hfrac_out) hfrac_out[prob] = frac;
             if (stage_out) stage_out[prob] = done;
         }
+        finish();
         return;
     }
     // mode 2: steady continuation
@@ -894,8 +980,7 @@ newton1d_kernel(int mode, int batch, int n, const double* __restrict__ x, const 
             __syncwarp();
             if (writer && alive) P[GMPNP_P_V] = Vs;
             __syncwarp();
-            // kappa = 0: u_n is never read for its value; pass u itself
-            NewtonOut o = newton_solve<PIVOT, NQJ>(g, L, x, n, up, up, ws, o2, alive);
+            NewtonOut o = newton_solve<PIVOT>(g, n, up, ws, o2, alive, cmd);
             if (alive) {
                 if (writer && iters) iters[(long)prob * n_stage + s] = o.iters;
                 if (writer && rout) rout[prob] = o.r;
@@ -910,6 +995,7 @@ newton1d_kernel(int mode, int batch, int n, const double* __restrict__ x, const 
             if (status) status[prob] = st;
             if (stage_out) stage_out[prob] = done;
         }
+        finish();
     }
 }
 
@@ -1048,7 +1134,7 @@ static cudaError_t launch_newton_variant(gmpnp_handle* h, int blocks, size_t sme
     using namespace edl1d;
     cudaError_t e = cudaFuncSetAttribute(newton1d_kernel<PIV, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    newton1d_kernel<PIV, NQ><<<blocks, THREADS, smem, st>>>(mode, h->batch, h->n_nodes, h->d_x, h->d_params, d_u, d_un_rw,
+    newton1d_kernel<PIV, NQ><<<blocks, NW_THREADS, smem, st>>>(mode, h->batch, h->n_nodes, h->d_x, h->d_params, d_u, d_un_rw,
         d_un_ro, h->d_ws, *opts, n_stage, d_Vpath, d_hist, d_iters, d_r0, d_r, d_hfrac, d_stage, d_status);
     return cudaGetLastError();
 }
@@ -1059,7 +1145,7 @@ int edl1d_launch_newton(gmpnp_handle* h, int mode, double* d_u, double* d_un_rw,
                         int* d_status, cudaStream_t st) {
     using namespace edl1d;
     const int blocks = (h->batch + PROBLEMS_PER_BLOCK - 1) / PROBLEMS_PER_BLOCK;
-    const size_t smem = (size_t)(GROUPS_PER_BLOCK * (SM_GROUP + SM_RING) + PROBLEMS_PER_BLOCK * GMPNP_NPAR) * sizeof(double);
+    const size_t smem = NEWTON_SMEM_DOUBLES * sizeof(double);
     const bool consistent = (opts->jac_rule == 1);
     cudaError_t e;
 #define GMPNP_ARGS h, blocks, smem, mode, d_u, d_un_rw, d_un_ro, opts, n_stage, d_Vpath, d_hist, d_iters, d_r0, d_r, d_hfrac, d_stage, d_status, st
