@@ -6,7 +6,17 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <nvtx3/nvToolsExt.h>
 #include "../../include/gmpnp.h"
+
+// NVTX range of one library phase (assemble / preconditioner / linear solve / Newton / march step): shows up on an
+// Nsight Systems timeline, costs a few nanoseconds when no tool is attached (header-only NVTX3, no extra library).
+struct GmpnpRange {
+    explicit GmpnpRange(const char* name) { nvtxRangePushA(name); }
+    ~GmpnpRange() { nvtxRangePop(); }
+    GmpnpRange(const GmpnpRange&) = delete;
+    GmpnpRange& operator=(const GmpnpRange&) = delete;
+};
 
 #define GMPNP_CUDA_TRY(h, expr)                                              \
     do {                                                                     \

@@ -25,18 +25,19 @@ constexpr int NS = 6;
 constexpr int NC = 7;
 // Shared memory of newton1d_kernel, per 8-lane group (doubles):
 // Block-row queue between a producer group and its consumer group: NSLOT slots of
-//   A[7][8] (sub-diagonal block = block (1,0) of the cell behind, row-major: A[i*8+c]), B[7][8] (diagonal block),
-//   C[7][8] (coupling block ahead; column 7 of row 0 carries the half's residual sum of squares in the closing slot),
-//   d[8] (right-hand side = residual rows of the node)
+//   A[7][8] (sub-diagonal block = block (1,0) of the cell behind, row-major: A[i*8+c]; its unused column 7 carries
+//   the right-hand side d[i] = residual row i of the node), B[7][8] (diagonal block), C[7][8] (coupling block ahead;
+//   column 7 of row 0 carries the half's residual sum of squares in the closing slot)
 // Slot r % NSLOT carries block row r; while integrating the cell ahead of row r the producer already deposits that
 // cell's (1,0)/(1,1) blocks in slot (r+1) % NSLOT, so three slots keep producer and consumer one row apart.
 constexpr int NSLOT = 3;
-constexpr int Q_A = 0, Q_B = 56, Q_C = 112, Q_D = 168, Q_SLOT = 176;
+constexpr int Q_A = 0, Q_B = 56, Q_C = 112, Q_SLOT = 168;
+__device__ __forceinline__ constexpr int Q_D(int i) { return Q_A + i * 8 + 7; }      // d[i] rides in column 7 of A
 constexpr int SM_Q = 0;                     // [NSLOT][Q_SLOT]
 constexpr int SM_M = NSLOT * Q_SLOT;        // producer: residual rows of the current node [8]
 constexpr int SM_X = SM_M + 8;              // consumer, back-substitution: solution of the neighbour row, double-buffered [2][8]
 constexpr int SM_PC = SM_X + 16;            // consumer, Gauss-Jordan: pivot column broadcast, double-buffered [2][8]
-constexpr int SM_GROUP = SM_PC + 16 + 16;   // doubles per group (== 8 mod 16: the two groups of a half-warp use
+constexpr int SM_GROUP = SM_PC + 16 + 8;    // doubles per group (== 8 mod 16: the two groups of a half-warp use
                                             // disjoint banks)
 static_assert(SM_GROUP % 16 == 8, "bank layout");
 // plus, per pair of groups (= problem): the parameter record [64]; the merge area of a pair aliases the
@@ -527,7 +528,7 @@ __device__ void producer_sweep(const Group& g, const LaneConst& L, const double*
             const double yp = (r == 0) ? Y[NS] : Y[NS] * qscale;
             rsq += yp * yp;
 #pragma unroll
-            for (int i = 0; i < NC; ++i) qs[Q_D + i] = Y[i];
+            for (int i = 0; i < NC; ++i) qs[Q_D(i)] = Y[i];
         }
         __syncwarp();                                // every lane is past its last read of ring slot r
         issue(r + RING);
@@ -540,7 +541,7 @@ __device__ void producer_sweep(const Group& g, const LaneConst& L, const double*
     // closing slot: (1,0)/(1,1) blocks of the last cell are in it already; add its residual row and the half's sum
     {
         double* qs = g.q + slot * Q_SLOT;
-        qs[Q_D + c] = f1_behind;
+        if (c < NC) qs[Q_D(c)] = f1_behind;
         if (c == 7) qs[Q_C + 7] = rsq;
         bar_arrive(g.bar + slot);
     }
@@ -564,7 +565,7 @@ __device__ int consumer_sweep(const Group& g, int first, int dir, int rows, doub
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
             B[i] = qs[Q_B + i * 8 + c];
-            Y[i] = (c < NC) ? qs[Q_C + i * 8 + c] : qs[Q_D + i];
+            Y[i] = (c < NC) ? qs[Q_C + i * 8 + c] : qs[Q_D(i)];
         }
         eliminate_row<PIVOT>(g, r > 0 ? qs + Q_A : nullptr, B, Y, X, singular);
         if (r + 2 < rows) bar_arrive(g.bar + NSLOT + slot);      // slot free for the producer's row r+2
@@ -666,7 +667,7 @@ __device__ double factor_problem(const Group& g, int n, double* ws, double (&xm)
     const int cslot = consumer_sweep<PIVOT>(g, first, dir, m, ws, X, singular);
     const double* qc = g.q + cslot * Q_SLOT;         // closing slot of this half
     double rsq = qc[Q_C + 7];
-    const double f1_last = qc[Q_D + c];
+    const double f1_last = (c < NC) ? qc[Q_D(c)] : 0.0;
     double Y[NC];
 #pragma unroll
     for (int i = 0; i < NC; ++i) Y[i] = 0.0;
@@ -697,7 +698,7 @@ __device__ double factor_problem(const Group& g, int n, double* ws, double (&xm)
             const double2* row = reinterpret_cast<const double2*>(sA_last + i * 8);
             const double2 a0 = row[0], a1 = row[1], a2 = row[2], a3 = row[3];
             const double t = a0.x * X[0] + a0.y * X[1] + a1.x * X[2] + a1.y * X[3] + a2.x * X[4] + a2.y * X[5] + a3.x * X[6];
-            part[i] = ((c < NC) ? sB_last[i * 8 + c] : qc[Q_D + i]) - t;
+            part[i] = ((c < NC) ? sB_last[i * 8 + c] : qc[Q_D(i)]) - t;
         }
         if (g.half) {
 #pragma unroll
@@ -717,7 +718,7 @@ __device__ double factor_problem(const Group& g, int n, double* ws, double (&xm)
             const double qscale = g.P[GMPNP_P_Q];
 #pragma unroll
             for (int i = 0; i < NC; ++i) {
-                double d = qc[Q_D + i] + g.psm[56 + i];
+                double d = qc[Q_D(i)] + g.psm[56 + i];
                 if (i == NS) d *= qscale;
                 rsq += d * d;
             }
@@ -1144,6 +1145,7 @@ int edl1d_launch_newton(gmpnp_handle* h, int mode, double* d_u, double* d_un_rw,
                         int* d_iters, double* d_r0, double* d_r, double* d_hfrac, int* d_stage,
                         int* d_status, cudaStream_t st) {
     using namespace edl1d;
+    GmpnpRange nvtx_range(mode == 0 ? "gmpnp:newton_1d" : mode == 1 ? "gmpnp:march_1d" : "gmpnp:steady_continuation_1d");
     const int blocks = (h->batch + PROBLEMS_PER_BLOCK - 1) / PROBLEMS_PER_BLOCK;
     const size_t smem = NEWTON_SMEM_DOUBLES * sizeof(double);
     const bool consistent = (opts->jac_rule == 1);

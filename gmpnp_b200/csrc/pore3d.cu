@@ -690,38 +690,27 @@ coarse_accumulate_kernel(int n_rows, const int* __restrict__ row_ptr, const int*
         if (Ac[i] != 0.0) atomicAdd(&Ac_out[i], Ac[i]);
 }
 
-// Aci = inverse of the (all-reduced) Galerkin matrix; empty coarse columns (all members Dirichlet) -> identity
+__device__ void gj_invert_pivoted(double* Ac, int* perm, double* s_pivinv, int* s_prow, int* s_nbad);
+
+// Aci = pivoted inverse of the (all-reduced) Galerkin matrix; empty coarse rows (all members Dirichlet) -> identity
 __global__ void __launch_bounds__(1024)
-coarse_invert_kernel(const double* __restrict__ Ac_in, double* __restrict__ Aci) {
+coarse_invert_kernel(const double* __restrict__ Ac_in, double* __restrict__ Aci, int* __restrict__ flag) {
     extern __shared__ double Ac[];          // [NCO][NCO]
-    for (int i = threadIdx.x; i < NCO * NCO; i += blockDim.x) Ac[i] = Ac_in[i];
-    __syncthreads();
-    for (int i = threadIdx.x; i < NCO; i += blockDim.x)
-        if (Ac[i * NCO + i] == 0.0) Ac[i * NCO + i] = 1.0;
-    __syncthreads();
+    __shared__ int perm[NCO];
     __shared__ double pivinv;
-    for (int c = 0; c < NCO; ++c) {
-        if (threadIdx.x == 0) {
-            double p = Ac[c * NCO + c];
-            if (!(fabs(p) > 1e-300)) p = 1.0;
-            pivinv = 1.0 / p;
-        }
-        __syncthreads();
-        const double pi = pivinv;
-        for (int j = threadIdx.x; j < NCO; j += blockDim.x)
-            if (j != c) Ac[c * NCO + j] *= pi;
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < NCO * NCO; idx += blockDim.x) {
-            const int r = idx / NCO, j = idx % NCO;
-            if (r == c || j == c) continue;
-            Ac[idx] -= Ac[r * NCO + c] * Ac[c * NCO + j];
-        }
-        __syncthreads();
-        for (int r = threadIdx.x; r < NCO; r += blockDim.x)
-            Ac[r * NCO + c] = (r == c) ? pi : -Ac[r * NCO + c] * pi;
-        __syncthreads();
+    __shared__ int prow, nbad;
+    for (int i = threadIdx.x; i < NCO * NCO; i += blockDim.x) Ac[i] = Ac_in[i];
+    if (threadIdx.x == 0) nbad = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < NCO; i += blockDim.x) {
+        bool empty = true;
+        for (int j = 0; j < NCO; ++j) if (Ac[i * NCO + j] != 0.0) { empty = false; break; }
+        if (empty) Ac[i * NCO + i] = 1.0;
     }
+    __syncthreads();
+    gj_invert_pivoted(Ac, perm, &pivinv, &prow, &nbad);
     for (int i = threadIdx.x; i < NCO * NCO; i += blockDim.x) Aci[i] = Ac[i];
+    if (threadIdx.x == 0 && flag) flag[0] = nbad;
 }
 
 // rc += P^T r over the block rows [0, n_rows) (Dirichlet DOFs excluded)
@@ -895,6 +884,65 @@ coarse_partial_kernel(int n_blocks, const int* __restrict__ chunk_ptr, const int
     part[((long)prob * n_chunk + chunk) * 81 + e] = s;
 }
 
+// In-place Gauss-Jordan inversion of the NCO x NCO matrix Ac (shared memory) with partial pivoting, by one CTA.  A
+// vanishing pivot (singular coarse operator) is replaced by 1 and counted in *nbad.  perm / pivinv / prow: shared scratch.
+__device__ void gj_invert_pivoted(double* Ac, int* perm, double* s_pivinv, int* s_prow, int* s_nbad) {
+    const int tid = threadIdx.x;
+    // in-place Gauss-Jordan inversion with partial pivoting (row swaps recorded in perm)
+    for (int c = 0; c < NCO; ++c) {
+        if (tid < 32) {
+            double best = -1.0; int bi = c;
+            for (int r = c + tid; r < NCO; r += 32) {
+                const double a = fabs(Ac[r * NCO + c]);
+                if (a > best) { best = a; bi = r; }
+            }
+            for (int o = 16; o >= 1; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            if (tid == 0) { *s_prow = bi; perm[c] = bi; }
+        }
+        __syncthreads();
+        const int p = *s_prow;
+        if (p != c) {
+            for (int j = tid; j < NCO; j += blockDim.x) {
+                const double t = Ac[c * NCO + j]; Ac[c * NCO + j] = Ac[p * NCO + j]; Ac[p * NCO + j] = t;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double pv = Ac[c * NCO + c];
+            if (!(fabs(pv) > 1e-300) || !isfinite(pv)) { pv = 1.0; (*s_nbad)++; }
+            *s_pivinv = 1.0 / pv;
+        }
+        __syncthreads();
+        const double pi = *s_pivinv;
+        for (int j = tid; j < NCO; j += blockDim.x)
+            if (j != c) Ac[c * NCO + j] *= pi;
+        __syncthreads();
+        for (int idx = tid; idx < NCO * NCO; idx += blockDim.x) {
+            const int r = idx / NCO, j = idx % NCO;
+            if (r == c || j == c) continue;
+            Ac[idx] -= Ac[r * NCO + c] * Ac[c * NCO + j];
+        }
+        __syncthreads();
+        for (int r = tid; r < NCO; r += blockDim.x)
+            Ac[r * NCO + c] = (r == c) ? pi : -Ac[r * NCO + c] * pi;
+        __syncthreads();
+    }
+    // (P A)^-1 = A^-1 P^T: undo the row swaps as column swaps, last swap first
+    for (int c = NCO - 1; c >= 0; --c) {
+        const int p = perm[c];
+        if (p != c) {
+            for (int r = tid; r < NCO; r += blockDim.x) {
+                const double t = Ac[r * NCO + c]; Ac[r * NCO + c] = Ac[r * NCO + p]; Ac[r * NCO + p] = t;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // one CTA per problem; Ac in shared memory [NCO][NCO]; flag[prob] = number of vanishing pivots replaced by 1
 __global__ void __launch_bounds__(1024)
 coarse_invert_pivoted_kernel(const int* __restrict__ chunk_pair, const double* __restrict__ part, int n_chunk,
@@ -927,59 +975,7 @@ coarse_invert_pivoted_kernel(const int* __restrict__ chunk_pair, const double* _
         if (empty) Ac[i * NCO + i] = 1.0;
     }
     __syncthreads();
-    // in-place Gauss-Jordan inversion with partial pivoting (row swaps recorded in perm)
-    for (int c = 0; c < NCO; ++c) {
-        if (tid < 32) {
-            double best = -1.0; int bi = c;
-            for (int r = c + tid; r < NCO; r += 32) {
-                const double a = fabs(Ac[r * NCO + c]);
-                if (a > best) { best = a; bi = r; }
-            }
-            for (int o = 16; o >= 1; o >>= 1) {
-                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-            }
-            if (tid == 0) { prow = bi; perm[c] = bi; }
-        }
-        __syncthreads();
-        const int p = prow;
-        if (p != c) {
-            for (int j = tid; j < NCO; j += blockDim.x) {
-                const double t = Ac[c * NCO + j]; Ac[c * NCO + j] = Ac[p * NCO + j]; Ac[p * NCO + j] = t;
-            }
-        }
-        __syncthreads();
-        if (tid == 0) {
-            double pv = Ac[c * NCO + c];
-            if (!(fabs(pv) > 1e-300) || !isfinite(pv)) { pv = 1.0; nbad++; }
-            pivinv = 1.0 / pv;
-        }
-        __syncthreads();
-        const double pi = pivinv;
-        for (int j = tid; j < NCO; j += blockDim.x)
-            if (j != c) Ac[c * NCO + j] *= pi;
-        __syncthreads();
-        for (int idx = tid; idx < NCO * NCO; idx += blockDim.x) {
-            const int r = idx / NCO, j = idx % NCO;
-            if (r == c || j == c) continue;
-            Ac[idx] -= Ac[r * NCO + c] * Ac[c * NCO + j];
-        }
-        __syncthreads();
-        for (int r = tid; r < NCO; r += blockDim.x)
-            Ac[r * NCO + c] = (r == c) ? pi : -Ac[r * NCO + c] * pi;
-        __syncthreads();
-    }
-    // (P A)^-1 = A^-1 P^T: undo the row swaps as column swaps, last swap first
-    for (int c = NCO - 1; c >= 0; --c) {
-        const int p = perm[c];
-        if (p != c) {
-            for (int r = tid; r < NCO; r += blockDim.x) {
-                const double t = Ac[r * NCO + c]; Ac[r * NCO + c] = Ac[r * NCO + p]; Ac[r * NCO + p] = t;
-            }
-        }
-        __syncthreads();
-    }
+    gj_invert_pivoted(Ac, perm, &pivinv, &prow, &nbad);
     for (int idx = tid; idx < NCO * NCO; idx += blockDim.x) {
         const int r = idx / NCO, j = idx % NCO;
         AciT[(long)prob * NCO * NCO + (long)j * NCO + r] = Ac[idx];      // transposed
@@ -1791,6 +1787,7 @@ static int check_3d(gmpnp_handle* h) {
 
 static int launch_assemble(gmpnp_handle* h, const double* d_u, const double* d_un, double* d_F, double* d_J,
                            cudaStream_t st) {
+    GmpnpRange nvtx_range("gmpnp:assemble_3d");
     const int T = h->n_tet, V = h->n_nodes, B = h->batch;
     dim3 gA((T + 127) / 128, B);
     tet_moments_kernel<<<gA, 128, 0, st>>>(T, V, h->d_tets, h->d_geom, h->d_params, d_u, d_un, h->d_mom, h->d_Fe,
@@ -1819,6 +1816,7 @@ static int launch_assemble(gmpnp_handle* h, const double* d_u, const double* d_u
 
 static int launch_spmv(gmpnp_handle* h, const double* d_J, const double* d_x, double* d_y, cudaStream_t st,
                        int row0 = 0, int row1 = -1) {
+    GmpnpRange nvtx_range("gmpnp:spmv_3d");
     if (row1 < 0) row1 = h->n_nodes;
     if (row1 <= row0) return GMPNP_OK;
     dim3 g((row1 - row0 + 7) / 8, h->batch);
@@ -1880,6 +1878,7 @@ static size_t gmres_smem_bytes(int m) {
 
 // Jacobian of the current iterate is in h->d_J: block-Jacobi inverses + coarse inverse (deterministic, pivoted)
 static int launch_precond_setup(gmpnp_handle* h, cudaStream_t st) {
+    GmpnpRange nvtx_range("gmpnp:precond_setup_3d");
     Host3D* e = ext(h);
     const int V = h->n_nodes, B = h->batch;
     dim3 gj((V + 63) / 64, B);
@@ -1899,6 +1898,7 @@ static int launch_precond_setup(gmpnp_handle* h, cudaStream_t st) {
 // J dx = b for every enabled problem: ONE launch, no host synchronisation (gmres_cluster_kernel)
 static int launch_gmres(gmpnp_handle* h, const double* d_b, double* d_x, int m, int maxit, double rtol,
                         const int* d_enabled, cudaStream_t st) {
+    GmpnpRange nvtx_range("gmpnp:gmres_3d");
     Host3D* e = ext(h);
     GmresArgs a;
     a.n_vert = h->n_nodes; a.n_blocks = h->n_blocks; a.m = m; a.maxit = maxit; a.rtol = rtol;
@@ -1929,6 +1929,7 @@ static int launch_gmres(gmpnp_handle* h, const double* d_b, double* d_x, int m, 
 // iteration.  d_enabled (device, may be NULL): problems with 0 are left untouched and report GMPNP_CONVERGED, 0 iterations.
 static int newton_run(gmpnp_handle* h, double* d_u, const double* d_un, const gmpnp_newton_opts* o, const int* d_enabled,
                       cudaStream_t st) {
+    GmpnpRange nvtx_range("gmpnp:newton_3d");
     Host3D* e = ext(h);
     const int V = h->n_nodes, B = h->batch;
     const long n = (long)V * NC;
@@ -2056,6 +2057,7 @@ int gmpnp_set_march_data_3d(gmpnp_handle* h, const signed char* h_kind, const do
 static int march_step(gmpnp_handle* h, double* d_u, double* d_un, const gmpnp_newton_opts* o, int step, int n_steps,
                       double ramp, double* d_hist_row, long hist_stride, int* d_iters, int* d_lin_iters, double* d_co2_out,
                       int* n_alive, cudaStream_t st, double steady_tol = 0.0) {
+    GmpnpRange nvtx_range("gmpnp:march_step_3d");
     Host3D* e = ext(h);
     const int V = h->n_nodes, B = h->batch;
     const long n = (long)V * NC;
@@ -2323,7 +2325,7 @@ int gmpnp_coarse_invert_3d(gmpnp_handle* h, const double* d_Ac, void* stream) {
     GMPNP_CUDA_TRY(h, cudaSetDevice(h->device));
     const int smem = (int)(sizeof(double) * NCO * NCO);
     GMPNP_CUDA_TRY(h, cudaFuncSetAttribute(coarse_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    coarse_invert_kernel<<<1, 1024, smem, (cudaStream_t)stream>>>(d_Ac, ext(h)->d_Aci);
+    coarse_invert_kernel<<<1, 1024, smem, (cudaStream_t)stream>>>(d_Ac, ext(h)->d_Aci, ext(h)->d_cflag);
     h->launches++;
     GMPNP_CUDA_TRY(h, cudaGetLastError());
     return GMPNP_OK;

@@ -84,6 +84,9 @@ class TorchComm:
     def halo(self, xs):
         dist = self.dist
         (p,), (x,) = self.parts, xs
+        nvtx = x.is_cuda
+        if nvtx:
+            torch.cuda.nvtx.range_push("gmpnp:halo_exchange")
         ops, recvs = [], []
         for nbr in sorted(set(p.send) | set(p.recv)):
             if nbr in p.send:
@@ -99,6 +102,8 @@ class TorchComm:
         for nbr, rb in recvs:
             x[self._index(p.recv[nbr], x.device)] = rb
             self.halo_bytes += rb.numel() * 8
+        if nvtx:
+            torch.cuda.nvtx.range_pop()
 
     def allreduce_sum(self, ts):
         t = ts[0].clone()

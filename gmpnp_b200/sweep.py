@@ -250,6 +250,41 @@ class Sweep1D:
             res[g["idx"], 9] = f
         return res
 
+    def solve_checkpointed(self, directory: str, profiles: bool = False):
+        """Long sweeps (the reference keeps everything in RAM and writes once at the end, so a crash loses the
+        run): one mesh group at a time, each group's per-point results flushed to ``directory/group_<k>.npz`` as soon
+        as it has converged (atomic rename); a re-run skips the groups whose file exists and returns the same table.
+        Columns: status, Newton iterations, u(OHP)[7], projected field at the OHP; ``profiles`` also stores u."""
+        import os
+        os.makedirs(directory, exist_ok=True)
+        if not all("u" in g for g in self.groups):
+            self.upload()
+        table = np.zeros((self.n_points, N_SUMMARY))
+        solved = 0
+        for k, g in enumerate(self.groups):
+            path = os.path.join(directory, f"group_{k}.npz")
+            if os.path.exists(path):
+                d = np.load(path)
+                if np.array_equal(d["point_index"], np.array([self.points[i].index for i in g["idx"]])):
+                    table[g["idx"]] = d["summary"]
+                    continue
+            u = g["u"]
+            u.fill_(1.0)
+            u[:, :, NC - 1] = 0.0
+            out = g["solver"].steady(u, g["d_path"], self.opts())
+            f = g["solver"].field(u)[:, 0]
+            rows = torch.cat([out["status"].to(torch.float64)[:, None], out["iters"].sum(dim=1).to(torch.float64)[:, None],
+                              u[:, 0, :], f[:, None]], dim=1).cpu().numpy()
+            table[g["idx"]] = rows
+            data = dict(summary=rows, point_index=np.array([self.points[i].index for i in g["idx"]]), L_n=g["L_n"])
+            if profiles:
+                data["u"] = u.cpu().numpy()
+            tmp = path + ".tmp.npz"
+            np.savez_compressed(tmp, **data)
+            os.replace(tmp, path)
+            solved += 1
+        return table, solved
+
     def close(self):
         for g in self.groups:
             g["solver"].close()

@@ -312,6 +312,39 @@ def march_3d(mesh_x, mesh_cells, prm, bc_dofs, bc_kind, n_steps, rtol=1e-4, atol
     return np.array(hist), its, co2s
 
 
+def steady_march_3d(mesh_x, mesh_cells, prm, bc_dofs, bc_kind, tol=1e-8, max_steps=40, n_ramp=1, sechenov=None,
+                    rtol=1e-4, atol=1e-4, maxit=50, relax=0.9):
+    """Steady state as the limit of the reference's pseudo-time march (3D:782-858) with the wall voltage ramped linearly
+    over the first ``n_ramp`` steps (voltage continuation) -- the algorithm of ``gmpnp_steady_3d`` (include/gmpnp.h):
+    starts from the bulk state; per step the Dirichlet values with the current CO2 entry value, one damped Newton solve,
+    the Sechenov update from the nodal medians, u_n <- u; stops at the first step >= n_ramp whose relative increment
+    max|u - u_n| / max(1, max|u|) is <= tol.  Returns (u[nv, ncomp], Newton counts, increments, CO2 entry value)."""
+    ncomp = prm.ns + 1
+    disc = Discretisation(mesh_x, mesh_cells, ncomp)
+    nv = disc.nv
+    eq = prm.extras["eq_scaled"]
+    co2 = float(eq[0])
+    un = np.tile(np.array([1.0] * prm.ns + [0.0]), nv)
+    u = un.copy()
+    its, incs = [], []
+    for s_ in range(max_steps):
+        V = prm.V * min(1.0, (s_ + 1) / n_ramp)
+        vals = np.array([0.0, V, co2, eq[1], eq[2]])[bc_kind.astype(np.int64)]
+        u, k, conv, r0, r = newton(disc, prm.with_(V=V), u, un, bc_dofs, vals, rtol=rtol, atol=atol, maxit=maxit, relax=relax)
+        if not conv:
+            raise RuntimeError(f"Newton solver did not converge in pseudo-time step {s_}")
+        its.append(k)
+        U = u.reshape(nv, ncomp)
+        if sechenov is not None:
+            co2 = sechenov(np.median(U[:, 1]), np.median(U[:, 2]), np.median(U[:, 3]), np.median(U[:, prm.ns - 1]))
+        inc = float(np.abs(u - un).max() / max(1.0, np.abs(u).max()))
+        incs.append(inc)
+        un = u.copy()
+        if s_ + 1 >= n_ramp and inc <= tol:
+            break
+    return u.reshape(nv, ncomp), its, incs, co2
+
+
 def steady_3d(mesh_x, mesh_cells, prm, bc_dofs, bc_kind, V_path, co2_entry, u0=None, xtol=1e-12, maxit=50):
     """Steady 3D equations (kappa = 0) with voltage continuation, full Newton steps, fixed CO2 entry value."""
     ncomp = prm.ns + 1

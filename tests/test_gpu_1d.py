@@ -480,3 +480,19 @@ def test_rxn_diff_drop_in_matches_oracle(lib, tmp_path):
     for i, nm in enumerate(("H", "OH", "HCO3", "CO32", "CO2")):
         assert rel_l2(un[nm][3], U[:, i]) < 1e-8, nm
     assert np.abs(U[:, 5] - 1.0).max() < 1e-12 and np.abs(U[:, 6]).max() < 1e-12
+
+
+def test_checkpointed_sweep_resumes(lib, tmp_path):
+    """Per-group result flushing: a second run of the same sweep finds every group on disk and solves nothing; removing
+    one file re-solves only that group; the tables are identical."""
+    from gmpnp_b200 import sweep
+    pts = sweep.config2_points(3, meshes=(1e-6, 5e-6), concs=(0.1,), cations=("K",))
+    sw = sweep.Sweep1D(pts, device=0, dv_max=0.75, xtol_path=1.0)
+    t1, n1 = sw.solve_checkpointed(str(tmp_path))
+    assert n1 == 2 and (t1[:, 0] == 0).all() and (t1[:, 1] > 0).all()
+    t2, n2 = sw.solve_checkpointed(str(tmp_path))
+    assert n2 == 0 and np.array_equal(t1, t2)
+    os.remove(os.path.join(str(tmp_path), "group_1.npz"))
+    t3, n3 = sw.solve_checkpointed(str(tmp_path))
+    assert n3 == 1 and np.array_equal(t1, t3)
+    sw.close()

@@ -427,3 +427,49 @@ def test_api_errors_3d(lib):
     out = s.newton(ubad, u.clone())
     assert int(out["status"][1]) == 2 and int(out["status"][0]) == 0
     s.close()
+
+
+def test_cuda_assembly_matches_the_exact_integral_restatement(lib):
+    """CUDA tet assembly with nu = 0 against the SECOND, independent restatement (oracle/pnp3d_exact.py: exact monomial
+    integrals, no quadrature tables): residual and every BSR entry of the full 9-component problem."""
+    from gmpnp_b200 import params, solver3d
+    from oracle import pnp3d_exact
+    mesh = cube_tet_mesh(3, scale=(0.2, 0.3, 1.0))
+    n = mesh.num_vertices
+    prm = params.params_3d(L=50e-9, R=5e-9, voltage_multiplier=-2.0)
+    p0 = prm.with_(nu=np.zeros(8))
+    rng = np.random.default_rng(9)
+    u = admissible_state(rng, n, 8, prm.nu, V=-5.0)
+    un = admissible_state(rng, n, 8, prm.nu, V=-5.0)
+    s = solver3d.Solver3D(mesh, np.zeros(0, dtype=np.int32), batch=1)
+    s.set_params([p0])
+    s.set_dirichlet(np.zeros((1, 0)))
+    F, J = s.assemble(_t(u[None]), _t(un[None]))
+    rp, ci = s.pattern()
+    ex = pnp3d_exact.Pnp3DExact(mesh.x, mesh.cells, p0)
+    Fo = ex.residual(u.ravel(), un.ravel())
+    Ao = ex.jacobian(u.ravel()).toarray()
+    assert np.abs(F[0].cpu().numpy().ravel() - Fo).max() <= 1e-11 * np.abs(Fo).max()
+    A = bsr_to_dense(J[0].cpu().numpy(), rp, ci, n)
+    assert (np.abs(A - Ao) <= 1e-11 * np.abs(Ao).max(axis=1, keepdims=True)).all()
+    s.close()
+
+
+def test_steady_with_voltage_ramp_matches_oracle(lib):
+    """North-star steady solve in 3D (voltage continuation): gmpnp_steady_3d on L_10_R_5, wall voltage -2 V_T ramped
+    over 4 pseudo-time steps, against the oracle's restatement of the same march (tests/golden/
+    make_golden_3d_steady.py): number of steps, Newton counts within 1, CO2 entry value, final state to 1e-8."""
+    from gmpnp_b200 import meshio, params, solver3d
+    g = np.load(os.path.join(GOLDEN, "steady_3d_L10R5.npz"))
+    mesh = meshio.load_mesh("L_10_R_5")
+    prm = params.params_3d(L=10e-9, R=5e-9, voltage_multiplier=float(g["V"]))
+    pp = solver3d.PoreProblem(mesh, 10e-9, 5e-9, [prm])
+    out = pp.steady(tol=1e-8, max_steps=40, dv_max=0.5)
+    assert out["converged"].tolist() == [True]
+    assert out["steps"] == len(g["its"]), (out["steps"], g["its"])
+    assert np.abs(out["iters"][:, 0] - g["its"]).max() <= 1, (out["iters"][:, 0], g["its"])
+    assert abs(out["co2_entry"][0] - float(g["co2"])) <= 1e-8 * float(g["co2"])
+    got = out["u"][0].cpu().numpy()
+    for c in range(9):
+        assert rel_l2(got[:, c], g["u"][:, c]) < PARITY_3D, c
+    pp.solver.close()

@@ -88,3 +88,33 @@ def test_rxn_diff_3d_golden_vectors_present_and_consistent():
     g = np.load(os.path.join(GOLDEN, "rxn_diff_3d_L10R5.npz"))
     assert g["steps"].shape == (2, 1767, 7) and g["its"].tolist() == [7, 5]
     assert np.isfinite(g["steps"]).all() and g["steps"][:, :, 4].min() > 0.0
+
+
+def test_two_independent_restatements_agree_on_the_polynomial_terms():
+    """oracle/pnp3d_exact.py (exact monomial integrals, written from the reference's forms, no quadrature tables) against
+    oracle/forms.py + oracle/quadrature.py with nu = 0: residual and Jacobian of the full 9-component problem agree to
+    round-off on a generic tet mesh -- every term except the rational steric one is pinned by two restatements."""
+    import numpy as np
+    from conftest import admissible_state, cube_tet_mesh
+    from gmpnp_b200 import params
+    from oracle import pnp3d_exact, solver as osolver
+    mesh = cube_tet_mesh(3, scale=(0.2, 0.3, 1.0))
+    n = mesh.num_vertices
+    for kw in (dict(L=50e-9, R=5e-9), dict(L=100e-9, R=5e-9, concentration_elec=0.5, time_step=1e-5)):
+        prm = params.params_3d(**kw)
+        p0 = prm.with_(nu=np.zeros(8))
+        rng = np.random.default_rng(3)
+        u = admissible_state(rng, n, 8, prm.nu, V=-5.0).ravel()
+        un = admissible_state(rng, n, 8, prm.nu, V=-5.0).ravel()
+        disc = osolver.Discretisation(mesh.x, mesh.cells, 9)
+        ex = pnp3d_exact.Pnp3DExact(mesh.x, mesh.cells, p0)
+        F1, F2 = disc.residual(u, un, p0), ex.residual(u, un)
+        assert np.abs(F1 - F2).max() <= 1e-12 * np.abs(F2).max()
+        A1, A2 = disc.jacobian(u, p0).toarray(), ex.jacobian(u).toarray()
+        rows = np.abs(A2).max(axis=1, keepdims=True)
+        assert (np.abs(A1 - A2) <= 1e-12 * rows).all()
+        # the exact Jacobian is the derivative of the exact residual (central differences, relative step 1e-6)
+        v = rng.normal(size=u.shape)
+        h = 1e-6
+        fd = (ex.residual(u + h * v, un) - ex.residual(u - h * v, un)) / (2 * h)
+        assert np.abs(fd - A2 @ v).max() <= 1e-6 * np.abs(A2 @ v).max()

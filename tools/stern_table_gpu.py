@@ -7,6 +7,8 @@ The CPU oracle reproduces the table to 9-10 digits; this i
     python tools/stern_table_gpu.py                 # two coarse marches (2e-4 s, 1e-4 s) + extrapolation to 1e-5 s: ~1 min
     python tools/stern_table_gpu.py --exact         # the 20 000 steps themselves (consistent Jacobian: ~6 min on a B200)
     python tools/stern_table_gpu.py --exact --jac_rule 0     # ... with FFC's rule pair, i.e. the reference's iteration path
+                                                             # (measured: at -12.5 V_T that Newton iteration reaches
+                                                             # maxit = 50 at some step, so that voltage stops early)
 
 Product API only (no oracle); one JSON line per mode.
 """
@@ -47,7 +49,9 @@ def march_to(s, opts, t_end=0.2, dt=1.0e-5, dt2=0.0, n1=100, grow=1.25):
         n = int(round(t_end / dt))
         s.set_params(plist(dt))
         out = s.march(u, un, n, opts)
-        assert not out["status"].any().item(), out["status"].tolist()
+        # a voltage whose Newton iteration hits maxit at some step (FFC's rule pair at -12.5 V_T) stops alone; the
+        # others are reported (status per voltage in the JSON line)
+        march_to.status = out["status"].tolist()
         return u, n, int(out["iters"].sum(dim=1).max())
     s.set_params(plist(dt))
     out = s.march(u, un, n1, opts)
@@ -82,7 +86,7 @@ def main():
     if a.exact:
         u, n, its = march_to(s, opts)
         f, e = ohp(s, u, prm)
-        line = {"mode": "exact", "steps": n, "newton_max": its}
+        line = {"mode": "exact", "steps": n, "newton_max": its, "status_per_voltage": march_to.status}
     else:
         ua, na, ia = march_to(s, opts, dt2=2.0e-4)
         fa, ea = ohp(s, ua, prm)
