@@ -56,11 +56,12 @@ class Sweep3D:
     NCOL = 9
 
     def __init__(self, points, device: int = 0, utilities_dir=None, dv_max: float = 0.5, tol: float = 1e-8,
-                 max_steps: int = 40, opts: NewtonOpts | None = None, **param_kw):
+                 max_steps: int = 40, opts: NewtonOpts | None = None, retry: bool = True, **param_kw):
         self.points = list(points)
         self.device = int(device)
         self.dv_max, self.tol, self.max_steps = dv_max, tol, max_steps
         self.opts = opts or NewtonOpts.sweep_3d()
+        self.retry = bool(retry)
         self.utilities_dir, self.param_kw = utilities_dir, param_kw
         self.by_mesh = {}
         for i, p in enumerate(self.points):
@@ -75,6 +76,19 @@ class Sweep3D:
             pp = PoreProblem(mesh, L, R, plist, device=self.device)
             res[idx] = self._steady_with_parking(pp)
             pp.solver.close()
+            bad = [k for k, i in enumerate(idx) if res[i, 0] != 0]
+            if self.retry and bad:
+                # parked points once more on their own: half the voltage increment, twice the pseudo-time steps and
+                # the parity linear solver GMRES(100)/1e-10 (failure handling: never abort the batch)
+                pp = PoreProblem(mesh, L, R, [plist[k] for k in bad], device=self.device)
+                keep = (self.dv_max, self.max_steps, self.opts)
+                self.dv_max, self.max_steps, self.opts = 0.5 * self.dv_max, 2 * self.max_steps, NewtonOpts.reference_3d()
+                again = self._steady_with_parking(pp)
+                self.dv_max, self.max_steps, self.opts = keep
+                pp.solver.close()
+                for k, row in zip(bad, again):
+                    if row[0] == 0:
+                        res[idx[k]] = row
         return res
 
     def _steady_with_parking(self, pp: PoreProblem):

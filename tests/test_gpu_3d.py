@@ -473,3 +473,27 @@ def test_steady_with_voltage_ramp_matches_oracle(lib):
     for c in range(9):
         assert rel_l2(got[:, c], g["u"][:, c]) < PARITY_3D, c
     pp.solver.close()
+
+
+def test_run_to_run_bitwise_reproducibility_3d(lib):
+    """The persistent cluster GMRES reduces through distributed shared memory in a fixed rank order and the coarse
+    operator is summed in a fixed chunk order: two runs of the same batched Newton solve agree BITWISE (iterates, Newton
+    and GMRES iteration counts), and so do the two identical problems of the batch."""
+    from gmpnp_b200 import meshio, params, solver3d
+    from gmpnp_b200._lib import NewtonOpts
+    mesh = meshio.load_mesh("L_10_R_5")
+    prm = params.params_3d(L=10e-9, R=5e-9, voltage_multiplier=-0.75)
+    pp = solver3d.PoreProblem(mesh, 10e-9, 5e-9, [prm, prm, prm])
+    s = pp.solver
+    s.set_dirichlet(pp.dirichlet_values([float(prm.extras["eq_scaled"][0])] * 3))
+    outs = []
+    for _ in range(2):
+        u = torch.zeros(3, s.n, 9, dtype=torch.float64, device=_dev())
+        un = solver3d.bulk_state(3, s.n, _dev())
+        o = s.newton(u, un, NewtonOpts.reference_3d())
+        torch.cuda.synchronize()
+        outs.append((u.clone(), o["iters"].clone(), o["lin_iters"].clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    assert torch.equal(outs[0][0][0], outs[0][0][1]) and torch.equal(outs[0][0][0], outs[0][0][2])
+    assert int(outs[0][1][0]) > 0
+    s.close()

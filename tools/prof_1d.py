@@ -18,17 +18,16 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--mesh", type=float, nargs="*", default=[1e-6])
 ap.add_argument("--voltages", type=int, default=256)
 ap.add_argument("--reps", type=int, default=2)
-ap.add_argument("--pivot", type=int, default=1)
-ap.add_argument("--dv", type=float, default=0.5)
-ap.add_argument("--xtol_path", type=float, default=1e-3)
+ap.add_argument("--pivot", type=int, default=0)
+ap.add_argument("--dv", type=float, default=0.75)
+ap.add_argument("--xtol_path", type=float, default=1.0)
 ap.add_argument("--jac_rule", type=int, default=1)
 a = ap.parse_args()
 
 pts = sweep.config2_points(a.voltages, meshes=tuple(a.mesh))
-sw = sweep.Sweep1D(pts, device=0, dv_max=a.dv, xtol_path=a.xtol_path)
+sw = sweep.Sweep1D(pts, device=0, dv_max=a.dv, xtol_path=a.xtol_path, jac_rule=a.jac_rule)      # the bench's settings
 sw.upload()
-opts = NewtonOpts.steady(xtol=1e-12, maxit=50, xtol_path=a.xtol_path, jac_rule=a.jac_rule)
-opts.pivot = a.pivot
+opts = sw.opts(pivot=a.pivot)
 for g in sw.groups:
     s = g["solver"]
     for rep in range(a.reps):

@@ -1,4 +1,7 @@
 #!/bin/bash
+# NOTE (round 2): compute-sanitizer is CLOSED on the B200 pool this repo is measured on (profiles/r02_sanitizer_unavailable.log:
+# "runs under it have left GPUs needing a reset"); races and bad accesses are covered instead by the tiny-mesh edge cases
+# against the CPU oracle and the bitwise run-to-run / batch-position reproducibility tests (tests/test_gpu_*.py).
 # compute-sanitizer pass over the small-mesh GPU tests (race detection / sanitizers): memcheck and racecheck on
 # the warp-specialised 1D kernel (shared-memory queue, named barriers, cp.async rings), the persistent cluster GMRES
 # (distributed shared memory, cluster barriers) and the gather-style 3D assembly.  Writes gpurun_out/sanitize_*.log.
@@ -6,7 +9,7 @@ mkdir -p gpurun_out
 T1='tests/test_gpu_1d.py::test_tiny_even_and_odd_meshes_match_the_oracle tests/test_gpu_1d.py::test_stalled_increment_is_reported_not_accepted'
 T3='tests/test_gpu_3d.py::test_newton_3d_small_mesh_vs_oracle tests/test_gpu_3d.py::test_assemble_3d_matches_golden_entrywise tests/test_gpu_3d.py::test_library_march_reports_failures_per_problem'
 for tool in memcheck racecheck; do
-  timeout 1500 compute-sanitizer --tool $tool --target-processes all --error-exitcode 9 \
+  timeout 600 compute-sanitizer --tool $tool --target-processes all --error-exitcode 9 \
       python -m pytest $T1 $T3 -x -q -p no:cacheprovider > gpurun_out/sanitize_$tool.log 2>&1
   echo "$tool rc=$?" >> gpurun_out/sanitize_$tool.log
   grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed|rc=" gpurun_out/sanitize_$tool.log | tail -5
