@@ -153,9 +153,9 @@ __device__ __forceinline__ void cell_columns(const double* __restrict__ P, const
     // that the row is O(1) like the species rows and the in-block pivot is almost always the diagonal
     // (q ~ 1e9 in 1D, 1D:193); the materialising kernel passes 1.
     const double ih = fast_rcp(h);
-    double g[NC];
+    double g[NC], dU[NC];
 #pragma unroll
-    for (int i = 0; i < NC; ++i) g[i] = (U1[i] - U0[i]) * ih;
+    for (int i = 0; i < NC; ++i) { dU[i] = U1[i] - U0[i]; g[i] = dU[i] * ih; }
     double G = 0.0;
 #pragma unroll
     for (int i = 0; i < NS; ++i) G += P[GMPNP_P_NU + i] * g[i];
@@ -195,7 +195,7 @@ __device__ __forceinline__ void cell_columns(const double* __restrict__ P, const
                 const double l1 = GX2[q], l0 = 1.0 - l1, W = GW2[q] * h;
                 double uq[NS], S = 0.0;
 #pragma unroll
-                for (int i = 0; i < NS; ++i) { uq[i] = l0 * U0[i] + l1 * U1[i]; S += P[GMPNP_P_NU + i] * uq[i]; }
+                for (int i = 0; i < NS; ++i) { uq[i] = fma(l1, dU[i], U0[i]); S += P[GMPNP_P_NU + i] * uq[i]; }
                 const double D = fast_rcp(1.0 - S);
                 species_acc(l0, l1, W, uq, D);
                 resid_acc(l0, l1, W, uq, D);
@@ -206,7 +206,7 @@ __device__ __forceinline__ void cell_columns(const double* __restrict__ P, const
                 const double l1 = GX3[q], l0 = 1.0 - l1, W = GW3[q] * h;
                 double uq[NS], S = 0.0;
 #pragma unroll
-                for (int i = 0; i < NS; ++i) { uq[i] = l0 * U0[i] + l1 * U1[i]; S += P[GMPNP_P_NU + i] * uq[i]; }
+                for (int i = 0; i < NS; ++i) { uq[i] = fma(l1, dU[i], U0[i]); S += P[GMPNP_P_NU + i] * uq[i]; }
                 species_acc(l0, l1, W, uq, fast_rcp(1.0 - S));
             }
 #pragma unroll
@@ -214,7 +214,7 @@ __device__ __forceinline__ void cell_columns(const double* __restrict__ P, const
                 const double l1 = GX2[q], l0 = 1.0 - l1, W = GW2[q] * h;
                 double uq[NS], S = 0.0;
 #pragma unroll
-                for (int i = 0; i < NS; ++i) { uq[i] = l0 * U0[i] + l1 * U1[i]; S += P[GMPNP_P_NU + i] * uq[i]; }
+                for (int i = 0; i < NS; ++i) { uq[i] = fma(l1, dU[i], U0[i]); S += P[GMPNP_P_NU + i] * uq[i]; }
                 resid_acc(l0, l1, W, uq, fast_rcp(1.0 - S));
             }
         }
@@ -492,15 +492,23 @@ __device__ void producer_sweep(const Group& g, const LaneConst& L, const double*
             CellCols cc;
             cell_columns<NQJ, true>(P, fu + s0, fu + s1, L, c, h, prow, U0, U1, myU0, myU1, myN0, myN1, cc, qn + Q_A, qn + Q_B);
             // ---- row k: A = (1,0) behind (already in the slot), B = (1,1) behind + c00, coupling ahead = c01 ----
-            const bool dir_all = (r == 0 && k == n - 1);     // Dirichlet node x = 1: all components (1D:350-353)
-            const bool dir_pot = (r == 0 && k == 0);         // OHP: potential = V (1D:354)
+            if (r > 0) {                                     // the common case, kept free of the boundary selects
 #pragma unroll
-            for (int i = 0; i < NC; ++i) {
-                double bv = cc.c00[i] + ((r > 0) ? qs[Q_B + i * 8 + c] : 0.0);
-                double cv = cc.c01[i];
-                if (dir_all || (dir_pot && i == NS)) { bv = (i == c) ? 1.0 : 0.0; cv = 0.0; }
-                qs[Q_B + i * 8 + c] = bv;
-                qs[Q_C + i * 8 + c] = cv;
+                for (int i = 0; i < NC; ++i) {
+                    qs[Q_B + i * 8 + c] += cc.c00[i];
+                    qs[Q_C + i * 8 + c] = cc.c01[i];
+                }
+            } else {
+                // first row of a half = boundary node: nothing behind it; Dirichlet rows become identity rows
+                const bool dir_all = (k == n - 1);           // x = 1: all components (1D:350-353)
+                const bool dir_pot = (k == 0);               // OHP: potential = V (1D:354)
+#pragma unroll
+                for (int i = 0; i < NC; ++i) {
+                    double bv = cc.c00[i], cv = cc.c01[i];
+                    if (dir_all || (dir_pot && i == NS)) { bv = (i == c) ? 1.0 : 0.0; cv = 0.0; }
+                    qs[Q_B + i * 8 + c] = bv;
+                    qs[Q_C + i * 8 + c] = cv;
+                }
             }
             sF[c] = f1_behind + cc.f0;               // this lane's residual row of node k
             f1_behind = cc.f1;
@@ -510,22 +518,23 @@ __device__ void producer_sweep(const Group& g, const LaneConst& L, const double*
             double Y[NC];
 #pragma unroll
             for (int i = 0; i < NC; ++i) Y[i] = sF[i];
-            // point fluxes `J_i v_i ds` at both end points (1D:553, 738)
-            if (r == 0) {
+            double pscale = qscale;                  // ||b||_2 of the reference's (unscaled) system: undo the Poisson-row
+            if (r == 0) {                            // scaling except on Dirichlet rows
+                // point fluxes `J_i v_i ds` at both end points (1D:553, 738)
 #pragma unroll
                 for (int i = 0; i < NS; ++i) Y[i] += P[GMPNP_P_JFLUX + i];
-            }
-            // Dirichlet rows (1D:350-355): x=1 all components = (1,..,1,0); x=0 potential = V.  Only the first row
-            // of a half is a boundary node (the halves start at nodes 0 and n-1).
-            if (r == 0 && k == n - 1) {
+                // Dirichlet rows (1D:350-355): x=1 all components = (1,..,1,0); x=0 potential = V.  Only the first row
+                // of a half is a boundary node (the halves start at nodes 0 and n-1).
+                if (k == n - 1) {
 #pragma unroll
-                for (int i = 0; i < NC; ++i) Y[i] = fu[s0 + i] - ((i < NS) ? 1.0 : 0.0);
+                    for (int i = 0; i < NC; ++i) Y[i] = fu[s0 + i] - ((i < NS) ? 1.0 : 0.0);
+                }
+                if (k == 0) Y[NS] = fu[s0 + NS] - P[GMPNP_P_V];
+                pscale = 1.0;
             }
-            if (r == 0 && k == 0) Y[NS] = fu[s0 + NS] - P[GMPNP_P_V];
-            // ||b||_2 of the reference's (unscaled) system: undo the Poisson-row scaling except on Dirichlet rows
 #pragma unroll
             for (int i = 0; i < NS; ++i) rsq += Y[i] * Y[i];
-            const double yp = (r == 0) ? Y[NS] : Y[NS] * qscale;
+            const double yp = Y[NS] * pscale;
             rsq += yp * yp;
 #pragma unroll
             for (int i = 0; i < NC; ++i) qs[Q_D(i)] = Y[i];
@@ -828,6 +837,8 @@ constexpr size_t NEWTON_SMEM_DOUBLES = (size_t)NW_GROUPS * (SM_GROUP + SM_RING) 
 // the producer of consumer warp w.  A lane and its twin in the partner warp handle the same (problem, half).
 __device__ __forceinline__ void group_setup(Group& g, int batch, int& prob, double* smem, bool& producer, int*& cmd) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // consumers in warps [0, NW_PAIRS), producers above.  (Measured: alternating the roles with the CTA index, so that
+    // every scheduler sees a mix of producer and consumer warps, is SLOWER -- 87.9 vs 70.2 ms on the saturated launch.)
     producer = warp >= NW_PAIRS;
     const int wp = producer ? warp - NW_PAIRS : warp;          // warp pair
     g.c = lane & 7;

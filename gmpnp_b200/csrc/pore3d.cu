@@ -1866,6 +1866,12 @@ static int ensure_solver(gmpnp_handle* h, int m) {
 
 // cluster size of the persistent GMRES kernel: fill the 148 SMs when the batch is small
 static int gmres_cluster_size(int batch) {
+    // experiments / tests only: GMPNP_GMRES_CLUSTER=1|2|4|8 forces the cluster size (the result of a solve does not
+    // depend on it beyond the summation order of the dot products)
+    if (const char* env = getenv("GMPNP_GMRES_CLUSTER")) {
+        const int g = atoi(env);
+        if (g == 1 || g == 2 || g == 4 || g == 8) return g;
+    }
     int g = 1;
     while (g < 8 && batch * g * 2 <= 148) g *= 2;
     return g;

@@ -27,7 +27,7 @@ a = ap.parse_args()
 mesh = meshio.load_mesh(a.mesh)
 for _ in range(a.refine):
     mesh = meshio.red_refine(mesh, project_radius=a.R / a.L)
-Vs = -1.0 - 0.01 * np.arange(a.batch)
+Vs = -0.5 - 0.75 * np.arange(a.batch) / max(1, a.batch - 1)          # the bench's voltage range [-0.5, -1.25] V_T
 plist = [params.params_3d(L=a.L, R=a.R, voltage_multiplier=float(V)) for V in Vs]
 t0 = time.time()
 pp = solver3d.PoreProblem(mesh, a.L, a.R, plist)
@@ -73,8 +73,12 @@ if a.steady:
     print("increments", np.array2string(out["increments"], precision=2))
 elif a.steps:
     t0 = time.time()
-    out = pp.march(a.steps, history=False)
+    s.set_params(plist)
+    s.set_march_data(*pp.march_data())
+    u0 = torch.zeros(a.batch, s.n, 9, dtype=torch.float64, device=dev)
+    out = s.march(u0, solver3d.bulk_state(a.batch, s.n, dev), a.steps)          # per-problem status, never raises
     torch.cuda.synchronize()
     dt = time.time() - t0
-    print(f"march {a.steps} steps: {dt:.2f}s, Newton its {out['iters'][:, 0].tolist()}, GMRES its {out['lin_iters'][:, 0].tolist()}, "
-          f"launches {s.launch_count()}")
+    st = out["status"].cpu().numpy()
+    print(f"march {a.steps} steps: {dt:.2f}s, converged {int((st == 0).sum())}/{a.batch}, Newton its (problem 0) "
+          f"{out['iters'][0].tolist()}, GMRES its (problem 0) {out['lin_iters'][0].tolist()}, launches {s.launch_count()}")
