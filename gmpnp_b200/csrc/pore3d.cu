@@ -991,7 +991,10 @@ coarse_invert_pivoted_kernel(const int* __restrict__ chunk_pair, const double* _
 // bitwise-identical sum, so the control flow stays cluster-uniform) and meet at cluster barriers.  The small
 // Hessenberg / Givens recurrences are done redundantly by thread 0 of every CTA.
 // ---------------------------------------------------------------------------------------
-constexpr int GM_THREADS = 512;
+#ifndef GMPNP_GM_THREADS
+#define GMPNP_GM_THREADS 512
+#endif
+constexpr int GM_THREADS = GMPNP_GM_THREADS;
 constexpr int GM_WARPS = GM_THREADS / 32;
 constexpr int GM_KT = 8;                 // dot products per pass over the chunk
 
@@ -1244,8 +1247,18 @@ gmres_cluster_kernel(GmresArgs a) {
                 cluster_reduce(cl, S, buf, j + 1, red_n);
                 double nrm2 = 0.0;
                 for (long i = i0 + tid; i < i1; i += GM_THREADS) {
+                    // eight independent basis loads in flight per thread (the loop over k has a run-time bound, so
+                    // without the explicit batch every load would wait for the previous FMA: latency-bound)
                     double s = w[i];
-                    for (int k = 0; k <= j; ++k) s -= S.sums[k] * Vp[(long)k * n + i];
+                    int k = 0;
+                    for (; k + GM_KT <= j + 1; k += GM_KT) {
+                        double v[GM_KT];
+#pragma unroll
+                        for (int q = 0; q < GM_KT; ++q) v[q] = Vp[(long)(k + q) * n + i];
+#pragma unroll
+                        for (int q = 0; q < GM_KT; ++q) s -= S.sums[k + q] * v[q];
+                    }
+                    for (; k <= j; ++k) s -= S.sums[k] * Vp[(long)k * n + i];
                     w[i] = s;
                     nrm2 += s * s;
                 }
@@ -1303,7 +1316,15 @@ gmres_cluster_kernel(GmresArgs a) {
         __syncthreads();
         for (long i = i0 + tid; i < i1; i += GM_THREADS) {
             double s = 0.0;
-            for (int k = 0; k < jd; ++k) s += S.y[k] * Vp[(long)k * n + i];
+            int k = 0;
+            for (; k + GM_KT <= jd; k += GM_KT) {
+                double v[GM_KT];
+#pragma unroll
+                for (int q = 0; q < GM_KT; ++q) v[q] = Vp[(long)(k + q) * n + i];
+#pragma unroll
+                for (int q = 0; q < GM_KT; ++q) s += S.y[k + q] * v[q];
+            }
+            for (; k < jd; ++k) s += S.y[k] * Vp[(long)k * n + i];
             w[i] = s;
         }
         cl.sync();                                       // t = V y complete (in w)

@@ -31,7 +31,7 @@ def test_both_arms_describe_the_same_config():
     spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    a = argparse.Namespace(voltages=256, dv=0.75, xtol_path=1.0)
+    a = argparse.Namespace(voltages=256, dv=0.75, xtol_path=1.0, xtol=1e-10)
     cfg = mod.base_config(a)
     assert cfg["workload"].startswith("config2") and cfg["points_total_config2"] == 7680
     pts = mod.stratified_points(2, 256)
@@ -41,7 +41,7 @@ def test_both_arms_describe_the_same_config():
 def test_cpu_workers_do_not_import_torch():
     """The CPU arm's workers import NumPy/SciPy only (no multi-second `import torch` inside the measurement)."""
     code = ("import sys; sys.path.insert(0, %r); import bench; bench._worker_init(); "
-            "r = bench._cpu_solve_point(('K', 0.1, 1e-6, -0.5, 0.75, 1.0, True)); "
+            "r = bench._cpu_solve_point(('K', 0.1, 1e-6, -0.5, 0.75, 1.0, True, 1e-10)); "
             "assert r['ok'] and r['u'].shape == (1091, 7) and 'torch' not in sys.modules; print('ok')") % ROOT
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr[-2000:]
