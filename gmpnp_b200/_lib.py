@@ -19,15 +19,15 @@ class NewtonOpts(C.Structure):
     _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("relax", C.c_double), ("xtol", C.c_double),
                 ("maxit", C.c_int), ("criterion", C.c_int), ("pivot", C.c_int), ("lin_maxit", C.c_int),
                 ("lin_restart", C.c_int), ("lin_rtol", C.c_double), ("xtol_path", C.c_double),
-                ("jac_rule", C.c_int), ("reserved", C.c_int), ("xtol_floor", C.c_double)]
+                ("jac_rule", C.c_int), ("partitions", C.c_int), ("xtol_floor", C.c_double)]
 
     @classmethod
     def reference_1d(cls):
-        return cls(1e-4, 1e-4, 1.0, 1e-12, 50, 0, 1, 0, 0, 0.0, 0.0, 0, 0, 0.0)
+        return cls(1e-4, 1e-4, 1.0, 1e-12, 50, 0, 1, 0, 0, 0.0, 0.0, 0, 2, 0.0)
 
     @classmethod
     def reference_3d(cls):
-        return cls(1e-4, 1e-4, 0.9, 1e-12, 50, 0, 1, 2000, 100, 1e-10, 0.0, 0, 0, 0.0)
+        return cls(1e-4, 1e-4, 0.9, 1e-12, 50, 0, 1, 2000, 100, 1e-10, 0.0, 0, 2, 0.0)
 
     @classmethod
     def sweep_3d(cls):
@@ -52,7 +52,7 @@ class NewtonOpts(C.Structure):
 
     @classmethod
     def steady(cls, xtol=1e-12, maxit=50, relax=1.0, xtol_path=0.0, jac_rule=0, xtol_floor=0.0):
-        return cls(1e-4, 1e-4, relax, xtol, maxit, 1, 1, 2000, 100, 1e-12, xtol_path, jac_rule, 0, xtol_floor)
+        return cls(1e-4, 1e-4, relax, xtol, maxit, 1, 1, 2000, 100, 1e-12, xtol_path, jac_rule, 2, xtol_floor)
 
 
 STATUS_NAMES = {0: "converged", 1: "maxit", 2: "not_finite", 3: "linear_failed", 4: "stagnated"}

@@ -147,7 +147,7 @@ extern "C" void gmpnp_destroy(gmpnp_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->dim == 3) pore3d_free_ext(h);
-    void* bufs[] = {h->d_x, h->d_params, h->d_ws, h->d_tets, h->d_geom, h->d_row_ptr, h->d_col_idx, h->d_diag_idx,
+    void* bufs[] = {h->d_x, h->d_params, h->d_ws, h->d_ws2, h->d_tets, h->d_geom, h->d_row_ptr, h->d_col_idx, h->d_diag_idx,
                     h->d_blk_ptr, h->d_blk_src, h->d_node_ptr, h->d_node_src, h->d_dir_dof, h->d_dir_flag,
                     h->d_dir_val, h->d_mom, h->d_Fe, h->d_J, h->d_Dinv, h->d_F, h->d_krylov, h->d_small,
                     h->d_ismall, h->d_sort};

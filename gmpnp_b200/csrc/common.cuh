@@ -42,6 +42,7 @@ struct gmpnp_handle {
     bool params_set = false;
     // ---- 1D ----
     double* d_ws = nullptr;       // elimination workspace [batch][n][56]
+    double* d_ws2 = nullptr;      // partitioned elimination: spike workspace [batch][n][56] (allocated on first use)
     // ---- 3D ----
     int n_tet = 0, n_dir = 0, n_blocks = 0;
     int* d_tets = nullptr;        // [T][4]

@@ -1011,6 +1011,713 @@ newton1d_kernel(int mode, int batch, int n, const double* __restrict__ x, const 
     }
 }
 
+// =======================================================================================
+// Partitioned elimination: S = 4 or 8 sweeps per problem (strong scaling / single-problem latency)
+// =======================================================================================
+// The two-sided factorisation above has a critical path of n/2 block rows per Newton iteration whatever the number
+// of idle SMs.  Here the chain is cut into Q = S/2 + 1 sub-domains by Q - 1 SEPARATOR nodes.  The two outer sub-domains
+// are swept once (from the domain boundary towards their separator, as above); every interior sub-domain is swept
+// TWICE, downwards and upwards, each sweep starting next to a separator whose unknown value it carries along as a
+// 7-column SPIKE W (x_k = d'_k - C'_k x_next - W'_k x_sep).  All S sweeps run concurrently (one producer group + one
+// consumer group each) over ~n/Q rows.  The two sweeps that END at a separator contribute their halves of its block
+// row; substituting their last rows gives a block-tridiagonal system in the Q - 1 separator unknowns, solved
+// redundantly by every group (<= 4 block rows).  Back substitution then runs concurrently again: an outer sweep
+// recovers all its rows, the two sweeps of an interior sub-domain recover the half nearest their end separator
+// (only those rows' factors are stored).  Work: ~1.6x the assembly and ~2.6x the elimination at S = 8 for a 2.5x
+// shorter chain -- chosen only when the batch leaves SMs idle (gmpnp_newton_opts.partitions).
+// NumPy prototype of the algebra: tests/studies/partitioned_thomas_prototype.py.
+constexpr int NSEP_MAX = 4;                 // separators per CTA (S = 4: 2 problems x 2; S = 8: 1 problem x 4)
+constexpr int SEP_PART = 0, SEP_SPIKE = 112, SEP_FRAW = 224, SEP_RED = 240, SEP_XS = 296, SEP_REC = 304;
+constexpr int PART_SCRATCH = 64;            // per CTA: reduction scratch of the problem-wide control values
+constexpr size_t PART_SMEM_DOUBLES = (size_t)NW_GROUPS * (SM_GROUP + SM_RING) + 2 * GMPNP_NPAR + NSEP_MAX * SEP_REC +
+                                     PART_SCRATCH + 8;
+constexpr int BAR_PROBLEM = 15;             // S = 8: the two consumer warps of a problem meet here
+
+struct Sweep {
+    int first, dir, rows, rows_max, off;   // off = rows_max - rows (0 or 1): idle iterations at the start of the uniform loop
+    int bs0;                               // back substitution covers sweep rows [bs0, rows)
+    int pre;                               // 1: starts next to a separator (carries the spike; integrates the separator cell first)
+    int si_start, si_end;                  // separator index at the start (-1: domain boundary) and at the end of the sweep
+    int half_end;                          // half of the end separator's record this sweep fills: 0 arrives from above, 1 from below
+    int sep_end;                           // node index of the end separator
+};
+
+template <int S>
+__device__ __forceinline__ void sweep_layout(int n, int j, Sweep& w) {
+    constexpr int Q = S / 2 + 1;
+    const int inner = n - (Q - 1), base = inner / Q, rem = inner % Q;
+    int q, dir;
+    if (j == 0) { q = 0; dir = 1; }
+    else if (j == S - 1) { q = Q - 1; dir = -1; }
+    else { q = (j + 1) >> 1; dir = (j & 1) ? 1 : -1; }
+    const int rows = base + (q < rem ? 1 : 0);
+    const int a = q * base + min(q, rem) + q, b = a + rows - 1;
+    w.dir = dir; w.rows = rows; w.first = dir > 0 ? a : b;
+    w.rows_max = base + (rem > 0 ? 1 : 0);
+    w.off = w.rows_max - rows;
+    const bool outer = (j == 0) || (j == S - 1);
+    w.pre = outer ? 0 : 1;
+    if (dir > 0) { w.si_start = outer ? -1 : q - 1; w.si_end = q; w.half_end = 0; w.sep_end = b + 1; }
+    else { w.si_start = outer ? -1 : q; w.si_end = q - 1; w.half_end = 1; w.sep_end = a - 1; }
+    const int h = rows >> 1;
+    w.bs0 = outer ? 0 : (dir > 0 ? h : rows - h);
+}
+
+template <int S>
+__device__ __forceinline__ void problem_sync() {
+    if (S == 8) bar_sync(BAR_PROBLEM);
+    else __syncwarp();
+}
+
+// eliminate_row with a spike block: W (lane c < 7: column c) is one more right-hand-side block of the row.
+//   spike_init : first row next to a separator -- its sub-diagonal block couples to the separator unknown: W = A
+//   otherwise  : W = -A Wp (Wp = eliminated spike of the previous row), B -= A X_C, d -= A X_d as in eliminate_row
+template <bool PIVOT>
+__device__ __forceinline__ void eliminate_row_w(const Group& g, const double* __restrict__ sA, bool spike_init,
+                                                double (&B)[NC], double (&Y)[NC], double (&W)[NC], const double (&X)[NC],
+                                                const double (&Wp)[NC], int& singular) {
+    const int c = g.c;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) W[i] = 0.0;
+    if (sA != nullptr) {
+        if (spike_init) {
+            if (c < NC) {
+#pragma unroll
+                for (int i = 0; i < NC; ++i) W[i] = sA[i * 8 + c];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                const double2* row = reinterpret_cast<const double2*>(sA + i * 8);
+                const double2 a0 = row[0], a1 = row[1], a2 = row[2], a3 = row[3];
+                const double t = a0.x * X[0] + a0.y * X[1] + a1.x * X[2] + a1.y * X[3] + a2.x * X[4] + a2.y * X[5] + a3.x * X[6];
+                const double tw = a0.x * Wp[0] + a0.y * Wp[1] + a1.x * Wp[2] + a1.y * Wp[3] + a2.x * Wp[4] + a2.y * Wp[5] + a3.x * Wp[6];
+                if (c < NC) { B[i] -= t; W[i] = -tw; }
+                else Y[i] -= t;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        double pc[NC];
+        {
+            double2* pcs = reinterpret_cast<double2*>(g.sm + SM_PC + (j & 1) * 8);
+            if (c == j) {
+                pcs[0] = make_double2(B[0], B[1]); pcs[1] = make_double2(B[2], B[3]);
+                pcs[2] = make_double2(B[4], B[5]); pcs[3] = make_double2(B[6], 0.0);
+            }
+            __syncwarp();
+            const double2 p0 = pcs[0], p1 = pcs[1], p2 = pcs[2], p3 = pcs[3];
+            pc[0] = p0.x; pc[1] = p0.y; pc[2] = p1.x; pc[3] = p1.y; pc[4] = p2.x; pc[5] = p2.y; pc[6] = p3.x;
+        }
+        if (PIVOT) {
+            int p = j;
+            double best = fabs(pc[j]);
+#pragma unroll
+            for (int i = j + 1; i < NC; ++i) {
+                const double a = fabs(pc[i]);
+                if (a > best) { best = a; p = i; }
+            }
+            if (p != j) {
+#pragma unroll
+                for (int i = j + 1; i < NC; ++i) {
+                    const bool sw = (p == i);
+                    const double tp = pc[j], tb = B[j], ty = Y[j], tw = W[j];
+                    pc[j] = sw ? pc[i] : tp; pc[i] = sw ? tp : pc[i];
+                    B[j] = sw ? B[i] : tb;   B[i] = sw ? tb : B[i];
+                    Y[j] = sw ? Y[i] : ty;   Y[i] = sw ? ty : Y[i];
+                    W[j] = sw ? W[i] : tw;   W[i] = sw ? tw : W[i];
+                }
+            }
+        }
+        const double piv = pc[j];
+        const double inv = fast_rcp(piv);
+        if (!(fabs(piv) > 0.0) || !isfinite(inv)) singular = 1;
+        const double bj = B[j] * inv, yj = Y[j] * inv, wj = W[j] * inv;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            if (i == j) continue;
+            B[i] -= pc[i] * bj;
+            Y[i] -= pc[i] * yj;
+            W[i] -= pc[i] * wj;
+        }
+        B[j] = bj; Y[j] = yj; W[j] = wj;
+    }
+}
+
+// Producer of one sweep of the partitioned factorisation.  The loop counter `it` is uniform over the warp
+// (it = -1 .. rows_max-1); the sweep's own row is r = it - off, it integrates the cell ahead of row r for r >= -pre
+// (r = -1: the cell between its start separator and its first row, whose (1,0)/(1,1) blocks and residual row open row 0).
+template <int NQJ>
+__device__ void producer_sweep_part(const Group& g, const LaneConst& L, const Sweep& w, const double* __restrict__ x, int n,
+                                    const double* __restrict__ up, const double* __restrict__ unp) {
+    const double* P = g.P;
+    const int c = g.c;
+    double* sF = g.sm + SM_M;
+    const bool use_un = (P[GMPNP_P_KAPPA] != 0.0);
+    const double qscale = P[GMPNP_P_Q], prow = 1.0 / qscale;
+    double* fu = g.ring;
+    double* fn = g.ring + RING * 8;
+    const int dir = w.dir, node0 = w.first - dir * w.pre;        // first staged node (the start separator when pre)
+    auto issue = [&](int j) {
+        const int node = node0 + dir * j;
+        if (node >= 0 && node < n) {
+            const int s8 = (j & (RING - 1)) * 8;
+            if (c < NC) {
+                cp_async8(fu + s8 + c, up + (long)node * NC + c);
+                if (use_un) cp_async8(fn + s8 + c, unp + (long)node * NC + c);
+            } else {
+                cp_async8(fn + s8 + 7, x + node);
+            }
+        }
+        cp_async_commit();
+    };
+    if (c == 7) {
+#pragma unroll
+        for (int j = 0; j < RING; ++j) fu[j * 8 + 7] = 1.0;
+    }
+#pragma unroll
+    for (int j = 0; j < RING; ++j) issue(j);
+    double f1_behind = 0.0, rsq = 0.0;
+    int t = 0;                                       // staged-sequence index of the current node
+    for (int it = -1; it < w.rows_max; ++it) {
+        const int r = it - w.off;                    // this sweep's row (r < -pre: idle)
+        const int slot = (it < 0) ? 0 : it % NSLOT;
+        const int nslot = (it + 1) % NSLOT;
+        double* qs = g.q + slot * Q_SLOT;
+        double* qn = g.q + nslot * Q_SLOT;
+        if (it >= 2) bar_sync(g.bar + NSLOT + nslot);            // the consumers are done with iteration it-2 (slot nslot)
+        if (r >= -w.pre) {
+            const int s0 = (t & (RING - 1)) * 8, s1 = ((t + 1) & (RING - 1)) * 8;
+            const int k = w.first + dir * r;         // current node (the separator itself for r = -1)
+            cp_async_wait<RING - 2>();
+            __syncwarp(g.mask);
+            {
+                double U0[NC], U1[NC];
+                {
+                    const double2* q = reinterpret_cast<const double2*>(fu + s0);
+                    const double2 q0 = q[0], q1 = q[1], q2 = q[2];
+                    U0[0] = q0.x; U0[1] = q0.y; U0[2] = q1.x; U0[3] = q1.y; U0[4] = q2.x; U0[5] = q2.y; U0[6] = fu[s0 + 6];
+                    const double2* ww = reinterpret_cast<const double2*>(fu + s1);
+                    const double2 w0 = ww[0], w1 = ww[1], w2 = ww[2];
+                    U1[0] = w0.x; U1[1] = w0.y; U1[2] = w1.x; U1[3] = w1.y; U1[4] = w2.x; U1[5] = w2.y; U1[6] = fu[s1 + 6];
+                }
+                const double h = fabs(fn[s1 + 7] - fn[s0 + 7]);
+                const double myU0 = fu[s0 + c], myU1 = fu[s1 + c];
+                const double myN0 = (c < NC && use_un) ? fn[s0 + c] : 0.0, myN1 = (c < NC && use_un) ? fn[s1 + c] : 0.0;
+                CellCols cc;
+                cell_columns<NQJ, true>(P, fu + s0, fu + s1, L, c, h, prow, U0, U1, myU0, myU1, myN0, myN1, cc, qn + Q_A, qn + Q_B);
+                if (r >= 0) {
+                    if (r > 0 || w.pre) {            // a cell behind exists: its (1,1) block is in the slot already
+#pragma unroll
+                        for (int i = 0; i < NC; ++i) {
+                            qs[Q_B + i * 8 + c] += cc.c00[i];
+                            qs[Q_C + i * 8 + c] = cc.c01[i];
+                        }
+                    } else {
+                        const bool dir_all = (k == n - 1), dir_pot = (k == 0);
+#pragma unroll
+                        for (int i = 0; i < NC; ++i) {
+                            double bv = cc.c00[i], cv = cc.c01[i];
+                            if (dir_all || (dir_pot && i == NS)) { bv = (i == c) ? 1.0 : 0.0; cv = 0.0; }
+                            qs[Q_B + i * 8 + c] = bv;
+                            qs[Q_C + i * 8 + c] = cv;
+                        }
+                    }
+                    sF[c] = f1_behind + cc.f0;
+                }
+                f1_behind = cc.f1;
+            }
+            __syncwarp(g.mask);
+            if (r >= 0 && c == 7) {
+                double Y[NC];
+#pragma unroll
+                for (int i = 0; i < NC; ++i) Y[i] = sF[i];
+                double pscale = qscale;
+                if (r == 0 && !w.pre) {
+#pragma unroll
+                    for (int i = 0; i < NS; ++i) Y[i] += P[GMPNP_P_JFLUX + i];
+                    if (k == n - 1) {
+#pragma unroll
+                        for (int i = 0; i < NC; ++i) Y[i] = fu[s0 + i] - ((i < NS) ? 1.0 : 0.0);
+                    }
+                    if (k == 0) Y[NS] = fu[s0 + NS] - P[GMPNP_P_V];
+                    pscale = 1.0;
+                }
+                if (r >= w.bs0) {                    // every row is counted once: by the sweep that back-substitutes it
+#pragma unroll
+                    for (int i = 0; i < NS; ++i) rsq += Y[i] * Y[i];
+                    const double yp = Y[NS] * pscale;
+                    rsq += yp * yp;
+                }
+#pragma unroll
+                for (int i = 0; i < NC; ++i) qs[Q_D(i)] = Y[i];
+            }
+            __syncwarp(g.mask);
+            issue(t + RING);
+            ++t;
+        }
+        if (it >= 0) bar_arrive(g.bar + slot);       // iteration `it` is complete for this group (idle or not)
+    }
+    cp_async_wait<0>();
+    __syncwarp(g.mask);
+    {
+        double* qs = g.q + (w.rows_max % NSLOT) * Q_SLOT;        // closing slot
+        if (c < NC) qs[Q_D(c)] = f1_behind;
+        if (c == 7) qs[Q_C + 7] = rsq;
+        bar_arrive(g.bar + w.rows_max % NSLOT);
+    }
+}
+
+// Consumer of one sweep of the partitioned factorisation; returns the closing slot.  X / Wp return the eliminated
+// coupling column (lanes < 7) / right-hand side (lane 7) and the eliminated spike column of the sweep's last row.
+template <bool PIVOT>
+__device__ int consumer_sweep_part(const Group& g, const Sweep& w, double* __restrict__ ws, double* __restrict__ ws2,
+                                   double (&X)[NC], double (&Wp)[NC], int& singular) {
+    const int c = g.c;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) { X[i] = 0.0; Wp[i] = 0.0; }
+    for (int it = 0; it < w.rows_max; ++it) {
+        const int r = it - w.off;
+        const int slot = it % NSLOT;
+        double* qs = g.q + slot * Q_SLOT;
+        bar_sync(g.bar + slot);
+        double B[NC], Y[NC], W[NC];
+        const bool real = r >= 0;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            B[i] = real ? qs[Q_B + i * 8 + c] : ((i == c) ? 1.0 : 0.0);
+            Y[i] = real ? ((c < NC) ? qs[Q_C + i * 8 + c] : qs[Q_D(i)]) : 0.0;
+        }
+        int sing = 0;
+        eliminate_row_w<PIVOT>(g, (real && (r > 0 || w.pre)) ? qs + Q_A : nullptr, real && r == 0 && w.pre, B, Y, W, X, Wp, sing);
+        if (it + 2 < w.rows_max) bar_arrive(g.bar + NSLOT + slot);
+        if (real) {
+            singular |= sing;
+            if (r >= w.bs0 && g.live) {
+                const int k = w.first + w.dir * r;
+                double* o1 = ws + (long)k * 56;
+                double* o2 = ws2 + (long)k * 56;
+#pragma unroll
+                for (int i = 0; i < NC; ++i) { o1[i * 8 + c] = Y[i]; o2[i * 8 + c] = W[i]; }
+            }
+#pragma unroll
+            for (int i = 0; i < NC; ++i) { X[i] = Y[i]; Wp[i] = W[i]; }
+        }
+    }
+    const int cslot = w.rows_max % NSLOT;
+    bar_sync(g.bar + cslot);
+    return cslot;
+}
+
+// Back substitution of one sweep: rows r = rows-1 .. bs0 (from its end separator backwards),
+// x_k = d'_k - C'_k x_next - W'_k x_S; updates u and accumulates max|dx|, max|u|.  cnt_max: uniform trip count.
+__device__ void backward_sweep_part(const Group& g, const Sweep& w, int cnt_max, bool store, double (&xn)[NC],
+                                    const double (&xS)[NC], double* __restrict__ up, const double* __restrict__ ws,
+                                    const double* __restrict__ ws2, double relax, double& mdx, double& mu) {
+    const int c = g.c;
+    const int cnt = w.rows - w.bs0;
+    const int start = w.first + w.dir * (w.rows - 1), dir = -w.dir;
+    double2* bwc = reinterpret_cast<double2*>(g.ring) + c;     // [RING][4][8]: lane c's row of (C' | d')
+    double* buc = g.ring + RING * 64 + c;                      // [RING][8]:    lane c's component of u
+    double2* bw2 = reinterpret_cast<double2*>(g.q) + c;        // [RING][4][8]: lane c's row of W' (queue memory, idle now)
+    double* sx = g.sm + SM_X;
+    const double* wsrc = ws + (long)start * 56 + c * 8;
+    const double* w2src = ws2 + (long)start * 56 + c * 8;
+    const double* usrc = up + (long)start * NC + c;
+    double* udst = up + (long)start * NC + c;
+    const long wstep = (long)dir * 56, ustep = (long)dir * NC;
+    int staged = 0;
+    auto issue = [&](int s) {
+        if (staged < cnt && c < NC) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                cp_async16(bwc + (s * 4 + v) * 8, wsrc + 2 * v);
+                cp_async16(bw2 + (s * 4 + v) * 8, w2src + 2 * v);
+            }
+            cp_async8(buc + s * 8, usrc);
+        }
+        cp_async_commit();
+        wsrc += wstep; w2src += wstep; usrc += ustep; ++staged;
+    };
+#pragma unroll
+    for (int s = 0; s < RING; ++s) issue(s);
+    for (int q0 = 0; q0 < cnt_max; q0 += RING) {
+#pragma unroll
+        for (int s = 0; s < RING; ++s) {
+            if (q0 + s < cnt_max) {
+                cp_async_wait<RING - 1>();
+                double xi = 0.0;
+                if (c < NC && q0 + s < cnt) {
+                    const double2 r0 = bwc[(s * 4 + 0) * 8], r1 = bwc[(s * 4 + 1) * 8];
+                    const double2 r2 = bwc[(s * 4 + 2) * 8], r3 = bwc[(s * 4 + 3) * 8];
+                    const double2 v0 = bw2[(s * 4 + 0) * 8], v1 = bw2[(s * 4 + 1) * 8];
+                    const double2 v2 = bw2[(s * 4 + 2) * 8], v3 = bw2[(s * 4 + 3) * 8];
+                    const double ucur = buc[s * 8];
+                    xi = r3.y;
+                    xi -= r0.x * xn[0]; xi -= r0.y * xn[1]; xi -= r1.x * xn[2]; xi -= r1.y * xn[3];
+                    xi -= r2.x * xn[4]; xi -= r2.y * xn[5]; xi -= r3.x * xn[6];
+                    xi -= v0.x * xS[0]; xi -= v0.y * xS[1]; xi -= v1.x * xS[2]; xi -= v1.y * xS[3];
+                    xi -= v2.x * xS[4]; xi -= v2.y * xS[5]; xi -= v3.x * xS[6];
+                    const double un = ucur - relax * xi;
+                    if (store) *udst = un;
+                    mdx = fmax(mdx, fabs(xi));
+                    mu = fmax(mu, fabs(un));
+                }
+                udst += ustep;
+                issue(s);
+                double* sxq = sx + (s & 1) * 8;
+                sxq[c] = xi;
+                __syncwarp();
+                const double2* xs = reinterpret_cast<const double2*>(sxq);
+                const double2 a0 = xs[0], a1 = xs[1], a2 = xs[2];
+                xn[0] = a0.x; xn[1] = a0.y; xn[2] = a1.x; xn[3] = a1.y; xn[4] = a2.x; xn[5] = a2.y; xn[6] = sxq[6];
+            }
+        }
+    }
+    cp_async_wait<0>();
+    __syncwarp();
+}
+
+// per-problem shared data of the partitioned kernel
+struct Part {
+    double* sep;      // separator records of this problem [Q-1][SEP_REC]
+    double* scratch;  // [PART_SCRATCH / problems] reduction scratch
+    int j;            // sweep index of this group inside the problem
+    int lp, nlp;      // lane index among the problem's consumer lanes, their number
+};
+
+// Factorisation of one problem with S sweeps; returns ||b||^2; xE / xS return the solution at the sweep's end / start
+// separator.  Executed by all consumer lanes of the problem in lock step.
+template <bool PIVOT, int S>
+__device__ double factor_problem_part(const Group& g, const Sweep& w, const Part& pt, double* ws, double* ws2,
+                                      double (&xE)[NC], double (&xS)[NC], int& singular, int* cmd) {
+    constexpr int NSEP = S / 2;
+    const int c = g.c;
+    double X[NC], Wp[NC];
+    problem_sync<S>();          // all consumer groups of the problem are done with the previous phase (u, scratch, records)
+    if ((threadIdx.x & 31) == 0) *cmd = CMD_FACTOR;
+    bar_sync(g.bar + 2 * NSLOT);
+    int sing = 0;
+    const int cslot = consumer_sweep_part<PIVOT>(g, w, ws, ws2, X, Wp, sing);
+    const double* qc = g.q + cslot * Q_SLOT;
+    // this sweep's half of its end separator's block row: (1,1) block and residual row of its last cell, minus the
+    // (1,0) block times the last eliminated row; the spike part couples the separator to the sweep's start separator
+    {
+        double* rec = pt.sep + w.si_end * SEP_REC;
+        double* part = rec + SEP_PART + w.half_end * 56;
+        double* spk = rec + SEP_SPIKE + w.half_end * 56;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            const double2* row = reinterpret_cast<const double2*>(qc + Q_A + i * 8);
+            const double2 a0 = row[0], a1 = row[1], a2 = row[2], a3 = row[3];
+            const double t = a0.x * X[0] + a0.y * X[1] + a1.x * X[2] + a1.y * X[3] + a2.x * X[4] + a2.y * X[5] + a3.x * X[6];
+            const double tw = a0.x * Wp[0] + a0.y * Wp[1] + a1.x * Wp[2] + a1.y * Wp[3] + a2.x * Wp[4] + a2.y * Wp[5] + a3.x * Wp[6];
+            part[i * 8 + c] = ((c < NC) ? qc[Q_B + i * 8 + c] : qc[Q_D(i)]) - t;
+            spk[i * 8 + c] = (c < NC) ? -tw : 0.0;
+        }
+        if (c < NC) rec[SEP_FRAW + w.half_end * 8 + c] = qc[Q_D(c)];
+        if (c == 7) { pt.scratch[pt.j] = qc[Q_C + 7]; pt.scratch[S + pt.j] = (double)sing; }
+    }
+    problem_sync<S>();
+    // reduced block-tridiagonal system in the separator unknowns, solved redundantly by every group
+    {
+        double XX[NC];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) XX[i] = 0.0;
+        int sing_r = 0;
+        for (int si = 0; si < NSEP; ++si) {
+            const double* rec = pt.sep + si * SEP_REC;
+            double B[NC], Y[NC];
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                const double dsum = rec[SEP_PART + i * 8 + c] + rec[SEP_PART + 56 + i * 8 + c];
+                B[i] = (c < NC) ? dsum : 0.0;
+                Y[i] = (c < NC) ? rec[SEP_SPIKE + 56 + i * 8 + c] : dsum;      // coupling to the NEXT separator / rhs
+            }
+            eliminate_row<PIVOT>(g, si > 0 ? rec + SEP_SPIKE : nullptr, B, Y, XX, sing_r);
+#pragma unroll
+            for (int i = 0; i < NC; ++i) XX[i] = Y[i];
+            if (pt.j == 0) {
+                double* red = pt.sep + si * SEP_REC + SEP_RED;
+#pragma unroll
+                for (int i = 0; i < NC; ++i) red[i * 8 + c] = Y[i];
+            }
+        }
+        sing |= sing_r;
+    }
+    problem_sync<S>();
+    double xs[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) { xs[i] = 0.0; xE[i] = 0.0; xS[i] = 0.0; }
+    for (int si = NSEP - 1; si >= 0; --si) {
+        const double* red = pt.sep + si * SEP_REC + SEP_RED;
+        double xv[NC];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            double v = red[i * 8 + 7];
+            if (si < NSEP - 1) {
+#pragma unroll
+                for (int jj = 0; jj < NC; ++jj) v -= red[i * 8 + jj] * xs[jj];
+            }
+            xv[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            xs[i] = xv[i];
+            if (si == w.si_end) xE[i] = xv[i];
+            if (si == w.si_start) xS[i] = xv[i];
+        }
+        if (pt.j == 0 && c == 0) {
+            double* o = pt.sep + si * SEP_REC + SEP_XS;
+#pragma unroll
+            for (int i = 0; i < NC; ++i) o[i] = xv[i];
+        }
+    }
+    // ||b||^2: rows counted once by the sweep that back-substitutes them + the raw separator rows
+    double rsq = 0.0, sflag = (double)sing;
+#pragma unroll
+    for (int jj = 0; jj < S; ++jj) { rsq += pt.scratch[jj]; sflag += pt.scratch[S + jj]; }
+    const double qscale = g.P[GMPNP_P_Q];
+    for (int si = 0; si < NSEP; ++si) {
+        const double* rec = pt.sep + si * SEP_REC;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            double d = rec[SEP_FRAW + i] + rec[SEP_FRAW + 8 + i];
+            if (i == NS) d *= qscale;
+            rsq += d * d;
+        }
+    }
+    singular |= (sflag != 0.0);
+    return rsq;
+}
+
+// Back substitution of all sweeps, separator updates, problem-wide max|dx|, max|u|.
+template <int S>
+__device__ void solve_problem_part(const Group& g, const Sweep& w, const Part& pt, const double (&xE)[NC],
+                                   const double (&xS)[NC], double* up, const double* ws, const double* ws2, double relax,
+                                   bool store, double& dxmax, double& umax) {
+    double xn[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) xn[i] = xE[i];
+    double mdx = 0.0, mu = 0.0;
+    // the sweep that arrives at a separator from above updates the separator node itself
+    if (w.half_end == 0 && g.c < NC) {
+        double xi = xE[0];
+#pragma unroll
+        for (int i = 1; i < NC; ++i) if (i == g.c) xi = xE[i];
+        const double un = up[(long)w.sep_end * NC + g.c] - relax * xi;
+        if (store) up[(long)w.sep_end * NC + g.c] = un;
+        mdx = fabs(xi); mu = fabs(un);
+    }
+    backward_sweep_part(g, w, w.rows_max, store, xn, xS, up, ws, ws2, relax, mdx, mu);
+#pragma unroll
+    for (int o = 4; o >= 1; o >>= 1) {
+        mdx = fmax(mdx, __shfl_xor_sync(0xffffffffu, mdx, o));
+        mu = fmax(mu, __shfl_xor_sync(0xffffffffu, mu, o));
+    }
+    problem_sync<S>();                               // previous readers of the scratch are done
+    if (g.c == 0) { pt.scratch[2 * S + pt.j] = mdx; pt.scratch[3 * S + pt.j] = mu; }
+    problem_sync<S>();
+    mdx = 0.0; mu = 0.0;
+#pragma unroll
+    for (int jj = 0; jj < S; ++jj) { mdx = fmax(mdx, pt.scratch[2 * S + jj]); mu = fmax(mu, pt.scratch[3 * S + jj]); }
+    dxmax = mdx; umax = mu;
+}
+
+template <bool PIVOT, int S>
+__device__ NewtonOut newton_solve_part(const Group& g, const Sweep& w, const Part& pt, double* up, double* ws, double* ws2,
+                                       const gmpnp_newton_opts& o, bool enabled, int* cmd) {
+    NewtonOut out;
+    int singular = 0;
+    double xE[NC], xS[NC];
+    double rsq = factor_problem_part<PIVOT, S>(g, w, pt, ws, ws2, xE, xS, singular, cmd);
+    double r = sqrt(rsq);
+    out.r0 = r;
+    int k = 0;
+    bool conv = (o.criterion == 0) ? (r < o.atol) : false;
+    bool bad = !isfinite(r) || singular;
+    bool stag = false;
+    double dx_prev = INFINITY, dx_rel = INFINITY;
+    bool active = enabled && !conv && !bad && k < o.maxit;
+    while (active) {                                 // every consumer lane of the problem takes the same decisions
+        double dxmax, umax;
+        solve_problem_part<S>(g, w, pt, xE, xS, up, ws, ws2, o.relax, true, dxmax, umax);
+        ++k;
+        if (o.criterion == 1) {
+            const double scale = fmax(1.0, umax);
+            conv = dxmax <= o.xtol * scale;
+            if (!conv && o.xtol_floor > 0.0 && k >= 3 && dxmax <= o.xtol_floor * scale && dxmax >= 0.25 * dx_prev)
+                stag = true;
+            dx_prev = dxmax;
+            dx_rel = dxmax / scale;
+            if (!isfinite(dxmax)) bad = true;
+            if (conv || bad || stag) break;          // dolfin-like: no re-assembly after an increment stop
+        }
+        problem_sync<S>();                           // all u updates of the problem before the re-assembly
+        int sing2 = 0;
+        const double rsq2 = factor_problem_part<PIVOT, S>(g, w, pt, ws, ws2, xE, xS, sing2, cmd);
+        r = sqrt(rsq2);
+        if (!isfinite(r) || sing2) bad = true;
+        if (o.criterion == 0) conv = (r / out.r0 < o.rtol) || (r < o.atol);
+        active = !conv && !bad && k < o.maxit;
+    }
+    out.iters = k;
+    out.r = r;
+    out.dx = dx_rel;
+    out.status = bad ? GMPNP_NOT_FINITE : (conv ? GMPNP_CONVERGED : (stag ? GMPNP_STAGNATED : GMPNP_MAXIT));
+    return out;
+}
+
+// Partitioned variant of newton1d_kernel: same modes and outputs, S sweeps per problem (8 / S problems per CTA).
+template <bool PIVOT, int NQJ, int S>
+__global__ void __launch_bounds__(NW_THREADS, GMPNP_NEWTON_MIN_BLOCKS)
+newton1d_part_kernel(int mode, int batch, int n, const double* __restrict__ x, const double* __restrict__ params,
+                     double* __restrict__ u, double* __restrict__ un_rw, const double* __restrict__ un_ro,
+                     double* __restrict__ wsall, double* __restrict__ ws2all, gmpnp_newton_opts opts, int n_stage,
+                     const double* __restrict__ Vpath, double* __restrict__ hist, int* __restrict__ iters,
+                     double* __restrict__ r0out, double* __restrict__ rout, double* __restrict__ hfrac_out,
+                     int* __restrict__ stage_out, int* __restrict__ status) {
+    static_assert(S == 4 || S == 8, "sweeps per problem");
+    constexpr int PPB = 8 / S;                                  // problems per CTA
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool producer = warp >= NW_PAIRS;
+    const int wp = producer ? warp - NW_PAIRS : warp;
+    Group g;
+    g.c = lane & 7; g.base = lane & ~7; g.mask = 0xFFu << g.base;
+    g.half = 0; g.pbase = 0; g.pmask = 0; g.psm = nullptr; g.su = nullptr;
+    const int gid = wp * 4 + (lane >> 3);
+    g.sm = smem + gid * SM_GROUP;
+    g.q = g.sm + SM_Q;
+    g.ring = smem + NW_GROUPS * SM_GROUP + gid * SM_RING;
+    const int pl = (S == 4) ? wp : 0;                           // problem slot inside the CTA
+    double* tail = smem + NW_GROUPS * (SM_GROUP + SM_RING);
+    g.P = tail + pl * GMPNP_NPAR;
+    g.bar = 1 + wp * BAR_PER_PAIR;
+    Part pt;
+    pt.sep = tail + 2 * GMPNP_NPAR + pl * (S / 2) * SEP_REC;
+    pt.scratch = tail + 2 * GMPNP_NPAR + NSEP_MAX * SEP_REC + pl * (PART_SCRATCH / 2);
+    pt.j = (S == 4) ? (lane >> 3) : gid;
+    pt.lp = (S == 4) ? lane : wp * 32 + lane;
+    pt.nlp = (S == 4) ? 32 : 64;
+    int* cmd = reinterpret_cast<int*>(tail + 2 * GMPNP_NPAR + NSEP_MAX * SEP_REC + PART_SCRATCH) + wp;
+    int prob = blockIdx.x * PPB + pl;
+    g.live = prob < batch;
+    if (!g.live) prob = batch - 1;
+    Sweep w;
+    sweep_layout<S>(n, pt.j, w);
+    double* up = u + (long)prob * n * NC;
+    if (producer) {
+        const double* unp = (mode == 0) ? un_ro + (long)prob * n * NC : (mode == 1) ? un_rw + (long)prob * n * NC : up;
+        LaneConst L;
+        bool have_L = false;
+        while (true) {
+            bar_sync(g.bar + 2 * NSLOT);
+            if (*cmd == CMD_EXIT) break;
+            if (!have_L) { lane_consts(g.P, g.c, L); have_L = true; }
+            producer_sweep_part<NQJ>(g, L, w, x, n, up, unp);
+        }
+        return;
+    }
+    // ---- consumer warps: parameter record of the problem, control, elimination, back substitution ------------------
+    {
+        double* P = const_cast<double*>(g.P);
+        for (int i = pt.lp; i < GMPNP_NPAR; i += pt.nlp) P[i] = params[(long)prob * GMPNP_NPAR + i];
+    }
+    problem_sync<S>();
+    double* P = const_cast<double*>(g.P);
+    double* ws = wsall + (long)prob * n * 56;
+    double* ws2 = ws2all + (long)prob * n * 56;
+    const bool writer = (pt.lp == 0 && g.live);
+    auto finish = [&]() {
+        if ((threadIdx.x & 31) == 0) *cmd = CMD_EXIT;
+        bar_sync(g.bar + 2 * NSLOT);
+    };
+    if (mode == 0) {
+        NewtonOut o = newton_solve_part<PIVOT, S>(g, w, pt, up, ws, ws2, opts, g.live, cmd);
+        if (writer) {
+            if (iters) iters[prob] = o.iters;
+            if (r0out) r0out[prob] = o.r0;
+            if (rout) rout[prob] = o.r;
+            if (status) status[prob] = o.status;
+        }
+        finish();
+        return;
+    }
+    if (mode == 1) {
+        double* unp = un_rw + (long)prob * n * NC;
+        double frac = P[GMPNP_P_HFRAC];
+        const double hohp = P[GMPNP_P_HOHP];
+        int st = GMPNP_CONVERGED, done = 0;
+        bool alive = g.live;
+        for (int s = 0; s < n_stage && alive; ++s) {
+            NewtonOut o = newton_solve_part<PIVOT, S>(g, w, pt, up, ws, ws2, opts, alive, cmd);
+            if (writer && iters) iters[(long)prob * n_stage + s] = o.iters;
+            if (o.status != GMPNP_CONVERGED) { st = o.status; alive = false; }
+            else ++done;
+            problem_sync<S>();
+            if (alive) {
+                for (long i = pt.lp; i < (long)n * NC; i += pt.nlp) {
+                    const double v = up[i];
+                    unp[i] = v;
+                    if (hist) hist[((long)prob * n_stage + s) * n * NC + i] = v;
+                }
+            }
+            problem_sync<S>();
+            if (alive && hohp >= 0.0) {
+                const double f = up[0];
+                if (f < 0) frac = frac / 1.1;
+                else if (f < (hohp - 0.05)) frac = frac / 1.05;
+                else if (f < (hohp - 0.025)) frac = frac / 1.01;
+                else if (f > hohp && f <= (hohp + 0.4) && frac <= 1.0) frac = frac * 1.04;
+                else if (f > (hohp + 0.4) && frac <= 1.0) frac = frac * 1.15;
+            }
+            problem_sync<S>();
+            if (writer && alive && hohp >= 0.0) {
+                P[GMPNP_P_JFLUX + 1] = -1.0 * P[GMPNP_P_JOHPRE] * (1 - frac);
+                P[GMPNP_P_JFLUX + 0] = P[GMPNP_P_JHPRE] * frac;
+            }
+            problem_sync<S>();
+        }
+        if (writer) {
+            if (status) status[prob] = st;
+            if (hfrac_out) hfrac_out[prob] = frac;
+            if (stage_out) stage_out[prob] = done;
+        }
+        finish();
+        return;
+    }
+    {
+        if (pt.lp == 0) P[GMPNP_P_KAPPA] = 0.0;
+        problem_sync<S>();
+        int st = GMPNP_CONVERGED, done = 0;
+        const double xtol_final = opts.xtol;
+        bool alive = g.live;
+        for (int s = 0; s < n_stage && alive; ++s) {
+            const double Vs = Vpath[(long)prob * n_stage + s];
+            if (isnan(Vs)) break;                       // ragged path: this problem is done
+            const bool final_stage = (s + 1 == n_stage) || isnan(Vpath[(long)prob * n_stage + s + 1]);
+            gmpnp_newton_opts o2 = opts;
+            o2.xtol = (final_stage || !(opts.xtol_path > 0.0)) ? xtol_final : opts.xtol_path;
+            problem_sync<S>();
+            if (pt.lp == 0) P[GMPNP_P_V] = Vs;
+            problem_sync<S>();
+            NewtonOut o = newton_solve_part<PIVOT, S>(g, w, pt, up, ws, ws2, o2, alive, cmd);
+            if (writer && iters) iters[(long)prob * n_stage + s] = o.iters;
+            if (writer && rout) rout[prob] = o.r;
+            if (writer && hfrac_out) hfrac_out[prob] = o.dx;
+            if (o.status == GMPNP_CONVERGED || o.status == GMPNP_STAGNATED) { ++done; st = o.status; }
+            else { st = o.status; alive = false; }
+        }
+        if (writer) {
+            if (status) status[prob] = st;
+            if (stage_out) stage_out[prob] = done;
+        }
+        finish();
+    }
+}
+
 // Materialised residual + block-tridiagonal Jacobian (gmpnp_assemble_1d): one group per
 // (problem, node row).  Used for kernel-parity tests against the oracle.
 __global__ void __launch_bounds__(THREADS)
@@ -1151,20 +1858,51 @@ static cudaError_t launch_newton_variant(gmpnp_handle* h, int blocks, size_t sme
     return cudaGetLastError();
 }
 
+template <bool PIV, int NQ, int S>
+static cudaError_t launch_part_variant(gmpnp_handle* h, int mode, double* d_u, double* d_un_rw, const double* d_un_ro,
+                                       const gmpnp_newton_opts* opts, int n_stage, const double* d_Vpath, double* d_hist,
+                                       int* d_iters, double* d_r0, double* d_r, double* d_hfrac, int* d_stage, int* d_status,
+                                       cudaStream_t st) {
+    using namespace edl1d;
+    const size_t smem = PART_SMEM_DOUBLES * sizeof(double);
+    const int ppb = 8 / S, blocks = (h->batch + ppb - 1) / ppb;
+    cudaError_t e = cudaFuncSetAttribute(newton1d_part_kernel<PIV, NQ, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    newton1d_part_kernel<PIV, NQ, S><<<blocks, NW_THREADS, smem, st>>>(mode, h->batch, h->n_nodes, h->d_x, h->d_params, d_u,
+        d_un_rw, d_un_ro, h->d_ws, h->d_ws2, *opts, n_stage, d_Vpath, d_hist, d_iters, d_r0, d_r, d_hfrac, d_stage, d_status);
+    return cudaGetLastError();
+}
+
 int edl1d_launch_newton(gmpnp_handle* h, int mode, double* d_u, double* d_un_rw, const double* d_un_ro,
                         const gmpnp_newton_opts* opts, int n_stage, const double* d_Vpath, double* d_hist,
                         int* d_iters, double* d_r0, double* d_r, double* d_hfrac, int* d_stage,
                         int* d_status, cudaStream_t st) {
     using namespace edl1d;
     GmpnpRange nvtx_range(mode == 0 ? "gmpnp:newton_1d" : mode == 1 ? "gmpnp:march_1d" : "gmpnp:steady_continuation_1d");
-    const int blocks = (h->batch + PROBLEMS_PER_BLOCK - 1) / PROBLEMS_PER_BLOCK;
-    const size_t smem = NEWTON_SMEM_DOUBLES * sizeof(double);
     const bool consistent = (opts->jac_rule == 1);
+    // sweeps per problem: 2 = two-sided elimination (throughput), 4 / 8 = partitioned elimination (latency; needs at
+    // least 3 rows per sweep).  0 = automatic: partition when this launch alone cannot fill the 148 SMs.
+    int S = opts->partitions;
+    if (S == 0) S = (h->batch * 4 <= 148) ? 8 : (h->batch * 2 <= 148) ? 4 : 2;
+    if (S != 2 && S != 4 && S != 8) return GMPNP_ERR_ARG;
+    while (S > 2 && h->n_nodes < 4 * (S / 2 + 1)) S >>= 1;
     cudaError_t e;
+    if (S == 2) {
+        const int blocks = (h->batch + PROBLEMS_PER_BLOCK - 1) / PROBLEMS_PER_BLOCK;
+        const size_t smem = NEWTON_SMEM_DOUBLES * sizeof(double);
 #define GMPNP_ARGS h, blocks, smem, mode, d_u, d_un_rw, d_un_ro, opts, n_stage, d_Vpath, d_hist, d_iters, d_r0, d_r, d_hfrac, d_stage, d_status, st
-    if (opts->pivot) e = consistent ? launch_newton_variant<true, 2>(GMPNP_ARGS) : launch_newton_variant<true, 3>(GMPNP_ARGS);
-    else             e = consistent ? launch_newton_variant<false, 2>(GMPNP_ARGS) : launch_newton_variant<false, 3>(GMPNP_ARGS);
+        if (opts->pivot) e = consistent ? launch_newton_variant<true, 2>(GMPNP_ARGS) : launch_newton_variant<true, 3>(GMPNP_ARGS);
+        else             e = consistent ? launch_newton_variant<false, 2>(GMPNP_ARGS) : launch_newton_variant<false, 3>(GMPNP_ARGS);
 #undef GMPNP_ARGS
+    } else {
+        if (!h->d_ws2) GMPNP_CUDA_TRY(h, cudaMalloc(&h->d_ws2, sizeof(double) * 56 * (size_t)h->n_nodes * h->batch));
+#define GMPNP_ARGS h, mode, d_u, d_un_rw, d_un_ro, opts, n_stage, d_Vpath, d_hist, d_iters, d_r0, d_r, d_hfrac, d_stage, d_status, st
+#define GMPNP_PART(PIV, NQ) (S == 4 ? launch_part_variant<PIV, NQ, 4>(GMPNP_ARGS) : launch_part_variant<PIV, NQ, 8>(GMPNP_ARGS))
+        if (opts->pivot) e = consistent ? GMPNP_PART(true, 2) : GMPNP_PART(true, 3);
+        else             e = consistent ? GMPNP_PART(false, 2) : GMPNP_PART(false, 3);
+#undef GMPNP_PART
+#undef GMPNP_ARGS
+    }
     h->launches++;
     GMPNP_CUDA_TRY(h, e);
     return GMPNP_OK;

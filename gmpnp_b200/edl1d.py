@@ -95,7 +95,9 @@ def solve_EDL(concentration_elec=0.1, model="MPNP", voltage_multiplier=-1.0, H2_
                                         current_H_frac=current_H_frac)
             p_stage.extras["H_OHP"] = H_OHP
             solver.set_params([p_stage])
-            out = solver.march(u, un, ns, NewtonOpts.reference_1d(), history=True)
+            o_ref = NewtonOpts.reference_1d()
+            o_ref.partitions = 0          # one problem: the partitioned elimination (8 sweeps) halves the latency
+            out = solver.march(u, un, ns, o_ref, history=True)
             status = int(out["status"][0])
             if status != 0:
                 raise RuntimeError("Newton solver did not converge (status %d)" % status)   # dolfin raises too
@@ -116,7 +118,9 @@ def solve_EDL(concentration_elec=0.1, model="MPNP", voltage_multiplier=-1.0, H2_
         u = solver1d.bulk_state(1, num_vertices, dev)
         nst = max(1, int(math.ceil(abs(voltage_multiplier) / 0.5 - 1e-12)))
         Vpath = (voltage_multiplier * np.arange(1, nst + 1) / nst)[None, :]
-        out = solver.steady(u, Vpath, NewtonOpts.steady(xtol=1e-12, xtol_path=1e-3, jac_rule=1))
+        o_st = NewtonOpts.steady(xtol=1e-12, xtol_path=1e-3, jac_rule=1)
+        o_st.partitions = 0
+        out = solver.steady(u, Vpath, o_st)
         if int(out["status"][0]) != 0:
             raise RuntimeError("steady Newton did not converge (status %d)" % int(out["status"][0]))
         hist_rows.append(u[0].cpu().numpy())

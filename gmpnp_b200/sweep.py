@@ -50,7 +50,7 @@ class Sweep1D:
 
     def __init__(self, points, device: int = 0, utilities_dir=None, dv_max: float = 0.5,
                  xtol: float = 1e-10, xtol_path: float = 1e-1, maxit: int = 50, jac_rule: int = 1,
-                 pivot: int = 0, xtol_floor: float = 1e-8):
+                 pivot: int = 0, xtol_floor: float = 1e-8, partitions: int | None = None):
         """``pivot``: partial pivoting inside the 7x7 blocks of the block-Thomas elimination.  The sweep default is
         0: with the Poisson row equilibrated the in-block pivot is the diagonal in 99.95 % of the steps, and a
         Newton iteration that converges (increment criterion, residual evaluated independently of the linear
@@ -70,6 +70,10 @@ class Sweep1D:
         self.device = torch.device("cuda", int(device))
         self.dv_max, self.xtol, self.xtol_path, self.maxit = dv_max, xtol, xtol_path, maxit
         self.jac_rule, self.pivot, self.xtol_floor = jac_rule, pivot, xtol_floor
+        # sweeps per problem (gmpnp_newton_opts.partitions): the two-sided elimination is the throughput form; when the
+        # points of this rank leave the GPU idle (strong scaling: a shard of the sweep), the partitioned elimination
+        # shortens the critical path of the long problems at the price of ~2x the work
+        self.partitions = partitions          # None: automatic per mesh group (see _auto_partitions); int or callable(n, batch)
         self.groups = []
         by_mesh = {}
         for i, p in enumerate(self.points):
@@ -103,6 +107,22 @@ class Sweep1D:
         o = NewtonOpts.steady(xtol=self.xtol, maxit=self.maxit, xtol_path=self.xtol_path, jac_rule=self.jac_rule,
                               xtol_floor=self.xtol_floor)
         o.pivot = self.pivot if pivot is None else pivot
+        o.partitions = 2
+        return o
+
+    def _auto_partitions(self, n_nodes: int, batch: int) -> int:
+        """Sweeps per problem for one mesh group.  The critical path of a launch is (Newton iterations of its longest
+        path) x (rows per sweep); the partitioned elimination shortens it 2.5x (8 sweeps) at ~2x the work, which pays
+        only when this rank's points leave the GPU idle.  Measured on a B200 (tools/part_time.py, config-2 shards):
+        960 points 109.8 -> 61.6 ms, 1920 points 121.0 -> 102.7 ms, 3840 points 135.4 -> 199.7 ms; mixing (8 for the long
+        meshes only) is slower than 8 everywhere."""
+        if self.partitions is not None:
+            return int(self.partitions(n_nodes, batch)) if callable(self.partitions) else int(self.partitions)
+        return 8 if self.n_points <= 2400 else 2
+
+    def group_opts(self, g, pivot=None):
+        o = self.opts(pivot)
+        o.partitions = self._auto_partitions(g["solver"].n, g["solver"].batch)
         return o
 
     # -- device-resident solve (inputs already in HBM) -----------------------------------------
@@ -119,7 +139,6 @@ class Sweep1D:
         converged steady solution.  One launch per mesh, on concurrent streams.  ``host_out`` (one pinned host
         tensor per mesh group, shaped like the group's ``u``): the solution profiles are copied back on the
         group's own stream as soon as its launch finishes, overlapping the other meshes' compute."""
-        opts = self.opts()
         cur = torch.cuda.current_stream(self.device)
         outs = []
         for k, g in enumerate(self.groups):
@@ -129,7 +148,7 @@ class Sweep1D:
                 u = g["u"]
                 u.fill_(1.0)
                 u[:, :, NC - 1] = 0.0
-                outs.append(g["solver"].steady(u, g["d_path"], opts))
+                outs.append(g["solver"].steady(u, g["d_path"], self.group_opts(g)))
                 if host_out is not None:
                     host_out[k].copy_(u, non_blocking=True)
         for g in self.groups:
@@ -271,7 +290,7 @@ class Sweep1D:
             u = g["u"]
             u.fill_(1.0)
             u[:, :, NC - 1] = 0.0
-            out = g["solver"].steady(u, g["d_path"], self.opts())
+            out = g["solver"].steady(u, g["d_path"], self.group_opts(g))
             f = g["solver"].field(u)[:, 0]
             rows = torch.cat([out["status"].to(torch.float64)[:, None], out["iters"].sum(dim=1).to(torch.float64)[:, None],
                               u[:, 0, :], f[:, None]], dim=1).cpu().numpy()

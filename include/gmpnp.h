@@ -72,7 +72,12 @@ typedef struct gmpnp_newton_opts {
                            14-point Keast in 3D -- the reference's iteration path), 1 = the residual's
                            rule (exact derivative of the discrete F: quadratic convergence; same
                            converged solution, which depends on F's rule only)              */
-    int    reserved;
+    int    partitions;  /* 1D: sweeps per problem.  2 = two-sided elimination (top half downwards, bottom half upwards:
+                           the throughput form); 4 / 8 = partitioned elimination -- the chain is cut at 2 / 4 separator
+                           nodes, interior sub-domains are swept from both ends carrying a 7-column spike, the
+                           separators form a small reduced system: ~2.5x shorter critical path at 8 for ~2x the work,
+                           for batches that leave SMs idle (strong scaling, single-problem latency); 0 = automatic by
+                           batch size.  Same results to round-off.                                                  */
     double xtol_floor;  /* increment criterion only, 0 = off (the default: strict contract above).  > 0: an
                            increment that has stopped contracting (||dx|| >= 0.25 ||dx_prev||, after >= 3
                            iterations) with xtol*s < ||dx||_inf <= xtol_floor*s, s = max(1,||x||_inf), ends the

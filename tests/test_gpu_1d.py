@@ -203,7 +203,7 @@ def test_benchmarked_setting_matches_oracle(lib, cation, conc, L_n, V):
     from gmpnp_b200 import meshio, params, sweep
     from oracle import solver as osolver
     pt = sweep.SweepPoint(cation, conc, L_n, V, 0)
-    sw = sweep.Sweep1D([pt], device=0, dv_max=0.75, xtol_path=1.0, pivot=0)
+    sw = sweep.Sweep1D([pt], device=0, dv_max=0.75, xtol_path=1.0, pivot=0, partitions=2)      # as in bench.py at N = 1
     sw.upload()
     outs = sw.solve_resident()
     sw.finish(outs)
@@ -217,6 +217,32 @@ def test_benchmarked_setting_matches_oracle(lib, cation, conc, L_n, V):
     for c in range(7):
         assert rel_l2(got[:, c], uo[:, c]) < 1e-8, (c, rel_l2(got[:, c], uo[:, c]))
     assert abs(int(outs[0]["iters"].sum()) - sum(its)) <= 1, (outs[0]["iters"].tolist(), its)
+    sw.close()
+
+
+def test_sharded_sweep_setting_matches_oracle(lib):
+    """The strong-scaling setting (a shard of the sweep leaves the GPU idle -> Sweep1D picks the partitioned elimination with
+    8 sweeps per problem) against the oracle on the longest mesh at the largest voltage: rel-L2 <= 1e-8, same Newton count."""
+    from gmpnp_b200 import meshio, params, sweep
+    from oracle import solver as osolver
+    pts = [sweep.SweepPoint("K", 0.1, 50e-6, -12.5, 0), sweep.SweepPoint("Cs", 0.5, 200e-6, -7.0, 1)]
+    sw = sweep.Sweep1D(pts, device=0, dv_max=0.75, xtol_path=1.0)
+    assert sw._auto_partitions(5991, 1) == 8
+    sw.upload()
+    outs = sw.solve_resident()
+    sw.finish(outs)
+    torch.cuda.synchronize()
+    for g, out in zip(sw.groups, outs):
+        assert out["status"].tolist() == [0]
+        p = pts[int(g["idx"][0])]
+        x = meshio.load_mesh(params.mesh_name_1d(p.L_n)).x[:, 0]
+        prm = params.params_1d(concentration_elec=p.conc, cation=p.cation, L_n=p.L_n, voltage_multiplier=p.V)
+        path = sweep.voltage_paths(np.array([p.V]), 0.75)[0]
+        uo, its = osolver.steady_1d(x, prm, path[~np.isnan(path)], xtol=1e-10, xtol_path=1.0, jac_rule=1)
+        got = g["u"][0].cpu().numpy()
+        for c in range(7):
+            assert rel_l2(got[:, c], uo[:, c]) < 1e-8, (p, c)
+        assert abs(int(out["iters"].sum()) - sum(its)) <= 1
     sw.close()
 
 
@@ -396,7 +422,7 @@ def test_sweep_without_in_block_pivoting_matches_pivoted_solutions(lib):
     pts = [p for p in sweep.config2_points(8, meshes=(1e-6,)) if p.V in (-12.5, -12.5 * 3 / 8)]
     res = {}
     for piv in (0, 1):
-        sw = sweep.Sweep1D(pts, device=0, dv_max=0.75, xtol_path=1.0, pivot=piv)
+        sw = sweep.Sweep1D(pts, device=0, dv_max=0.75, xtol_path=1.0, pivot=piv, partitions=2)
         sw.upload()
         outs = sw.solve_resident()
         torch.cuda.synchronize()
@@ -498,7 +524,8 @@ def test_checkpointed_sweep_resumes(lib, tmp_path):
     sw.close()
 
 
-def test_run_to_run_bitwise_reproducibility_1d(lib):
+@pytest.mark.parametrize("partitions", [2, 8])
+def test_run_to_run_bitwise_reproducibility_1d(lib, partitions):
     """Race detector of last resort (compute-sanitizer is closed on the measurement pool): the warp-specialised kernel
     hands block rows between warps through a shared-memory queue guarded by named barriers; a missing or misplaced
     barrier shows up as run-to-run differences.  The same sweep twice, and the same problems at other batch positions
@@ -508,7 +535,7 @@ def test_run_to_run_bitwise_reproducibility_1d(lib):
     res = []
     for rep in range(3):
         use = pts if rep < 2 else list(reversed(pts))               # third run: other batch positions
-        sw = sweep.Sweep1D(use, device=0, dv_max=0.75, xtol_path=1.0)
+        sw = sweep.Sweep1D(use, device=0, dv_max=0.75, xtol_path=1.0, partitions=partitions)
         sw.upload()
         outs = sw.solve_resident()
         torch.cuda.synchronize()
@@ -518,3 +545,75 @@ def test_run_to_run_bitwise_reproducibility_1d(lib):
         sw.close()
     assert np.array_equal(res[0], res[1])
     assert np.array_equal(res[0], res[2])
+
+
+@pytest.mark.parametrize("S", [4, 8])
+def test_partitioned_elimination_matches_two_sided(lib, S):
+    """gmpnp_newton_opts.partitions = 4 / 8: the chain is cut at 2 / 4 separator nodes, interior sub-domains are swept from
+    both ends carrying a spike, the separators form a reduced system.  Same Newton counts and the same
+    iterates (to round-off) as the two-sided elimination: one reference solve() on meshes whose sub-domain lengths are
+    equal, differ by one (idle iterations) and are as short as 4 rows; the 5-step golden march; a ragged steady sweep."""
+    from gmpnp_b200 import meshio, params, solver1d
+    from gmpnp_b200._lib import NewtonOpts
+    g = np.load(os.path.join(GOLDEN, "march_1um.npz"))
+    meshes = [meshio.graded_interval(20, 0.01, 12).x[:, 0], meshio.graded_interval(41, 0.01, 23).x[:, 0],
+              meshio.graded_interval(40, 0.01, 23).x[:, 0], meshio.load_mesh("1D_variable_1um_mesh_1090").x[:, 0]]
+    for x in meshes:
+        n = len(x)
+        prm = params.params_1d(L_n=1.0e-6, voltage_multiplier=-0.3, time_step=1.0e-7 if n < 100 else 1.0e-5)
+        for jac_rule, pivot in ((0, 1), (1, 0)):
+            res = {}
+            for parts in (2, S):
+                s = solver1d.Solver1D(x, batch=3)
+                s.set_params([prm] * 3)
+                u = torch.zeros(3, n, 7, dtype=torch.float64, device=_dev())
+                un = solver1d.bulk_state(3, n, _dev())
+                o = NewtonOpts.reference_1d()
+                o.jac_rule, o.pivot, o.partitions = jac_rule, pivot, parts
+                out = s.newton(u, un, o)
+                torch.cuda.synchronize()
+                assert out["status"].tolist() == [0, 0, 0], (n, parts, out["status"].tolist())
+                res[parts] = (u.cpu().numpy().copy(), out["iters"].tolist(), out["r0"].cpu().numpy().copy(),
+                              out["r"].cpu().numpy().copy())
+                s.close()
+            assert res[S][1] == res[2][1], (n, jac_rule, res[S][1], res[2][1])
+            assert np.abs(res[S][2] - res[2][2]).max() <= 1e-10 * res[2][2].max()
+            for c in range(7):
+                assert rel_l2(res[S][0][1][:, c], res[2][0][1][:, c]) < 1e-9, (n, jac_rule, c)
+            assert np.array_equal(res[S][0][0], res[S][0][2])                 # batch positions bitwise identical
+    # the golden march of the reference algorithm
+    m = meshio.load_mesh("1D_variable_1um_mesh_1090")
+    prm = params.params_1d(L_n=1e-6)
+    s = solver1d.Solver1D(m.x[:, 0], batch=2)
+    s.set_params([prm, prm])
+    u = torch.zeros(2, s.n, 7, dtype=torch.float64, device=_dev())
+    un = solver1d.bulk_state(2, s.n, _dev())
+    o = NewtonOpts.reference_1d()
+    o.partitions = S
+    out = s.march(u, un, 5, o, history=True)
+    torch.cuda.synchronize()
+    assert out["status"].tolist() == [0, 0] and out["iters"][0].tolist() == g["its"].tolist()
+    hist = out["history"].cpu().numpy()
+    for step in range(5):
+        for c in range(7):
+            assert rel_l2(hist[0, step, :, c], g["hist"][step + 1][:, c]) < 1e-8
+    assert np.array_equal(un[0].cpu().numpy(), hist[0, -1])
+    # ragged steady continuation (the sweep setting)
+    Vs = np.array([-0.4, -3.0, -12.5])
+    from gmpnp_b200.sweep import voltage_paths
+    path = voltage_paths(Vs, 0.75)
+    sol = {}
+    for parts in (2, S):
+        u = solver1d.bulk_state(3, s.n, _dev())
+        s3 = solver1d.Solver1D(m.x[:, 0], batch=3)
+        s3.set_params([prm] * 3)
+        o = NewtonOpts.steady(xtol=1e-10, xtol_path=1.0, jac_rule=1)
+        o.pivot, o.partitions = 0, parts
+        out = s3.steady(u, path, o)
+        assert out["status"].tolist() == [0, 0, 0], (parts, out["status"].tolist())
+        sol[parts] = (u.cpu().numpy().copy(), out["iters"].cpu().numpy().copy())
+        s3.close()
+    assert np.array_equal(sol[S][1], sol[2][1])
+    for c in range(7):
+        assert rel_l2(sol[S][0][:, :, c], sol[2][0][:, :, c]) < 1e-9
+    s.close()
