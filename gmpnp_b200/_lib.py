@@ -76,6 +76,7 @@ SIGNATURES = {
     "gmpnp_march_1d": (_i, [_vp, _vp, _vp, _i, _po, _vp, _vp, _vp, _vp, _vp]),
     "gmpnp_steady_continuation_1d": (_i, [_vp, _vp, _vp, _i, _po, _vp, _vp, _vp, _vp, _vp]),
     "gmpnp_field_1d": (_i, [_vp, _vp, _vp, _vp]),
+    "gmpnp_field_ohp_1d": (_i, [_vp, _vp, _vp, _vp]),
     "gmpnp_create_3d": (_i, [C.POINTER(_vp), _i, _pd, _i, _pi, _i, _pi, _i, _i, _i]),
     "gmpnp_set_dirichlet_3d": (_i, [_vp, _pd, _i]),
     "gmpnp_pattern_3d": (_i, [_vp, _pi, _pi, _pi]),

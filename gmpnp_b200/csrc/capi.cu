@@ -6,6 +6,7 @@ int edl1d_launch_newton(gmpnp_handle*, int, double*, double*, const double*, con
                         const double*, double*, int*, double*, double*, double*, int*, int*, cudaStream_t);
 int edl1d_launch_assemble(gmpnp_handle*, const double*, const double*, double*, double*, cudaStream_t);
 int edl1d_launch_field(gmpnp_handle*, const double*, double*, cudaStream_t);
+int edl1d_launch_field_ohp(gmpnp_handle*, const double*, double*, cudaStream_t);
 
 extern "C" {
 
@@ -96,6 +97,13 @@ int gmpnp_field_1d(gmpnp_handle* h, const double* d_u, double* d_field, void* st
     if (!d_u || !d_field) return GMPNP_ERR_ARG;
     GMPNP_CUDA_TRY(h, cudaSetDevice(h->device));
     return edl1d_launch_field(h, d_u, d_field, (cudaStream_t)stream);
+}
+
+int gmpnp_field_ohp_1d(gmpnp_handle* h, const double* d_u, double* d_out, void* stream) {
+    int rc = check_1d(h); if (rc) return rc;
+    if (!d_u || !d_out) return GMPNP_ERR_ARG;
+    GMPNP_CUDA_TRY(h, cudaSetDevice(h->device));
+    return edl1d_launch_field_ohp(h, d_u, d_out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1840,6 +1840,48 @@ __global__ void field1d_kernel(int batch, int n, const double* __restrict__ x, c
     for (int k = n - 2; k >= 0; --k) f[k] -= cp[k] * f[k + 1];
 }
 
+// Projected field at the OHP only (node 0 of project(-grad(u_p), W), 1D:802-805: the quantity the reference's result
+// table holds), for per-point sweep summaries.  The P1 mass matrix is strictly diagonally dominant, so eliminating from
+// the far end towards node 0 (one sweep, no back substitution) only needs the first K nodes: the influence of node K on
+// node 0 is prod_k w_k <= 0.5^K (K = 256: far below round-off).  The elimination weights w_k depend on the mesh only:
+// thread 0 of every CTA computes them once into shared memory, then one thread per problem runs K fused multiply-adds.
+constexpr int FIELD_K = 256;
+__global__ void __launch_bounds__(128)
+field_ohp_kernel(int batch, int n, const double* __restrict__ x, const double* __restrict__ u, double* __restrict__ out) {
+    __shared__ double w[FIELD_K];      // w_k = c_k / d'_(k+1)
+    __shared__ double inv_d0;
+    const int K = min(n, FIELD_K);
+    if (threadIdx.x == 0) {
+        double dprime = 0.0;
+        for (int k = K - 1; k >= 0; --k) {
+            const double hm = (k > 0) ? x[k] - x[k - 1] : 0.0;
+            const double hp = (k + 1 < n) ? x[k + 1] - x[k] : 0.0;
+            const double d = (hm + hp) / 3.0, c = hp / 6.0;
+            // row k+1 (already reduced): a_(k+1) = hp / 6, diagonal dprime
+            w[k] = (k + 1 < K) ? c / dprime : 0.0;
+            dprime = d - w[k] * ((k + 1 < K) ? hp / 6.0 : 0.0);
+        }
+        inv_d0 = 1.0 / dprime;
+    }
+    __syncthreads();
+    const int prob = blockIdx.x * blockDim.x + threadIdx.x;
+    if (prob >= batch) return;
+    const double* up = u + (long)prob * n * NC + NS;          // potential component
+    // b_k = -(1/2) (phi_(k+1) - phi_(k-1)) with one-sided ends (the right-hand side of field1d_kernel)
+    double bprime = 0.0;
+    double phi_p = (K < n) ? up[(long)K * NC] : 0.0;          // phi_(k+1), starting at k = K-1
+    double phi_c = up[(long)(K - 1) * NC];
+    for (int k = K - 1; k >= 0; --k) {
+        const double phi_m = (k > 0) ? up[(long)(k - 1) * NC] : 0.0;
+        double b = 0.0;
+        if (k > 0) b += -0.5 * (phi_c - phi_m);
+        if (k + 1 < n) b += -0.5 * (phi_p - phi_c);
+        bprime = b - w[k] * bprime;
+        phi_p = phi_c; phi_c = phi_m;
+    }
+    out[prob] = bprime * inv_d0;
+}
+
 }  // namespace edl1d
 
 // ---------------------------------------------------------------------------------------
@@ -1915,6 +1957,14 @@ int edl1d_launch_assemble(gmpnp_handle* h, const double* d_u, const double* d_un
     const int blocks = (int)((items + GROUPS_PER_BLOCK - 1) / GROUPS_PER_BLOCK);
     const size_t smem = (size_t)GROUPS_PER_BLOCK * AS_GROUP * sizeof(double);
     assemble1d_kernel<<<blocks, THREADS, smem, st>>>(h->batch, h->n_nodes, h->d_x, h->d_params, d_u, d_un, d_F, d_J);
+    h->launches++;
+    GMPNP_CUDA_TRY(h, cudaGetLastError());
+    return GMPNP_OK;
+}
+
+int edl1d_launch_field_ohp(gmpnp_handle* h, const double* d_u, double* d_out, cudaStream_t st) {
+    using namespace edl1d;
+    field_ohp_kernel<<<(h->batch + 127) / 128, 128, 0, st>>>(h->batch, h->n_nodes, h->d_x, d_u, d_out);
     h->launches++;
     GMPNP_CUDA_TRY(h, cudaGetLastError());
     return GMPNP_OK;

@@ -146,5 +146,12 @@ class Solver1D:
         check(self.lib.gmpnp_field_1d(self._h, ptr(u), ptr(f), self._stream()), self._h)
         return f
 
+    def field_ohp(self, u):
+        """The projected field at the OHP (node 0 of :meth:`field`) only: [batch]."""
+        self._chk(u, (self.batch, self.n, NC))
+        f = torch.empty(self.batch, dtype=torch.float64, device=self.device)
+        check(self.lib.gmpnp_field_ohp_1d(self._h, ptr(u), ptr(f), self._stream()), self._h)
+        return f
+
     def launch_count(self) -> int:
         return int(self.lib.gmpnp_launch_count(self._h))

@@ -182,7 +182,7 @@ class Sweep1D:
         global sweep-point index of every row: the payload of the sharded sweep's one collective."""
         rows = torch.empty(self.n_points, N_SUMMARY, dtype=torch.float64, device=self.device)
         for g, out in zip(self.groups, outs):
-            f = g["solver"].field(g["u"])[:, 0]
+            f = g["solver"].field_ohp(g["u"])
             blk = torch.cat([out["status"].to(torch.float64)[:, None],
                              out["iters"].sum(dim=1).to(torch.float64)[:, None], g["u"][:, 0, :], f[:, None]], dim=1)
             rows[g["d_idx"]] = blk

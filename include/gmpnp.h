@@ -155,6 +155,11 @@ int gmpnp_steady_continuation_1d(gmpnp_handle* h, double* d_u, const double* d_V
  * every problem: d_field[batch][n].                                                       */
 int gmpnp_field_1d(gmpnp_handle* h, const double* d_u, double* d_field, void* stream);
 
+/* The same projection evaluated at the OHP only (node 0: the field_OHP of 1D:940-954 and of the result table
+ * 1D/Stern_CO2ER.py:66-68), d_out[batch] -- for per-point sweep summaries: a one-sweep elimination over the first 256
+ * nodes (the mass matrix is diagonally dominant: the truncation error is below 0.5^256).                              */
+int gmpnp_field_ohp_1d(gmpnp_handle* h, const double* d_u, double* d_out, void* stream);
+
 /* number of kernels this handle has launched so far (for bench.py's gpu_launches)          */
 long long gmpnp_launch_count(const gmpnp_handle* h);
 

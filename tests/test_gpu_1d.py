@@ -668,3 +668,25 @@ def test_full_config2_sweep_properties(lib):
     rows2, idx2 = sw2.results_device(outs2)
     assert np.array_equal(rows2[torch.argsort(idx2)].cpu().numpy(), table)
     sw2.close()
+
+
+def test_field_at_the_ohp_equals_the_full_projection(lib):
+    """gmpnp_field_ohp_1d (one-sweep elimination over the first 256 nodes) against node 0 of the full P1 projection
+    gmpnp_field_1d on steady states of the shortest and the longest mesh, and on a 9-node mesh (K = n)."""
+    from gmpnp_b200 import meshio, params, solver1d
+    from gmpnp_b200._lib import NewtonOpts
+    for x, V in ((meshio.load_mesh("1D_variable_1um_mesh_1090").x[:, 0], -3.0),
+                 (meshio.load_mesh("1D_variable_50um_mesh_5990").x[:, 0], -1.5),
+                 (meshio.graded_interval(5, 0.01, 3).x[:, 0], -0.2)):
+        L_n = 1e-6 if len(x) < 2000 else 50e-6
+        prm = params.params_1d(L_n=L_n, voltage_multiplier=V)
+        s = solver1d.Solver1D(x, batch=3)
+        s.set_params([prm] * 3)
+        u = solver1d.bulk_state(3, s.n, _dev())
+        out = s.steady(u, np.array([[V / 2, V]] * 3), NewtonOpts.steady(xtol=1e-10, jac_rule=1))
+        assert out["status"].tolist() == [0, 0, 0]
+        u[1] += 0.01 * torch.rand_like(u[1])
+        full = s.field(u)[:, 0].cpu().numpy()
+        ohp = s.field_ohp(u).cpu().numpy()
+        assert np.abs(ohp - full).max() <= 1e-12 * np.abs(full).max(), (len(x), ohp, full)
+        s.close()
