@@ -353,7 +353,8 @@ def bench_pore3d(local, world, dev, batch, peak):
         "assemble": {"ms": ms_asm, "GBs": b_asm / ms_asm / 1e6, "frac_of_hbm_peak": b_asm / ms_asm / 1e6 / peak,
                      "algorithmic_bytes": b_asm,
                      "dram_traffic_over_algorithmic_ncu": traffic.get("assemble3d_dram_bytes_over_algorithmic_bytes"),
-                     "kernels": "tet_moments_kernel + assemble_bsr_kernel + residual_gather_kernel"},
+                     "kernels": "batch-lane assembly (batch >= 24): lanes_transpose_kernel x2 + tet_moments_lanes_kernel + "
+                                "residual_gather_kernel + assemble_bsr_lanes_kernel per 32 problems"},
         "spmv": {"ms": ms_spmv, "GBs": b_spmv / ms_spmv / 1e6, "frac_of_hbm_peak": b_spmv / ms_spmv / 1e6 / peak,
                  "algorithmic_bytes": b_spmv,
                  "dram_traffic_over_algorithmic_ncu": traffic.get("spmv_dram_bytes_over_algorithmic_bytes"),

@@ -14,6 +14,7 @@
 // row sorted by column);  per-tet moment records mom[problem][tet][60], Fe[problem][tet][4][9].
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <numeric>
 #include <cooperative_groups.h>
 #include "common.cuh"
@@ -31,6 +32,7 @@ constexpr int M_MD = 0, M_UD2 = 4, M_IUD = 36, M_GA = 44, M_GPA = 48, M_SU = 52,
 #endif
 constexpr int NZ = 16;       // z-slabs of the coarse space
 constexpr int NCO = NZ * NC; // coarse dimension (144)
+constexpr size_t MEDIAN_SORT_BYTES = 200 * 1024;   // largest shared-memory sort (16384 vertices); radix select beyond
 
 // FIAT default tetrahedron schemes (oracle/quadrature.py): degree 3 -> 5-point
 // Zienkiewicz-Taylor rule for the residual, degree 4 -> 14-point Keast rule for the Jacobian.
@@ -71,39 +73,43 @@ static void upload_rules() {       // per handle creation: constant memory belon
 // ---------------------------------------------------------------------------------------
 // Kernel A: per (problem, tet) quadrature moments (14-point rule) and element residual (5-point)
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, TET_MIN_BLOCKS)
-tet_moments_kernel(int n_tet, int n_vert, const int* __restrict__ tets, const double* __restrict__ geom,
-                   const double* __restrict__ params, const double* __restrict__ u, const double* __restrict__ un,
-                   double* __restrict__ mom, double* __restrict__ Fe, int want_jac, int want_res) {
-    __shared__ double P[GMPNP_NPAR];
-    const int prob = blockIdx.y;
-    for (int i = threadIdx.x; i < GMPNP_NPAR; i += blockDim.x) P[i] = params[(long)prob * GMPNP_NPAR + i];
-    __syncthreads();
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_tet) return;
-    const double* up = u + (long)prob * n_vert * NC;
-    const double* unp = un + (long)prob * n_vert * NC;
+// The per-tet arithmetic is shared by the two layouts of the assembly (one problem per CTA / one problem per lane, see
+// "batch-lane assembly" below); only the strides differ: nodal values at up[(v * NC + i) * US], parameters through the
+// accessor P(k), moments at mo[k * MS], element residual at fe[(a * NC + i) * FS].
+struct ParamsCta {           // parameter record of the CTA's problem in shared memory
+    const double* P;
+    __device__ __forceinline__ double operator()(int k) const { return P[k]; }
+};
+struct ParamsLane {          // records of 32 problems in shared memory, transposed: [k][lane], already offset by the lane
+    const double* P;
+    __device__ __forceinline__ double operator()(int k) const { return P[k * 32]; }
+};
+
+template <int US, int MS, int FS, class PA>
+__device__ __forceinline__ void tet_core(const PA P, const int* __restrict__ tet, const double* __restrict__ geomt,
+                                         const double* __restrict__ up, const double* __restrict__ unp,
+                                         double* __restrict__ mo, double* __restrict__ fe, int want_jac, int want_res) {
     int v[4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) v[a] = tets[t * 4 + a];
+    for (int a = 0; a < 4; ++a) v[a] = tet[a];
     double g[4][3];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int d = 0; d < 3; ++d) g[a][d] = geom[(long)t * 13 + a * 3 + d];
-    const double vol = geom[(long)t * 13 + 12];
+        for (int d = 0; d < 3; ++d) g[a][d] = geomt[a * 3 + d];
+    const double vol = geomt[12];
     double U[4][NC];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int i = 0; i < NC; ++i) U[a][i] = up[(long)v[a] * NC + i];
+        for (int i = 0; i < NC; ++i) U[a][i] = up[((long)v[a] * NC + i) * US];
     // gradients: G = sum_i nu_i grad u_i, gp = grad p
     double G[3] = {0, 0, 0}, gp[3] = {0, 0, 0};
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         double s = 0.0;
 #pragma unroll
-        for (int i = 0; i < NS; ++i) s += P[GMPNP_P_NU + i] * U[a][i];
+        for (int i = 0; i < NS; ++i) s += P(GMPNP_P_NU + i) * U[a][i];
 #pragma unroll
         for (int d = 0; d < 3; ++d) { G[d] += s * g[a][d]; gp[d] += U[a][NS] * g[a][d]; }
     }
@@ -128,7 +134,7 @@ tet_moments_kernel(int n_tet, int n_vert, const int* __restrict__ tets, const do
 #pragma unroll
             for (int i = 0; i < NS; ++i) {
                 uq[i] = l0 * U[0][i] + l1 * U[1][i] + l2 * U[2][i] + l3 * U[3][i];
-                S += P[GMPNP_P_NU + i] * uq[i];
+                S += P(GMPNP_P_NU + i) * uq[i];
             }
             const double D = 1.0 / (1.0 - S);
             const double WD = W * D, WD2 = WD * D;
@@ -141,22 +147,21 @@ tet_moments_kernel(int n_tet, int n_vert, const int* __restrict__ tets, const do
                 m2[i][0] += w2 * l0; m2[i][1] += w2 * l1; m2[i][2] += w2 * l2; m2[i][3] += w2 * l3;
             }
         }
-        double* mo = mom + ((long)prob * n_tet + t) * NMOM;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) mo[M_MD + b] = mD[b];
+        for (int b = 0; b < 4; ++b) mo[(M_MD + b) * MS] = mD[b];
 #pragma unroll
         for (int i = 0; i < NS; ++i)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) mo[M_UD2 + i * 4 + b] = m2[i][b];
+            for (int b = 0; b < 4; ++b) mo[(M_UD2 + i * 4 + b) * MS] = m2[i][b];
 #pragma unroll
-        for (int i = 0; i < NS; ++i) mo[M_IUD + i] = iUD[i];
+        for (int i = 0; i < NS; ++i) mo[(M_IUD + i) * MS] = iUD[i];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) { mo[M_GA + a] = Ga[a]; mo[M_GPA + a] = gpa[a]; }
+        for (int a = 0; a < 4; ++a) { mo[(M_GA + a) * MS] = Ga[a]; mo[(M_GPA + a) * MS] = gpa[a]; }
 #pragma unroll
-        for (int i = 0; i < NS; ++i) mo[M_SU + i] = SU[i];
+        for (int i = 0; i < NS; ++i) mo[(M_SU + i) * MS] = SU[i];
         {
-            const double wm = (P[GMPNP_P_EPSC] * SU[NS - 1] + P[GMPNP_P_EPSH] * SU[0]) * 0.25;
-            mo[M_EPS] = P[GMPNP_P_EPSW] * ((55.0 - wm) / 55.0) + 6.0 * (wm / 55.0);
+            const double wm = (P(GMPNP_P_EPSC) * SU[NS - 1] + P(GMPNP_P_EPSH) * SU[0]) * 0.25;
+            mo[M_EPS * MS] = P(GMPNP_P_EPSW) * ((55.0 - wm) / 55.0) + 6.0 * (wm / 55.0);
         }
     }
     if (want_res) {
@@ -166,8 +171,8 @@ tet_moments_kernel(int n_tet, int n_vert, const int* __restrict__ tets, const do
         for (int i = 0; i < NS; ++i) sUD[i] = 0.0;
 #pragma unroll
         for (int i = 0; i < 5; ++i) R[i][0] = R[i][1] = R[i][2] = R[i][3] = 0.0;
-        const double kW = P[GMPNP_P_KW], kA = P[GMPNP_P_KA], kB = P[GMPNP_P_KB];
-        const double kA2 = P[GMPNP_P_KA2], kB2 = P[GMPNP_P_KB2], kw1 = P[GMPNP_P_KW1];
+        const double kW = P(GMPNP_P_KW), kA = P(GMPNP_P_KA), kB = P(GMPNP_P_KB);
+        const double kA2 = P(GMPNP_P_KA2), kB2 = P(GMPNP_P_KB2), kw1 = P(GMPNP_P_KW1);
         for (int q = 0; q < 5; ++q) {
             const double l[4] = {QF_L[q][0], QF_L[q][1], QF_L[q][2], QF_L[q][3]};
             const double W = QF_W[q] * vol;
@@ -175,7 +180,7 @@ tet_moments_kernel(int n_tet, int n_vert, const int* __restrict__ tets, const do
 #pragma unroll
             for (int i = 0; i < NS; ++i) {
                 uq[i] = l[0] * U[0][i] + l[1] * U[1][i] + l[2] * U[2][i] + l[3] * U[3][i];
-                S += P[GMPNP_P_NU + i] * uq[i];
+                S += P(GMPNP_P_NU + i) * uq[i];
             }
             const double WD = W / (1.0 - S);
 #pragma unroll
@@ -183,18 +188,17 @@ tet_moments_kernel(int n_tet, int n_vert, const int* __restrict__ tets, const do
             const double w = kW * uq[0] * uq[1], a = kA * uq[1] * uq[2], b = kB * uq[4] * uq[1];
             const double a2 = kA2 * uq[3], b2 = kB2 * uq[2];
             double mr[5];
-            mr[0] = P[GMPNP_P_S] * (w - kw1);
-            mr[1] = P[GMPNP_P_S + 1] * (w + a + b - kw1 - a2 - b2);
-            mr[2] = P[GMPNP_P_S + 2] * (a + b2 - a2 - b);
-            mr[3] = P[GMPNP_P_S + 3] * (a2 - a);
-            mr[4] = P[GMPNP_P_S + 4] * (b - b2);
+            mr[0] = P(GMPNP_P_S) * (w - kw1);
+            mr[1] = P(GMPNP_P_S + 1) * (w + a + b - kw1 - a2 - b2);
+            mr[2] = P(GMPNP_P_S + 2) * (a + b2 - a2 - b);
+            mr[3] = P(GMPNP_P_S + 3) * (a2 - a);
+            mr[4] = P(GMPNP_P_S + 4) * (b - b2);
 #pragma unroll
             for (int i = 0; i < 5; ++i)
 #pragma unroll
                 for (int aa = 0; aa < 4; ++aa) R[i][aa] += W * l[aa] * mr[i];
         }
-        const double kappa = P[GMPNP_P_KAPPA];
-        double* fe = Fe + ((long)prob * n_tet + t) * 36;
+        const double kappa = P(GMPNP_P_KAPPA);
         // K_ac = vol g_a.g_c
         double K[4][4];
 #pragma unroll
@@ -207,12 +211,12 @@ tet_moments_kernel(int n_tet, int n_vert, const int* __restrict__ tets, const do
             double dn[4], dsum = 0.0;
             if (kappa != 0.0) {
 #pragma unroll
-                for (int a = 0; a < 4; ++a) { dn[a] = U[a][i] - unp[(long)v[a] * NC + i]; dsum += dn[a]; }
+                for (int a = 0; a < 4; ++a) { dn[a] = U[a][i] - unp[((long)v[a] * NC + i) * US]; dsum += dn[a]; }
             } else {
 #pragma unroll
                 for (int a = 0; a < 4; ++a) dn[a] = 0.0;
             }
-            const double zi = P[GMPNP_P_Z + i];
+            const double zi = P(GMPNP_P_Z + i);
             const double iU = 0.25 * vol * SU[i];
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
@@ -220,17 +224,32 @@ tet_moments_kernel(int n_tet, int n_vert, const int* __restrict__ tets, const do
                 f += K[a][0] * U[0][i] + K[a][1] * U[1][i] + K[a][2] * U[2][i] + K[a][3] * U[3][i];
                 f += zi * gpa[a] * iU + Ga[a] * sUD[i];
                 if (i < 5) f += R[i][a];
-                fe[a * NC + i] = f;
-                rho[a] += P[GMPNP_P_ZC0 + i] * U[a][i];
+                fe[(a * NC + i) * FS] = f;
+                rho[a] += P(GMPNP_P_ZC0 + i) * U[a][i];
             }
         }
-        const double wm = (P[GMPNP_P_EPSC] * SU[NS - 1] + P[GMPNP_P_EPSH] * SU[0]) * 0.25;
-        const double epsm = P[GMPNP_P_EPSW] * ((55.0 - wm) / 55.0) + 6.0 * (wm / 55.0);
+        const double wm = (P(GMPNP_P_EPSC) * SU[NS - 1] + P(GMPNP_P_EPSH) * SU[0]) * 0.25;
+        const double epsm = P(GMPNP_P_EPSW) * ((55.0 - wm) / 55.0) + 6.0 * (wm / 55.0);
         const double rs = rho[0] + rho[1] + rho[2] + rho[3];
 #pragma unroll
         for (int a = 0; a < 4; ++a)
-            fe[a * NC + NS] = -gpa[a] * vol * epsm + P[GMPNP_P_Q] * (vol * 0.05) * (rs + rho[a]);
+            fe[(a * NC + NS) * FS] = -gpa[a] * vol * epsm + P(GMPNP_P_Q) * (vol * 0.05) * (rs + rho[a]);
     }
+}
+
+__global__ void __launch_bounds__(128, TET_MIN_BLOCKS)
+tet_moments_kernel(int n_tet, int n_vert, const int* __restrict__ tets, const double* __restrict__ geom,
+                   const double* __restrict__ params, const double* __restrict__ u, const double* __restrict__ un,
+                   double* __restrict__ mom, double* __restrict__ Fe, int want_jac, int want_res) {
+    __shared__ double P[GMPNP_NPAR];
+    const int prob = blockIdx.y;
+    for (int i = threadIdx.x; i < GMPNP_NPAR; i += blockDim.x) P[i] = params[(long)prob * GMPNP_NPAR + i];
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tet) return;
+    tet_core<1, 1, 1>(ParamsCta{P}, tets + (long)t * 4, geom + (long)t * 13, u + (long)prob * n_vert * NC,
+                      un + (long)prob * n_vert * NC, mom + ((long)prob * n_tet + t) * NMOM,
+                      Fe + ((long)prob * n_tet + t) * 36, want_jac, want_res);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -435,6 +454,248 @@ assemble_bsr_kernel(int n_blocks, int n_vert, int n_tet, const int* __restrict__
             // Dirichlet rows: identity
             if (dir_flag[(long)va * NC + ei] >= 0) val = (va == vb && e == ei * 10) ? 1.0 : 0.0;
             Jp[(long)blk * 81 + e] = val;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Batch-lane assembly (batches of >= LANES_MIN_BATCH problems on one mesh): one problem per LANE
+// ---------------------------------------------------------------------------------------
+// All problems of a batch share the mesh, so the gather lists, the geometry and the Dirichlet flags are the same for
+// every problem.  The kernels above spend ~90 % of their instructions on that shared index work (warp per (problem, block):
+// list loads, shuffles, address arithmetic, cross-lane reductions, 524 warp-instructions per block for ~30 fp64
+// operations per contribution).  Here a warp takes one tet / one BSR block for 32 PROBLEMS at once, lane = problem:
+// index work is warp-uniform and done once per 32 problems, every sum is lane-local (no shuffles, no reductions, fixed
+// ascending tet order -> deterministic and independent of the position in the batch), and the intermediate arrays are
+// stored problem-minor so that every load and store of a warp is one contiguous 256-byte segment:
+//     uT  [group][vertex][component][32]     nodal values   (lanes_transpose_kernel, from the caller's [problem][v][c])
+//     momT[group][tet][NMT = 61][32]         moments        (tet_moments_lanes_kernel)
+// The caller-facing layouts do not change: Fe [problem][tet][36] and J [problem][block][81] are written through a
+// shared-memory transposition (rows padded to 33 doubles: conflict-free both ways) as contiguous 288- / 648-byte rows.
+// Lanes past the batch size compute on a copy of the last problem and store nothing.
+constexpr int NMT = 61;                 // moments per tet (the record of NMOM without its padding)
+constexpr int LANES_MIN_BATCH = 24;     // below this the warp-per-(problem, block) kernels waste fewer lanes
+constexpr int TL_WARPS = 4;             // tets per CTA of tet_moments_lanes_kernel
+constexpr int BL_WARPS = 4;             // blocks in flight per CTA of assemble_bsr_lanes_kernel
+constexpr int BL_UNROLL = 3;            // contributions in flight per warp
+constexpr int TR_LD = 33;               // leading dimension of the transposition tiles
+
+__global__ void __launch_bounds__(256)
+lanes_transpose_kernel(int batch, long n, const double* __restrict__ u, double* __restrict__ uT) {
+    __shared__ double tile[32][TR_LD];
+    const int g = blockIdx.y, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const long i0 = (long)blockIdx.x * 32;
+    for (int r = ty; r < 32; r += 8) {
+        const int p = min(g * 32 + r, batch - 1);
+        tile[r][tx] = (i0 + tx < n) ? u[(long)p * n + i0 + tx] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8)
+        if (i0 + r < n) uT[((long)g * n + i0 + r) * 32 + tx] = tile[tx][r];
+}
+
+// dynamic shared memory: Ps[GMPNP_NPAR][32] | Tr[TL_WARPS][36][TR_LD]
+constexpr size_t TL_SMEM = sizeof(double) * (GMPNP_NPAR * 32 + TL_WARPS * 36 * TR_LD);
+
+__global__ void __launch_bounds__(TL_WARPS * 32, TET_MIN_BLOCKS)
+tet_moments_lanes_kernel(int batch, int n_tet, int n_vert, const int* __restrict__ tets, const double* __restrict__ geom,
+                         const double* __restrict__ params, const double* __restrict__ uT,
+                         const double* __restrict__ unT, double* __restrict__ momT, double* __restrict__ Fe,
+                         int want_jac, int want_res) {
+    extern __shared__ double sm_tl[];
+    double* Ps = sm_tl;
+    const int g = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < GMPNP_NPAR * 32; i += blockDim.x)    // [k][problem]: conflict-free stores
+        Ps[i] = params[(long)min(g * 32 + (i & 31), batch - 1) * GMPNP_NPAR + (i >> 5)];
+    __syncthreads();
+    double* Tr = sm_tl + GMPNP_NPAR * 32 + w * 36 * TR_LD;
+    const long goff = (long)g * n_vert * NC * 32 + lane;
+    for (int t = blockIdx.x * TL_WARPS + w; t < n_tet; t += gridDim.x * TL_WARPS) {
+        tet_core<32, 32, TR_LD>(ParamsLane{Ps + lane}, tets + (long)t * 4, geom + (long)t * 13, uT + goff, unT + goff,
+                                momT + ((long)g * n_tet + t) * NMT * 32 + lane, Tr + lane, want_jac, want_res);
+        if (want_res) {
+            __syncwarp();
+            int q = 0, e = lane;                                      // flat index q * 36 + e over the warp's 32 rows
+#pragma unroll 4
+            for (int it = 0; it < 36; ++it) {
+                if (e >= 36) { e -= 36; ++q; }
+                const int p = g * 32 + q;
+                if (p < batch) Fe[((long)p * n_tet + t) * 36 + e] = Tr[e * TR_LD + q];
+                e += 32;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// dynamic shared memory: Ps[GMPNP_NPAR][32] | kx[8][32] | St[WARPS][27][TR_LD]
+constexpr size_t bl_smem(int warps) { return sizeof(double) * (GMPNP_NPAR * 32 + 8 * 32 + warps * 27 * TR_LD); }
+
+// Block descriptors in PROCESSING order (host, gmpnp_create_3d): the blocks sorted along a space-filling curve of
+// their row vertex, so that the warps resident at one time work on one neighbourhood of the mesh and the 15.6-KB moment
+// records of its tets are re-read from L2, not from HBM (one launch per lane group for the same reason).
+// meta[2k] = (block, va, vb, first contribution), meta[2k+1] = (number of contributions, Dirichlet mask of the 9 rows
+// of va, 0, 0).  The loop is software-pipelined by one block: descriptors and the (tet, a, b) list of block k+1 are
+// requested while block k is accumulated / expanded, so the only exposed latency per block is that of the moment loads.
+// The 81 entries leave through a 27-entry (three block rows) staging tile per warp: 7 KB instead of 21 KB, which is
+// what lets more than 8 warps live on an SM.
+template <int UNR, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2)
+assemble_bsr_lanes_kernel(int g, int batch, int n_blocks, int n_vert, int n_tet, const int4* __restrict__ meta,
+                          const int* __restrict__ blk_src, const double2* __restrict__ blk_geo,
+                          const double* __restrict__ params, const double* __restrict__ uT,
+                          const double* __restrict__ momT, double* __restrict__ J,
+                          const double* __restrict__ exit_m, const double* __restrict__ bc) {
+    extern __shared__ double sm_bl[];
+    double* Ps = sm_bl;
+    double* kx = sm_bl + GMPNP_NPAR * 32;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < GMPNP_NPAR * 32; i += blockDim.x)
+        Ps[i] = params[(long)min(g * 32 + (i & 31), batch - 1) * GMPNP_NPAR + (i >> 5)];
+    for (int i = threadIdx.x; i < 8 * 32; i += blockDim.x)
+        kx[i] = (exit_m != nullptr) ? bc[(long)min(g * 32 + (i & 31), batch - 1) * 16 + 8 + (i >> 5)] : 0.0;
+    __syncthreads();
+    const ParamsLane P{Ps + lane};
+    double* St = sm_bl + GMPNP_NPAR * 32 + 8 * 32 + w * 27 * TR_LD;
+    const double* mo = momT + (long)g * n_tet * NMT * 32 + lane;
+    const double* up = uT + (long)g * n_vert * NC * 32 + lane;
+    const long jstride = (long)n_blocks * 81;
+    const int nq = min(32, batch - g * 32);              // live problems of this lane group
+    const int stride = gridDim.x * WARPS;
+    int k = blockIdx.x * WARPS + w;
+    int4 ma = make_int4(0, 0, 0, 0), mb = make_int4(0, 0, 0, 0);
+    int my_src = 0;
+    double2 my_kv = make_double2(0.0, 0.0);
+    if (k < n_blocks) {
+        ma = __ldg(meta + 2 * k); mb = __ldg(meta + 2 * k + 1);
+        if (lane < mb.x) { my_src = __ldg(blk_src + ma.w + lane); my_kv = __ldg(blk_geo + ma.w + lane); }
+    }
+    for (; k < n_blocks; k += stride) {
+        const int blk = ma.x, va = ma.y, vb = ma.z, s0 = ma.w, cnt = mb.x, pin = mb.y;
+        int cur_src = my_src;
+        double2 cur_kv = my_kv;
+        const int kn = k + stride;
+        if (kn < n_blocks) { ma = __ldg(meta + 2 * kn); mb = __ldg(meta + 2 * kn + 1); }     // descriptor of the next block
+        const double* ua = up + (long)va * NC * 32;
+        const double* ub = up + (long)vb * NC * 32;
+        const double n0 = ua[0] + ub[0], n1 = ua[32] + ub[32], n2 = ua[64] + ub[64], n4 = ua[128] + ub[128];
+        const double xm = (exit_m != nullptr) ? __ldg(exit_m + blk) : 0.0;
+        double Q[NS], Pc[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) { Q[i] = 0.0; Pc[i] = 0.0; }
+        double T0 = 0.0, T1 = 0.0, T2 = 0.0, T4 = 0.0;
+        double dG = 0.0, sK = 0.0, zsum = 0.0, ppsum = 0.0, sMab = 0.0, scT = 0.0;
+        for (int c0 = 0; c0 < cnt; c0 += 32) {
+            if (c0 > 0) {                                    // rare: more than 32 contributions (high-valence diagonal)
+                cur_src = 0; cur_kv = make_double2(0.0, 0.0);
+                if (c0 + lane < cnt) { cur_src = __ldg(blk_src + s0 + c0 + lane); cur_kv = __ldg(blk_geo + s0 + c0 + lane); }
+            }
+            const int nc = min(32, cnt - c0);
+#pragma unroll UNR
+            for (int c = 0; c < nc; ++c) {
+                const int src = __shfl_sync(0xffffffffu, cur_src, c);
+                const double kab = __shfl_sync(0xffffffffu, cur_kv.x, c), vol = __shfl_sync(0xffffffffu, cur_kv.y, c);
+                const int t = src >> 4, a = (src >> 2) & 3, b = src & 3;
+                const double* m = mo + (long)t * (NMT * 32);
+                const double* ma_ = m + a * 32;
+                const double* mb_ = m + b * 32;
+                const double Ga = ma_[M_GA * 32], gpa = ma_[M_GPA * 32], mDb = mb_[M_MD * 32], eps = m[M_EPS * 32];
+                const double Kab = kab * vol, mq = 0.25 * vol;
+                const double Mab = vol * ((a == b) ? 0.1 : 0.05);
+                const double cT = vol * ((a == b) ? (1.0 / 60.0) : (1.0 / 120.0));
+                const double kmq = kab * mq;
+                dG += Ga * mDb;
+                sK += Kab;
+                zsum += gpa * mq;
+                ppsum -= Kab * eps;
+                sMab += Mab;
+                scT += cT;
+#pragma unroll
+                for (int i = 0; i < NS; ++i) {
+                    const double su = m[(M_SU + i) * 32];
+                    Q[i] += Ga * mb_[(M_UD2 + 4 * i) * 32] + kab * m[(M_IUD + i) * 32];
+                    Pc[i] += kmq * su;
+                    if (i == 0) T0 += cT * su;
+                    if (i == 1) T1 += cT * su;
+                    if (i == 2) T2 += cT * su;
+                    if (i == 4) T4 += cT * su;
+                }
+            }
+        }
+        if (kn < n_blocks) {                                 // (tet, a, b) list of the next block: lands during the expansion
+            my_src = 0; my_kv = make_double2(0.0, 0.0);
+            if (lane < mb.x) { my_src = __ldg(blk_src + ma.w + lane); my_kv = __ldg(blk_geo + ma.w + lane); }
+        }
+        T0 += n0 * scT; T1 += n1 * scT; T2 += n2 * scT; T4 += n4 * scT;          // nodal part of the reaction moments
+        const double dsum = P(GMPNP_P_KAPPA) * sMab + sK + dG;
+        const double kW = P(GMPNP_P_KW), kA = P(GMPNP_P_KA), kB = P(GMPNP_P_KB);
+        const double r_wT1 = kW * T1, r_wT0 = kW * T0, r_aT2 = kA * T2, r_bT4 = kB * T4, r_aT1 = kA * T1, r_bT1 = kB * T1;
+        const double r_b2 = P(GMPNP_P_KB2) * sMab, r_a2 = P(GMPNP_P_KA2) * sMab;
+        const double deps = (6.0 - P(GMPNP_P_EPSW)) / 55.0;
+        double* jp0 = J + ((long)g * 32 * n_blocks + blk) * 81 + lane;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {                 // three block rows per pass through the staging tile
+            __syncwarp();                                // the previous pass has been read out of St
+#pragma unroll
+            for (int ii = 0; ii < 3; ++ii) {
+                const int i = ch * 3 + ii;
+                if ((pin >> i) & 1) {                    // Dirichlet row: identity (warp-uniform branch)
+#pragma unroll
+                    for (int j = 0; j < NC; ++j) St[(ii * NC + j) * TR_LD + lane] = (va == vb && i == j) ? 1.0 : 0.0;
+                    continue;
+                }
+#pragma unroll
+                for (int j = 0; j < NC; ++j) {
+                    double val;
+                    if (i < NS && j < NS) {
+                        val = P(GMPNP_P_NU + j) * Q[i];
+                        if (i == j) val += dsum + P(GMPNP_P_Z + i) * zsum + kx[(i & 7) * 32 + lane] * xm;
+                        if (i < 5 && j < 5) {
+                            double rr = 0.0;
+                            switch (i * 5 + j) {                     // d(reaction source of i)/d u_j, SURVEY App. A.2
+                                case 0: rr = r_wT1; break;
+                                case 1: rr = r_wT0; break;
+                                case 5: rr = r_wT1; break;
+                                case 6: rr = r_wT0 + r_aT2 + r_bT4; break;
+                                case 7: rr = r_aT1 - r_b2; break;
+                                case 8: rr = -r_a2; break;
+                                case 9: rr = r_bT1; break;
+                                case 11: rr = r_aT2 - r_bT4; break;
+                                case 12: rr = r_aT1 + r_b2; break;
+                                case 13: rr = -r_a2; break;
+                                case 14: rr = -r_bT1; break;
+                                case 16: rr = -r_aT2; break;
+                                case 17: rr = -r_aT1; break;
+                                case 18: rr = r_a2; break;
+                                case 21: rr = r_bT4; break;
+                                case 22: rr = -r_b2; break;
+                                case 24: rr = r_bT1; break;
+                                default: break;
+                            }
+                            val += P(GMPNP_P_S + (i < 5 ? i : 0)) * rr;
+                        }
+                    } else if (i < NS) {
+                        val = P(GMPNP_P_Z + (i & 7)) * Pc[i & 7];
+                    } else if (j < NS) {
+                        val = P(GMPNP_P_Q) * P(GMPNP_P_ZC0 + j) * sMab;
+                        if (j == 0) val -= deps * P(GMPNP_P_EPSH) * zsum;
+                        if (j == NS - 1) val -= deps * P(GMPNP_P_EPSC) * zsum;
+                    } else {
+                        val = ppsum;
+                    }
+                    St[(ii * NC + j) * TR_LD + lane] = val;
+                }
+            }
+            __syncwarp();
+            if (lane < 27) {                             // 27 contiguous doubles of problem q's block per store
+                double* jp = jp0 + ch * 27;
+                const double* sp = St + lane * TR_LD;
+#pragma unroll 4
+                for (int q = 0; q < nq; ++q) {
+                    __stcs(jp, sp[q]);                   // streaming: J must not displace the moment records in L2
+                    jp += jstride;
+                }
+            }
         }
     }
 }
@@ -1448,6 +1709,58 @@ median4_kernel(int n_vert, int npow2, int c0, int c1, int c2, int c3, const doub
         med[prob * 4 + blockIdx.y] = (n_vert & 1) ? sv[n_vert / 2] : 0.5 * (sv[n_vert / 2 - 1] + sv[n_vert / 2]);
 }
 
+// The same medians for meshes that do not fit the shared-memory sort (> 16384 vertices): exact radix SELECT of the two
+// middle order statistics straight from global memory -- eight passes of eight bits over order-preserving 64-bit keys,
+// a 256-bin histogram of the elements that match the prefix found so far, integer atomics only (deterministic, and
+// the result is an element of the input, so it equals np.median bit for bit).  grid = (batch, ncomp).
+__device__ __forceinline__ unsigned long long median_key(double x) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+__global__ void __launch_bounds__(1024)
+median_select_kernel(int n_vert, int ncomp_out, int c0, int c1, int c2, int c3, const double* __restrict__ u,
+                     double* __restrict__ med) {
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned int s_rank;
+    const int prob = blockIdx.x;
+    const int comps[4] = {c0, c1, c2, c3};
+    const double* up = u + (long)prob * n_vert * NC + comps[blockIdx.y];
+    double picked[2];
+    for (int which = 0; which < 2; ++which) {
+        if (threadIdx.x == 0) { s_prefix = 0ull; s_rank = (unsigned)(which == 0 ? (n_vert - 1) / 2 : n_vert / 2); }
+        unsigned long long mask = 0ull;
+        for (int pass = 7; pass >= 0; --pass) {
+            for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
+            __syncthreads();
+            const unsigned long long prefix = s_prefix;
+            for (int i = threadIdx.x; i < n_vert; i += blockDim.x) {
+                const unsigned long long k = median_key(up[(long)i * NC]);
+                if ((k & mask) == prefix) atomicAdd(&hist[(unsigned)(k >> (8 * pass)) & 255u], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned int r = s_rank, cum = 0u;
+                int bin = 0;
+                for (; bin < 255; ++bin) {
+                    if (cum + hist[bin] > r) break;
+                    cum += hist[bin];
+                }
+                s_rank = r - cum;
+                s_prefix = prefix | ((unsigned long long)bin << (8 * pass));
+            }
+            mask |= 0xffull << (8 * pass);
+            __syncthreads();
+        }
+        const unsigned long long k = s_prefix;
+        const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+        picked[which] = __longlong_as_double((long long)b);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) med[prob * ncomp_out + blockIdx.y] = (n_vert & 1) ? picked[0] : 0.5 * (picked[0] + picked[1]);
+}
+
 // Sechenov CO2 entry value from the nodal medians (3D:817-838; CO2_conc 3D:70-93).  sech[p][8] =
 // {A = fugacity * K_H * 1000 / c0_CO2, (h_OH + h_CO2) c0_OH / 1000, (h_HCO3 + h_CO2) c0_HCO3 / 1000,
 //  (h_CO32 + h_CO2) c0_CO32 / 1000, (h_cat + h_CO2) c0_cat / 1000, mode, c0_H, -}.
@@ -1578,6 +1891,11 @@ struct Host3D {   // device arrays that only the 3D path needs and common.cuh do
     double *d_tab = nullptr, *d_sech = nullptr, *d_co2 = nullptr, *d_med = nullptr, *d_inc = nullptr;
     int *d_alive = nullptr, *d_steps = nullptr, *d_mstatus = nullptr, *d_conv = nullptr;
     bool march_set = false, sech_mode1 = false;
+    // batch-lane assembly (batches of >= LANES_MIN_BATCH problems): one problem per lane, problem-minor work arrays
+    bool lanes = false;
+    int n_groups = 0;               // ceil(batch / 32)
+    double *d_uT = nullptr, *d_unT = nullptr;   // [n_groups][V][NC][32]
+    int4* d_lane_meta = nullptr;    // [2 * n_blocks] block descriptors in processing order (assemble_bsr_lanes_kernel)
 };
 // owned by the handle (gmpnp_handle::ext3d): no process-wide state, handles are independent
 static Host3D* ext(gmpnp_handle* h) { return static_cast<Host3D*>(h->ext3d); }
@@ -1590,7 +1908,7 @@ void pore3d_free_ext(gmpnp_handle* h) {
                     e->d_dx, e->d_nrm, e->d_dxmax, e->d_umax, e->d_relres, e->d_r0, e->d_r, e->d_active, e->d_status,
                     e->d_iters, e->d_lin_total, e->d_lin_its, e->d_nact, e->d_cp_blk, e->d_chunk_ptr, e->d_chunk_pair,
                     e->d_cpart, e->d_AciT, e->d_cflag, e->d_kind, e->d_tab, e->d_sech, e->d_co2, e->d_med, e->d_inc,
-                    e->d_alive, e->d_steps, e->d_mstatus, e->d_conv};
+                    e->d_alive, e->d_steps, e->d_mstatus, e->d_conv, e->d_uT, e->d_unT, e->d_lane_meta};
     for (void* b : bufs) if (b) cudaFree(b);
     delete e;
 }
@@ -1770,7 +2088,58 @@ int gmpnp_create_3d(gmpnp_handle** out, int device, const double* h_xyz, int n_v
     }
     GMPNP_CUDA_TRY(h, cudaMalloc(&h->d_params, sizeof(double) * GMPNP_NPAR * B));
     GMPNP_CUDA_TRY(h, cudaMalloc(&h->d_dir_val, sizeof(double) * std::max(1, n_dir) * B));
-    GMPNP_CUDA_TRY(h, cudaMalloc(&h->d_mom, sizeof(double) * NMOM * (size_t)n_tet * B));
+    {   // assembly layout: one problem per lane for real batches (GMPNP_ASM_LANES=0/1 forces the choice, for tests)
+        const char* env = getenv("GMPNP_ASM_LANES");
+        e->lanes = env ? (atoi(env) != 0) : (batch >= LANES_MIN_BATCH);
+        e->n_groups = (batch + 31) / 32;
+    }
+    size_t mom_doubles = NMOM * (size_t)n_tet * B;
+    if (e->lanes) {
+        mom_doubles = std::max(mom_doubles, (size_t)NMT * n_tet * e->n_groups * 32);
+        const size_t ut = (size_t)e->n_groups * n_vert * NC * 32;
+        GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_uT, sizeof(double) * ut));
+        GMPNP_CUDA_TRY(h, cudaMalloc(&e->d_unT, sizeof(double) * ut));
+        {   // block descriptors, ordered along a Morton curve of the row vertex (one common scale for the three axes)
+            double lo[3] = {h_xyz[0], h_xyz[1], h_xyz[2]}, ext_max = 0.0;
+            double hi[3] = {h_xyz[0], h_xyz[1], h_xyz[2]};
+            for (int v = 0; v < n_vert; ++v)
+                for (int d = 0; d < 3; ++d) { lo[d] = std::min(lo[d], h_xyz[3 * v + d]); hi[d] = std::max(hi[d], h_xyz[3 * v + d]); }
+            for (int d = 0; d < 3; ++d) ext_max = std::max(ext_max, hi[d] - lo[d]);
+            auto spread = [](unsigned long long x) {       // 21 bits -> every third bit
+                x &= 0x1fffffull;
+                x = (x | x << 32) & 0x1f00000000ffffull; x = (x | x << 16) & 0x1f0000ff0000ffull;
+                x = (x | x << 8) & 0x100f00f00f00f00full; x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+                x = (x | x << 2) & 0x1249249249249249ull;
+                return x;
+            };
+            std::vector<unsigned long long> code(n_vert);
+            for (int v = 0; v < n_vert; ++v) {
+                unsigned long long c = 0;
+                for (int d = 0; d < 3; ++d) {
+                    const double f = ext_max > 0 ? (h_xyz[3 * v + d] - lo[d]) / ext_max : 0.0;
+                    c |= spread((unsigned long long)(f * 2097151.0)) << d;
+                }
+                code[v] = c;
+            }
+            std::vector<int> order(nb);
+            std::iota(order.begin(), order.end(), 0);
+            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return code[blk_row[x]] < code[blk_row[y]]; });
+            std::vector<int4> meta(2 * (size_t)nb);
+            for (int k = 0; k < nb; ++k) {
+                const int b_ = order[k], va = blk_row[b_];
+                int pin = 0;
+                for (int i = 0; i < NC; ++i) pin |= (dir_flag[(size_t)va * NC + i] >= 0) << i;
+                meta[2 * k] = make_int4(b_, va, h->h_col_idx[b_], blk_cnt[b_]);
+                meta[2 * k + 1] = make_int4(blk_cnt[b_ + 1] - blk_cnt[b_], pin, 0, 0);
+            }
+            if ((rc = dev_upload(h, &e->d_lane_meta, meta))) return rc;
+        }
+        GMPNP_CUDA_TRY(h, cudaFuncSetAttribute(tet_moments_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)TL_SMEM));
+        GMPNP_CUDA_TRY(h, cudaFuncSetAttribute(assemble_bsr_lanes_kernel<BL_UNROLL, BL_WARPS>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bl_smem(BL_WARPS)));
+    }
+    GMPNP_CUDA_TRY(h, cudaMalloc(&h->d_mom, sizeof(double) * mom_doubles));
     GMPNP_CUDA_TRY(h, cudaMalloc(&h->d_Fe, sizeof(double) * 36 * (size_t)n_tet * B));
     GMPNP_CUDA_TRY(h, cudaMalloc(&h->d_J, sizeof(double) * 81 * (size_t)nb * B));
     GMPNP_CUDA_TRY(h, cudaMalloc(&h->d_Dinv, sizeof(double) * 81 * (size_t)n_vert * B));
@@ -1810,25 +2179,58 @@ static int launch_assemble(gmpnp_handle* h, const double* d_u, const double* d_u
                            cudaStream_t st) {
     GmpnpRange nvtx_range("gmpnp:assemble_3d");
     const int T = h->n_tet, V = h->n_nodes, B = h->batch;
-    dim3 gA((T + 127) / 128, B);
-    tet_moments_kernel<<<gA, 128, 0, st>>>(T, V, h->d_tets, h->d_geom, h->d_params, d_u, d_un, h->d_mom, h->d_Fe,
-                                           d_J != nullptr, d_F != nullptr);
-    h->launches++;
+    Host3D* e = ext(h);
+    const double* exit_m = e->facet_terms ? e->d_exit_m : nullptr;
+    if (e->lanes) {
+        const int G = e->n_groups;
+        const long n = (long)V * NC;
+        dim3 gT((unsigned)((n + 31) / 32), G);
+        lanes_transpose_kernel<<<gT, 256, 0, st>>>(B, n, d_u, e->d_uT);
+        h->launches++;
+        const double* unT = e->d_uT;                 // without u_n the time term must be off (kappa = 0), as above
+        if (d_F && d_un) {
+            lanes_transpose_kernel<<<gT, 256, 0, st>>>(B, n, d_un, e->d_unT);
+            h->launches++;
+            unT = e->d_unT;
+        }
+        const int per_group = std::max(1, (148 * TET_MIN_BLOCKS + G - 1) / G);  // one wave
+        dim3 gA(std::min((T + TL_WARPS - 1) / TL_WARPS, per_group), G);
+        tet_moments_lanes_kernel<<<gA, TL_WARPS * 32, TL_SMEM, st>>>(B, T, V, h->d_tets, h->d_geom, h->d_params, e->d_uT,
+                                                                    unT, h->d_mom, h->d_Fe, d_J != nullptr,
+                                                                    d_F != nullptr);
+        h->launches++;
+    } else {
+        dim3 gA((T + 127) / 128, B);
+        tet_moments_kernel<<<gA, 128, 0, st>>>(T, V, h->d_tets, h->d_geom, h->d_params, d_u, d_un, h->d_mom, h->d_Fe,
+                                               d_J != nullptr, d_F != nullptr);
+        h->launches++;
+    }
     if (d_F) {
         dim3 gB(((long)V * NC + 255) / 256, B);
         residual_gather_kernel<<<gB, 256, 0, st>>>(V, T, h->n_dir, h->d_node_ptr, h->d_node_src, h->d_dir_flag,
                                                    h->d_dir_val, h->d_Fe, d_u, d_F,
-                                                   ext(h)->facet_terms ? ext(h)->d_wall_w : nullptr, ext(h)->d_exit_m,
-                                                   ext(h)->d_exit_flag, ext(h)->d_bc, h->d_row_ptr, h->d_col_idx);
+                                                   e->facet_terms ? e->d_wall_w : nullptr, e->d_exit_m,
+                                                   e->d_exit_flag, e->d_bc, h->d_row_ptr, h->d_col_idx);
         h->launches++;
     }
-    if (d_J) {
+    if (d_J && e->lanes) {
+        // one launch (one wave of 2 CTAs per SM) per lane group: the whole GPU works on ONE group's moment records at a
+        // time, so the distance between the four rows that re-read a tet's record stays within the L2
+        // measured on a B200 (batch 128, config 3): 4 warps per CTA, 2 CTAs per SM, three contributions in flight per warp;
+        // more warps (6 or 8 per CTA) or more CTAs are slower (3.2-3.6 vs 2.9 ms), see DESIGN 3.3
+        const int gx = std::min((h->n_blocks + BL_WARPS - 1) / BL_WARPS, 148 * 2);
+        for (int g = 0; g < e->n_groups; ++g) {
+            assemble_bsr_lanes_kernel<BL_UNROLL, BL_WARPS><<<gx, BL_WARPS * 32, bl_smem(BL_WARPS), st>>>(
+                g, B, h->n_blocks, V, T, e->d_lane_meta, h->d_blk_src, e->d_blk_geo, h->d_params, e->d_uT, h->d_mom, d_J,
+                exit_m, e->d_bc);
+            h->launches++;
+        }
+    } else if (d_J) {
         int gx = std::min((h->n_blocks + ASM_WARPS - 1) / ASM_WARPS, 148 * 16);
         dim3 gC(gx, B);
         assemble_bsr_kernel<<<gC, ASM_WARPS * 32, 0, st>>>(h->n_blocks, V, T, h->d_blk_ptr, h->d_blk_src,
-                                                           ext(h)->d_blk_geo, ext(h)->d_blk_row, h->d_col_idx,
-                                                           h->d_dir_flag, h->d_params, d_u, h->d_mom, d_J,
-                                                           ext(h)->facet_terms ? ext(h)->d_exit_m : nullptr, ext(h)->d_bc);
+                                                           e->d_blk_geo, e->d_blk_row, h->d_col_idx,
+                                                           h->d_dir_flag, h->d_params, d_u, h->d_mom, d_J, exit_m, e->d_bc);
         h->launches++;
     }
     GMPNP_CUDA_TRY(h, cudaGetLastError());
@@ -2098,10 +2500,14 @@ static int march_step(gmpnp_handle* h, double* d_u, double* d_un, const gmpnp_ne
                                                         e->d_steps, e->d_co2, d_co2_out, e->d_nact);
     int np2 = 1;
     while (np2 < V) np2 <<= 1;
-    cudaFuncSetAttribute(median4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(np2 * sizeof(double)));
     dim3 gm(B, 4);
-    if (e->sech_mode1) median4_kernel<<<gm, 1024, np2 * sizeof(double), st>>>(V, np2, 0, 1, 2, 3, d_u, e->d_med);
-    else median4_kernel<<<gm, 1024, np2 * sizeof(double), st>>>(V, np2, 1, 2, 3, 7, d_u, e->d_med);
+    const int mc0 = e->sech_mode1 ? 0 : 1, mc1 = e->sech_mode1 ? 1 : 2, mc2 = e->sech_mode1 ? 2 : 3, mc3 = e->sech_mode1 ? 3 : 7;
+    if ((size_t)np2 * sizeof(double) > MEDIAN_SORT_BYTES) {
+        median_select_kernel<<<gm, 1024, 0, st>>>(V, 4, mc0, mc1, mc2, mc3, d_u, e->d_med);
+    } else {
+        cudaFuncSetAttribute(median4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(np2 * sizeof(double)));
+        median4_kernel<<<gm, 1024, np2 * sizeof(double), st>>>(V, np2, mc0, mc1, mc2, mc3, d_u, e->d_med);
+    }
     sechenov_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, e->d_alive, e->d_med, e->d_sech, e->d_co2);
     march_advance_kernel<<<B, 1024, 0, st>>>(n, e->d_alive, d_u, d_un, d_hist_row, hist_stride, e->d_inc);
     h->launches += 4;
@@ -2122,12 +2528,6 @@ static int march_begin(gmpnp_handle* h, cudaStream_t st) {
     Host3D* e = ext(h);
     const int B = h->batch;
     if (!e->march_set) return GMPNP_ERR_STATE;
-    int np2 = 1;
-    while (np2 < h->n_nodes) np2 <<= 1;
-    if ((size_t)np2 * sizeof(double) > 200 * 1024) {
-        h->last_cuda_error = "the Sechenov median (shared-memory sort) supports meshes of at most 16384 vertices";
-        return GMPNP_ERR_ARG;
-    }
     std::vector<int> ones(B, 1), zeros(B, 0);
     std::vector<double> co2(B);
     std::vector<double> tab(4 * (size_t)B);
@@ -2386,10 +2786,14 @@ int gmpnp_median_3d(gmpnp_handle* h, const double* d_u, int comp, double* d_med,
     if (!h || h->dim != 3 || !d_u || !d_med || comp < 0 || comp >= NC) return GMPNP_ERR_ARG;
     int np2 = 1;
     while (np2 < h->n_nodes) np2 <<= 1;
-    if ((size_t)np2 * sizeof(double) > 200 * 1024) return GMPNP_ERR_ARG;      // shared-memory sort only
     GMPNP_CUDA_TRY(h, cudaSetDevice(h->device));
-    cudaFuncSetAttribute(median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(np2 * sizeof(double)));
-    median_kernel<<<h->batch, 1024, np2 * sizeof(double), (cudaStream_t)stream>>>(h->n_nodes, np2, comp, d_u, d_med);
+    if ((size_t)np2 * sizeof(double) > MEDIAN_SORT_BYTES) {               // beyond the shared-memory sort: radix select
+        median_select_kernel<<<dim3(h->batch, 1), 1024, 0, (cudaStream_t)stream>>>(h->n_nodes, 1, comp, comp, comp, comp,
+                                                                                 d_u, d_med);
+    } else {
+        cudaFuncSetAttribute(median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(np2 * sizeof(double)));
+        median_kernel<<<h->batch, 1024, np2 * sizeof(double), (cudaStream_t)stream>>>(h->n_nodes, np2, comp, d_u, d_med);
+    }
     h->launches++;
     GMPNP_CUDA_TRY(h, cudaGetLastError());
     return GMPNP_OK;

@@ -497,3 +497,115 @@ def test_run_to_run_bitwise_reproducibility_3d(lib):
     assert torch.equal(outs[0][0][0], outs[0][0][1]) and torch.equal(outs[0][0][0], outs[0][0][2])
     assert int(outs[0][1][0]) > 0
     s.close()
+
+
+# ---- batch-lane assembly (one problem per lane; chosen automatically for batches >= 24) -------------------------------
+
+@pytest.fixture
+def asm_lanes(monkeypatch):
+    monkeypatch.setenv("GMPNP_ASM_LANES", "1")
+
+
+def test_batch_lane_assembly_matches_oracle(lib, asm_lanes):
+    """The problem-per-lane assembly kernels against the oracle: F and every BSR entry, two different parameter sets
+    (so lanes really carry different problems; 30 idle lanes), Dirichlet rows, time term."""
+    test_assemble_3d_vs_oracle_random_params(lib)
+    test_cuda_assembly_matches_the_exact_integral_restatement(lib)
+    test_assemble_3d_matches_golden_entrywise(lib)
+
+
+def test_batch_lane_assembly_intended_boundary_terms(lib, asm_lanes):
+    test_intended_boundary_integrals_match_oracle(lib)
+
+
+def test_batch_lane_assembly_equals_block_kernels_on_a_ragged_batch(lib, monkeypatch):
+    """35 different problems (two lane groups, the second with 3 live lanes) on L_10_R_5 with the intended boundary
+    terms and the time term: the lane kernels and the warp-per-(problem, block) kernels agree to round-off in every
+    entry; identical problems at batch positions 0, 17 and 34 give bitwise identical rows (position independence)."""
+    from gmpnp_b200 import meshio, params, solver3d
+    mesh = meshio.load_mesh("L_10_R_5")
+    Vs = np.linspace(-0.25, -2.0, 35)
+    Vs[17] = Vs[34] = Vs[0]
+    plist = [params.params_3d(L=10e-9, R=5e-9, voltage_multiplier=float(v), concentration_elec=(0.5 if k % 2 else 1.0))
+             for k, v in enumerate(Vs)]
+    plist[17] = plist[34] = plist[0]
+    rng = np.random.default_rng(11)
+    n = mesh.num_vertices
+    u1 = admissible_state(rng, n, 8, plist[0].nu, V=-2.0)
+    un1 = admissible_state(rng, n, 8, plist[0].nu, V=-2.0)
+    us = np.stack([u1 * (1.0 + 0.002 * k) for k in range(35)]); uns = np.stack([un1] * 35)
+    us[17] = us[34] = us[0]
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("GMPNP_ASM_LANES", mode)
+        pp = solver3d.PoreProblem(mesh, 10e-9, 5e-9, plist, intended_bcs=True)
+        s = pp.solver
+        s.set_dirichlet(pp.dirichlet_values([float(p.extras["eq_scaled"][0]) for p in plist]))
+        F, J = s.assemble(_t(us), _t(uns))
+        F2, _ = s.assemble(_t(us), _t(uns), want_J=False)
+        torch.cuda.synchronize()
+        assert torch.equal(F, F2)
+        res[mode] = (F.cpu().numpy(), J.cpu().numpy())
+        s.close()
+    (F0, J0), (F1, J1) = res["0"], res["1"]
+    assert np.isfinite(F1).all() and np.isfinite(J1).all()
+    assert np.abs(F1 - F0).max() <= 1e-13 * np.abs(F0).max()
+    rowmax = np.abs(J0).max(axis=(1, 3), keepdims=True)            # per problem and block-row component
+    assert (np.abs(J1 - J0) <= 1e-12 * np.maximum(rowmax, 1e-300)).all()
+    for k in (17, 34):
+        assert np.array_equal(J1[k], J1[0]) and np.array_equal(F1[k], F1[0])
+
+
+def test_batch_lane_newton_matches_block_kernels(lib, monkeypatch):
+    """One reference time step (damped Newton + cluster GMRES) of three L_10_R_5 problems with either assembly: same
+    Newton counts, iterates equal to 1e-10."""
+    from gmpnp_b200 import meshio, params, solver3d
+    mesh = meshio.load_mesh("L_10_R_5")
+    plist = [params.params_3d(L=10e-9, R=5e-9, voltage_multiplier=v) for v in (-0.5, -0.75, -1.0)]
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("GMPNP_ASM_LANES", mode)
+        pp = solver3d.PoreProblem(mesh, 10e-9, 5e-9, plist)
+        o = pp.march(1, history=True)
+        outs[mode] = (o["iters"].copy(), o["history"][1].copy())
+        pp.solver.close()
+    assert np.array_equal(outs["0"][0], outs["1"][0])
+    for b in range(3):
+        for c in range(9):
+            assert rel_l2(outs["1"][1][b][:, c], outs["0"][1][b][:, c]) < 1e-10, (b, c)
+
+
+def test_median_beyond_the_shared_memory_sort(lib):
+    """Meshes with more than 16384 vertices (the config-5 sizes): exact radix select, bit-equal to np.median for odd and
+    even vertex counts, signed values, many ties; and the library march (Sechenov feedback every step) accepts such a mesh."""
+    from gmpnp_b200 import meshio, params, solver3d
+    mesh = meshio.load_mesh("L_10_R_5")
+    for _ in range(2):
+        mesh = meshio.red_refine(mesh, project_radius=0.5)
+    assert mesh.num_vertices > 16384
+    prm = params.params_3d(L=10e-9, R=5e-9, voltage_multiplier=-0.25)
+    pp = solver3d.PoreProblem(mesh, 10e-9, 5e-9, [prm, prm])
+    s = pp.solver
+    g = torch.Generator(device=_dev()).manual_seed(7)
+    u = torch.randn(2, s.n, 9, dtype=torch.float64, device=_dev(), generator=g)
+    u[:, :, 2] = torch.round(u[:, :, 2] * 4.0) / 4.0                          # heavy ties, both signs, +-0
+    u[1, : s.n // 2, 5] = 0.0
+    for comp in (1, 2, 5, 7):
+        med = s.median(u, comp).cpu().numpy()
+        assert np.array_equal(med, np.median(u[:, :, comp].cpu().numpy(), axis=1)), comp
+    for drop in (1,):                                                         # the other parity of the vertex count
+        v = u[:, : s.n - drop].contiguous()
+        s2 = solver3d.Solver3D(meshio.Mesh(x=mesh.x[: s.n - drop], cells=mesh.cells[(mesh.cells < s.n - drop).all(axis=1)]),
+                               np.array([8], dtype=np.int32), batch=2)
+        assert np.array_equal(s2.median(v, 1).cpu().numpy(), np.median(v[:, :, 1].cpu().numpy(), axis=1))
+        s2.close()
+    # the library march (Sechenov medians every step) used to refuse such a mesh; one capped Newton iteration is enough
+    from gmpnp_b200._lib import NewtonOpts
+    o = NewtonOpts.sweep_3d()
+    o.maxit, o.lin_maxit = 1, 40
+    s.set_dirichlet(pp.dirichlet_values([float(prm.extras["eq_scaled"][0])] * 2))
+    s.set_march_data(*pp.march_data())
+    out = s.march(torch.zeros(2, s.n, 9, dtype=torch.float64, device=_dev()), solver3d.bulk_state(2, s.n, _dev()), 1, o)
+    co2 = out["co2_entry"].cpu().numpy()
+    assert np.isfinite(co2).all() and (co2 > 0).all()
+    s.close()
