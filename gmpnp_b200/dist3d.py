@@ -61,6 +61,10 @@ class LocalComm:
             out += t
         return out
 
+    def gather_values(self, vs):
+        """vs[k]: 1-D tensor of part k's OWNED values -> all values of the mesh (any order), on every part."""
+        return torch.cat([v.reshape(-1) for v in vs])
+
 
 class TorchComm:
     """One part per process: halo exchange = batched isend/irecv, reductions = all_reduce
@@ -110,6 +114,22 @@ class TorchComm:
         if self.world > 1:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
         return t
+
+    def gather_values(self, vs):
+        """All-gather of the ranks' owned values (ragged: sizes first, then padded buffers)."""
+        v = vs[0].reshape(-1).contiguous()
+        if self.world == 1:
+            return v
+        dist = self.dist
+        n = torch.tensor([v.numel()], dtype=torch.int64, device=v.device)
+        sizes = [torch.zeros_like(n) for _ in range(self.world)]
+        dist.all_gather(sizes, n, group=self.group)
+        sizes = [int(t.item()) for t in sizes]
+        buf = torch.zeros(max(sizes), dtype=v.dtype, device=v.device)
+        buf[: v.numel()] = v
+        outs = [torch.empty_like(buf) for _ in range(self.world)]
+        dist.all_gather(outs, buf, group=self.group)
+        return torch.cat([o[:k] for o, k in zip(outs, sizes)])
 
 
 # ------------------------------------------------------------------------------------------------
@@ -372,6 +392,46 @@ class PartitionedPore:
             if not math.isfinite(r):
                 break
         return dict(iters=k, r0=r0, r=r, lin_iters=lin, converged=bool(conv))
+
+    # -- the reference's loop 3D:782-858 on the partitioned mesh -----------------------------------------
+    def median(self, us, comp: int) -> float:
+        """np.median of component ``comp`` over ALL vertices of the mesh (3D:817-820): the owned values of every part are
+        gathered on every rank (V doubles), sorted on the device, and the middle value (odd V) or the mean of the two
+        middle values (even V) is returned -- an order statistic, so it is exact and identical on every rank."""
+        vals = self.comm.gather_values([u[0, : p.n_own, comp] for u, p in zip(us, self.parts)])
+        srt, _ = torch.sort(vals)
+        n = srt.numel()
+        assert n == self.mesh.x.shape[0], (n, self.mesh.x.shape[0])
+        mid = srt[n // 2] if n % 2 else 0.5 * (srt[n // 2 - 1] + srt[n // 2])
+        return float(mid)
+
+    def march(self, n_steps: int, us=None, uns=None, callback=None, **newton_kw):
+        """``for n in range(tot_num_steps)`` of 3D/MPNP_CO2ER_pore.py:782-858 for ONE problem on the partitioned mesh:
+        u = 0, u_n = (1, .., 1, 0); per step the CO2 entry Dirichlet value (bc4 rebuild, 3D:835-838), one damped Newton
+        solve (3D:789-799), the Sechenov update from the nodal medians of OH-, HCO3-, CO3-- and the cation
+        (3D:817-833), u_n <- u (3D:856).  Like dolfin, a Newton solve that does not converge raises."""
+        if us is None:
+            us = self.zeros()
+        if uns is None:
+            uns = self.zeros()
+            for x in uns:
+                x[:, :, : NC - 1] = 1.0
+        co2 = float(self.prm.extras["eq_scaled"][0])
+        iters, lin_iters, co2_hist = [], [], []
+        for step in range(n_steps):
+            self.set_dirichlet(co2)
+            out = self.newton(us, uns, **newton_kw)
+            if not out["converged"]:
+                raise RuntimeError(f"Newton solver did not converge at step {step}: r = {out['r']:.3e} after {out['iters']} iterations")
+            iters.append(out["iters"]); lin_iters.append(out["lin_iters"]); co2_hist.append(co2)
+            self.comm.halo([u[0] for u in us])                       # ghosts of the accepted state (u_n must be complete)
+            med = [self.median(us, c) for c in (1, 2, 3, 7)]
+            co2 = float(_params.sechenov_co2_scaled(self.prm, *med))
+            for x, xn in zip(us, uns):
+                xn.copy_(x)
+            if callback is not None:
+                callback(step, us, out)
+        return dict(us=us, uns=uns, iters=iters, lin_iters=lin_iters, co2_entry=co2_hist, co2_next=co2)
 
     def close(self):
         for s in self.solvers:

@@ -79,7 +79,12 @@ def _worker(rank, world, port, q):
     ok_halo = bool(np.array_equal(xl.numpy(), xg[part.glob]))
     local = torch.tensor([float((xg[part.glob[: part.n_own]] ** 2).sum()), float(part.n_own)], dtype=torch.float64)
     tot = comm.allreduce_sum([local])
-    q.put((rank, ok_halo, tot.tolist(), float((xg ** 2).sum()), m.x.shape[0], comm.halo_bytes, part.halo_doubles() * 8))
+    # ragged all-gather behind the distributed median (PartitionedPore.median): every rank ends up with all owned values
+    vals = comm.gather_values([torch.as_tensor(xg[part.glob[: part.n_own], 3])])
+    srt = torch.sort(vals)[0].numpy()
+    ok_gather = bool(vals.numel() == m.x.shape[0] and np.array_equal(srt, np.sort(xg[:, 3])))
+    q.put((rank, ok_halo and ok_gather, tot.tolist(), float((xg ** 2).sum()), m.x.shape[0], comm.halo_bytes,
+           part.halo_doubles() * 8))
     dist.barrier()
     dist.destroy_process_group()
 
