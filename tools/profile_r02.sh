@@ -19,3 +19,8 @@ ncu --set full --clock-control none --import-source on -k regex:gmres_cluster -s
     python tools/prof_3d.py --batch 128 --steps 1 > gpurun_out/r02_ncu_gmres.log 2>&1
 echo "ncu 3d rc=$?"; cat gpurun_out/r02_prof3d.log
 ls -la gpurun_out/*.ncu-rep
+# batch-lane 3D assembly: the eight launches of one J+F assembly at batch 128 (profiles/r02_asm_lanes_ncu_summary.md)
+python tools/prof_3d.py --batch 128 --steps 0 > gpurun_out/r02_prof3d_asm.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:"lanes|residual_gather" -s 8 -c 8 -f -o gpurun_out/r02_asm_lanes_final \
+    python tools/prof_3d.py --batch 128 --steps 0 > gpurun_out/r02_ncu_asm.log 2>&1
+echo "ncu asm rc=$?"; cat gpurun_out/r02_prof3d_asm.log
