@@ -339,10 +339,20 @@ def bench_pore3d(local, world, dev, batch, peak):
                          gpu_launches=int(s.launch_count() - l1))
 
     out, main_run = steady_run(NewtonOpts.sweep_3d())
+
+    def distance(o, run):
+        d = (o["u"] - out["u"]).abs().amax(dim=(1, 2)) / out["u"].abs().amax(dim=(1, 2))
+        l2 = (o["u"] - out["u"]).pow(2).sum(dim=1).sqrt() / out["u"].pow(2).sum(dim=1).sqrt().clamp_min(1e-300)
+        run["max_rel_distance_to_the_1e-8_iterate"] = float(d.max())
+        run["worst_rel_l2_per_field_to_the_1e-8_iterate"] = float(l2.max())         # the parity norm (north_star: 1e-8)
+
     out2, fast_run = steady_run(NewtonOpts.sweep_3d_inexact())
-    d = (out2["u"] - out["u"]).abs().amax(dim=(1, 2)) / out["u"].abs().amax(dim=(1, 2))
-    fast_run["max_rel_distance_to_the_1e-8_iterate"] = float(d.max())
+    distance(out2, fast_run)
     fast_run["setting"] = "NewtonOpts.sweep_3d_inexact: GMRES(40) to eta = 1e-4 (constant forcing term)"
+    out3, mid_run = steady_run(NewtonOpts.sweep_3d_inexact(1e-6))
+    distance(out3, mid_run)
+    mid_run["setting"] = "NewtonOpts.sweep_3d_inexact(1e-6): the loosest forcing term that stays within the parity tolerance"
+    del out2, out3
     res = {
         "workload": f"config3 batch: L_50_R_5 (V=3679, T=17297, 33111 DOFs), {batch} wall voltages in [-0.5,-1.25] V_T per GPU, "
                     "pseudo-time march to steady state (increment <= 1e-8 per problem) inside the library "
@@ -350,6 +360,7 @@ def bench_pore3d(local, world, dev, batch, peak):
                     "0.9, residual criterion 1e-4 as 3D:789-798), GMRES(40) to 1e-8 + block-Jacobi + z-slab coarse space",
         **main_run,
         "inexact": fast_run,
+        "inexact_1e-6": mid_run,
         "assemble": {"ms": ms_asm, "GBs": b_asm / ms_asm / 1e6, "frac_of_hbm_peak": b_asm / ms_asm / 1e6 / peak,
                      "algorithmic_bytes": b_asm,
                      "dram_traffic_over_algorithmic_ncu": traffic.get("assemble3d_dram_bytes_over_algorithmic_bytes"),
