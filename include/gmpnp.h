@@ -181,7 +181,9 @@ int gmpnp_set_dirichlet_3d(gmpnp_handle* h, const double* h_vals, int batch);
 int gmpnp_pattern_3d(const gmpnp_handle* h, int* n_blocks, int* h_row_ptr, int* h_col_idx);
 
 /* Residual d_F[batch][n_vert][9] and BSR values d_J[batch][n_blocks][9][9] at (u, u_n),
- * Dirichlet rows applied.  Either output may be NULL.                                     */
+ * Dirichlet rows applied.  Either output may be NULL.  Handles created with batch >= 24 use
+ * the problem-per-lane kernels (same results to round-off, same buffers); the
+ * environment variable GMPNP_ASM_LANES=0|1, read by gmpnp_create_3d, forces either layout. */
 int gmpnp_assemble_3d(gmpnp_handle* h, const double* d_u, const double* d_un,
                       double* d_F, double* d_J, void* stream);
 
