@@ -174,7 +174,7 @@ def test_config3_reference_march_six_steps(lib, setting):
           max(rel_l2(out["history"][step][0][:, c], g[f"step{step}"][:, c]) for step in (1, 2, 4, 6) for c in range(9)))
     assert np.abs(out["iters"][:, 0] - g["its"]).max() <= 1, (out["iters"][:, 0], g["its"])
     assert np.allclose(out["co2_entry"][:, 0], g["co2"], rtol=1e-8)
-    tol = PARITY_3D if setting == "reference_3d" else 1e-6        # transient states feel the linear-solve accuracy
+    tol = PARITY_3D if setting == "reference_3d" else 5e-8        # transient states feel the linear-solve accuracy (measured 1.2e-8)
     for step in (1, 2, 4, 6):
         for c in range(9):
             assert rel_l2(out["history"][step][0][:, c], g[f"step{step}"][:, c]) < tol, (step, c)
